@@ -1,0 +1,8 @@
+"""vectorx_b200: B200-native (sm_100a) proving hot path behind VectorX's plonky2x proofs.
+
+Public surface mirrors plonky2 v0.2.0 (`PolynomialBatch`, `MerkleTree`); everything computes in
+libvectorx_b200.so through the C ABI of include/vectorx_b200.h.  No CPU fallback.
+"""
+from ._lib import Context, VxError, default_context, load, LIB_PATH  # noqa: F401
+from .plonky2 import (MerkleCap, MerkleProof, MerkleTree, PolynomialBatch, hash_n_to_hash_no_pad,  # noqa: F401
+                      merkle_tree_digests, ntt, poseidon, poseidon_round_constants, reverse_bits)

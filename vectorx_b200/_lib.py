@@ -1,0 +1,137 @@
+"""ctypes binding of libvectorx_b200.so (the C ABI in include/vectorx_b200.h).
+
+There is deliberately no fallback: if the shared library is missing or no B200-class GPU is visible
+every entry point raises.  Nothing here imports the test oracle.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvectorx_b200.so")
+
+u64p = ctypes.POINTER(ctypes.c_uint64)
+u32p = ctypes.POINTER(ctypes.c_uint32)
+vp = ctypes.c_void_p
+c_u64, c_u32, c_i32 = ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int32
+
+# name -> (restype, argtypes); must list every symbol declared in include/vectorx_b200.h
+SIGNATURES = {
+    "vx_ctx_create": (c_i32, [c_i32, ctypes.POINTER(vp)]),
+    "vx_ctx_destroy": (None, [vp]),
+    "vx_last_error": (ctypes.c_char_p, []),
+    "vx_device_sync": (c_i32, [vp]),
+    "vx_ctx_stream": (vp, [vp]),
+    "vx_ctx_launch_count": (c_u64, [vp]),
+    "vx_commit_from_values": (c_i32, [vp, vp, c_u32, c_u32, c_u32, c_u32, ctypes.POINTER(vp)]),
+    "vx_commit_from_coeffs": (c_i32, [vp, vp, c_u32, c_u32, c_u32, c_u32, ctypes.POINTER(vp)]),
+    "vx_batch_free": (None, [vp]),
+    "vx_batch_shape": (c_i32, [vp, u32p]),
+    "vx_batch_cap": (c_i32, [vp, vp]),
+    "vx_batch_coeffs": (c_i32, [vp, vp]),
+    "vx_batch_leaves": (c_i32, [vp, vp, c_u32, vp]),
+    "vx_batch_merkle_paths": (c_i32, [vp, vp, c_u32, vp]),
+    "vx_batch_download": (c_i32, [vp, vp, vp]),
+    "vx_batch_lde_device": (vp, [vp]),
+    "vx_batch_coeffs_device": (vp, [vp]),
+    "vx_batch_digests_device": (vp, [vp]),
+    "vx_merkle_new": (c_i32, [vp, vp, c_u64, c_u32, c_u32, vp, vp, ctypes.POINTER(vp)]),
+    "vx_tree_prove": (c_i32, [vp, vp, c_u32, vp]),
+    "vx_tree_leaves": (c_i32, [vp, vp, c_u32, vp]),
+    "vx_tree_cap": (c_i32, [vp, vp]),
+    "vx_tree_free": (None, [vp]),
+    "vx_poseidon_permute": (c_i32, [vp, vp, c_u64, vp]),
+    "vx_hash_no_pad": (c_i32, [vp, vp, c_u64, c_u32, vp]),
+    "vx_poseidon_constants": (c_i32, [vp]),
+    "vx_ntt": (c_i32, [vp, vp, vp, c_u32, c_u32, c_i32, c_u64]),
+}
+
+_lib = None
+
+
+class VxError(RuntimeError):
+    pass
+
+
+def load() -> ctypes.CDLL:
+    """Load the shared library (no GPU needed for loading; compute calls need one)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise VxError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no CPU fallback)")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().vx_last_error().decode("utf-8", "replace")
+        raise VxError(f"{what} failed with code {rc}: {msg}")
+
+
+def ptr(a) -> int:
+    """Address of a numpy array (host) / torch tensor (host or device) / raw int pointer / None."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return a
+    if isinstance(a, np.ndarray):
+        assert a.dtype == np.uint64 and a.flags["C_CONTIGUOUS"], "need C-contiguous uint64"
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):      # torch tensor of dtype int64/uint64
+        assert a.is_contiguous() and a.element_size() == 8
+        return a.data_ptr()
+    raise TypeError(type(a))
+
+
+class Context:
+    """One per process and device: owns the stream, twiddle tables and Poseidon constants."""
+
+    def __init__(self, device: int = 0):
+        self._h = vp()
+        check(load().vx_ctx_create(device, ctypes.byref(self._h)), "vx_ctx_create")
+        self.device = device
+
+    @property
+    def handle(self):
+        return self._h
+
+    def sync(self):
+        check(load().vx_device_sync(self._h), "vx_device_sync")
+
+    @property
+    def stream(self) -> int:
+        return load().vx_ctx_stream(self._h) or 0
+
+    @property
+    def launch_count(self) -> int:
+        return load().vx_ctx_launch_count(self._h)
+
+    def close(self):
+        if self._h:
+            load().vx_ctx_destroy(self._h)
+            self._h = vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default_ctx = {}
+
+
+def default_context(device: int = 0) -> Context:
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]

@@ -1,0 +1,388 @@
+// C ABI of libvectorx_b200 (see include/vectorx_b200.h for what each entry point replaces).
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+
+void vx_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* vx_last_error(void) { return g_err; }
+
+bool vx_is_device_ptr(const void* p) {
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+int32_t DevBuf::alloc(size_t nbytes, cudaStream_t stream) {
+    release();
+    s = stream;
+    bytes = nbytes;
+    if (nbytes == 0) return VX_OK;
+    cudaError_t e = cudaMallocAsync((void**)&p, nbytes, stream);
+    if (e != cudaSuccess) {
+        p = nullptr;
+        vx_set_error("device allocation of %zu bytes failed: %s", nbytes, cudaGetErrorString(e));
+        cudaGetLastError();
+        return VX_ENOMEM;
+    }
+    return VX_OK;
+}
+void DevBuf::release() {
+    if (p) cudaFreeAsync(p, s);
+    p = nullptr;
+}
+
+// ------------------------------------------------------------------------------------------------ context
+extern "C" int32_t vx_ctx_create(int32_t device, vx_ctx** out) {
+    if (!out) { vx_set_error("vx_ctx_create: out is NULL"); return VX_EINVAL; }
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        vx_set_error("vx_ctx_create: no CUDA device visible (there is no CPU fallback)");
+        return VX_ENODEV;
+    }
+    VX_REQUIRE(device >= 0 && device < ndev, "vx_ctx_create: device %d out of range (0..%d)", device, ndev - 1);
+    cudaDeviceProp prop;
+    VX_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        vx_set_error("vx_ctx_create: device %d is sm_%d%d; this library is built for sm_100a only", device,
+                     prop.major, prop.minor);
+        return VX_ENODEV;
+    }
+    VX_CUDA(cudaSetDevice(device));
+    vx_ctx* ctx = new (std::nothrow) vx_ctx();
+    if (!ctx) return VX_ENOMEM;
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete ctx; vx_set_error("stream create: %s", cudaGetErrorString(e)); return VX_ECUDA; }
+    // keep freed blocks in the stream-ordered pool: commits allocate GBs per call
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thresh = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh);
+    }
+    int32_t r = poseidon_module_init(ctx);
+    if (r == VX_OK) r = ntt_module_init(ctx);
+    if (r != VX_OK) { vx_ctx_destroy(ctx); return r; }
+    *out = ctx;
+    return VX_OK;
+}
+
+extern "C" void vx_ctx_destroy(vx_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    ntt_module_destroy(ctx);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" int32_t vx_device_sync(vx_ctx* ctx) {
+    VX_REQUIRE(ctx, "vx_device_sync: ctx is NULL");
+    VX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VX_OK;
+}
+extern "C" void* vx_ctx_stream(vx_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+extern "C" uint64_t vx_ctx_launch_count(vx_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
+
+struct CtxGuard {       // one call at a time per context; binds the device to the calling thread
+    std::lock_guard<std::mutex> lk;
+    explicit CtxGuard(vx_ctx* c) : lk(c->mu) { cudaSetDevice(c->device); }
+};
+
+// copy helpers that accept host or device memory on either side
+static int32_t copy_in(vx_ctx* ctx, u64* dst_dev, const u64* src, size_t bytes) {
+    VX_CUDA(cudaMemcpyAsync(dst_dev, src, bytes, cudaMemcpyDefault, ctx->stream));
+    return VX_OK;
+}
+static int32_t copy_out(vx_ctx* ctx, u64* dst, const u64* src_dev, size_t bytes) {
+    VX_CUDA(cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDefault, ctx->stream));
+    return VX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ PolynomialBatch
+struct vx_batch {
+    vx_ctx* ctx;
+    uint32_t c, log_n, rate_bits, cap_height;
+    DevBuf coeffs;    // c x n
+    DevBuf lde;       // c x N column-major, leaf order
+    DevBuf digests;   // 2 (N - 2^cap) x 4
+    DevBuf cap;       // 2^cap x 4
+    uint64_t n() const { return 1ULL << log_n; }
+    uint64_t N() const { return 1ULL << (log_n + rate_bits); }
+};
+
+static int32_t commit_impl(vx_ctx* ctx, const u64* src, bool is_values, uint32_t c, uint32_t log_n,
+                           uint32_t rate_bits, uint32_t cap_height, vx_batch** out) {
+    VX_REQUIRE(ctx && src && out, "commit: NULL argument");
+    *out = nullptr;
+    VX_REQUIRE(c >= 1 && c < 16384, "commit: column count %u out of range", c);
+    VX_REQUIRE(log_n + rate_bits <= 26, "commit: 2^%u LDE points unsupported", log_n + rate_bits);
+    VX_REQUIRE(cap_height <= log_n + rate_bits, "commit: cap_height %u exceeds tree height %u", cap_height,
+               log_n + rate_bits);
+    CtxGuard g(ctx);
+    vx_batch* b = new (std::nothrow) vx_batch();
+    if (!b) return VX_ENOMEM;
+    b->ctx = ctx; b->c = c; b->log_n = log_n; b->rate_bits = rate_bits; b->cap_height = cap_height;
+    const uint64_t n = b->n(), N = b->N();
+    const size_t coeff_bytes = (size_t)c * n * sizeof(u64);
+    int32_t r = b->coeffs.alloc(coeff_bytes, ctx->stream);
+    if (r == VX_OK) r = b->lde.alloc((size_t)c * N * sizeof(u64), ctx->stream);
+    if (r == VX_OK) r = b->digests.alloc((size_t)2 * (N - (1ULL << cap_height)) * 4 * sizeof(u64), ctx->stream);
+    if (r == VX_OK) r = b->cap.alloc((size_t)(1ULL << cap_height) * 4 * sizeof(u64), ctx->stream);
+    if (r == VX_OK) {
+        if (is_values) {
+            // stage the values in the (not yet used) LDE buffer, transform there, emit coefficients
+            r = copy_in(ctx, b->lde.p, src, coeff_bytes);
+            if (r == VX_OK) r = intt_batch(ctx, b->lde.p, b->coeffs.p, c, log_n);
+        } else {
+            r = copy_in(ctx, b->coeffs.p, src, coeff_bytes);
+        }
+    }
+    if (r == VX_OK) r = lde_batch(ctx, b->coeffs.p, b->lde.p, c, log_n, rate_bits);
+    if (r == VX_OK) r = merkle_build_device(ctx, b->lde.p, true, N, N, c, cap_height, b->digests.p, b->cap.p);
+    if (r == VX_OK) {
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { vx_set_error("commit: %s", cudaGetErrorString(e)); r = VX_ECUDA; }
+    }
+    if (r != VX_OK) { delete b; return r; }
+    *out = b;
+    return VX_OK;
+}
+
+extern "C" int32_t vx_commit_from_values(vx_ctx* ctx, const uint64_t* cols, uint32_t c, uint32_t log_n,
+                                         uint32_t rate_bits, uint32_t cap_height, vx_batch** out) {
+    return commit_impl(ctx, (const u64*)cols, true, c, log_n, rate_bits, cap_height, out);
+}
+extern "C" int32_t vx_commit_from_coeffs(vx_ctx* ctx, const uint64_t* coeffs, uint32_t c, uint32_t log_n,
+                                         uint32_t rate_bits, uint32_t cap_height, vx_batch** out) {
+    return commit_impl(ctx, (const u64*)coeffs, false, c, log_n, rate_bits, cap_height, out);
+}
+
+extern "C" void vx_batch_free(vx_batch* b) {
+    if (!b) return;
+    {
+        CtxGuard g(b->ctx);
+        b->coeffs.release(); b->lde.release(); b->digests.release(); b->cap.release();
+    }
+    delete b;
+}
+
+extern "C" int32_t vx_batch_shape(const vx_batch* b, uint32_t out[4]) {
+    VX_REQUIRE(b && out, "vx_batch_shape: NULL argument");
+    out[0] = b->c; out[1] = b->log_n; out[2] = b->rate_bits; out[3] = b->cap_height;
+    return VX_OK;
+}
+
+extern "C" int32_t vx_batch_cap(vx_batch* b, uint64_t* cap_out) {
+    VX_REQUIRE(b && cap_out, "vx_batch_cap: NULL argument");
+    CtxGuard g(b->ctx);
+    VX_CHECK(copy_out(b->ctx, (u64*)cap_out, b->cap.p, b->cap.bytes));
+    VX_CUDA(cudaStreamSynchronize(b->ctx->stream));
+    return VX_OK;
+}
+
+extern "C" int32_t vx_batch_coeffs(vx_batch* b, uint64_t* coeffs_out) {
+    VX_REQUIRE(b && coeffs_out, "vx_batch_coeffs: NULL argument");
+    CtxGuard g(b->ctx);
+    VX_CHECK(copy_out(b->ctx, (u64*)coeffs_out, b->coeffs.p, b->coeffs.bytes));
+    VX_CUDA(cudaStreamSynchronize(b->ctx->stream));
+    return VX_OK;
+}
+
+static int32_t check_indices(const uint64_t* idx, uint32_t k, uint64_t N, const char* who) {
+    for (uint32_t i = 0; i < k; i++)
+        VX_REQUIRE(idx[i] < N, "%s: leaf index %llu out of range (%llu leaves)", who,
+                   (unsigned long long)idx[i], (unsigned long long)N);
+    return VX_OK;
+}
+
+static int32_t query_rows(vx_ctx* ctx, const u64* leaves, bool col_major, uint64_t stride, uint32_t c, uint64_t N,
+                          const uint64_t* idx, uint32_t k, uint64_t* rows_out) {
+    if (k == 0) return VX_OK;
+    VX_CHECK(check_indices(idx, k, N, "leaves"));
+    DevBuf di, dr;
+    VX_CHECK(di.alloc(k * sizeof(u64), ctx->stream));
+    VX_CHECK(dr.alloc((size_t)k * c * sizeof(u64), ctx->stream));
+    VX_CHECK(copy_in(ctx, di.p, (const u64*)idx, k * sizeof(u64)));
+    VX_CHECK(gather_rows_device(ctx, leaves, col_major, stride, c, di.p, k, dr.p));
+    VX_CHECK(copy_out(ctx, (u64*)rows_out, dr.p, dr.bytes));
+    VX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VX_OK;
+}
+
+static int32_t query_paths(vx_ctx* ctx, const u64* digests, uint64_t N, uint32_t cap_height, const uint64_t* idx,
+                           uint32_t k, uint64_t* siblings_out) {
+    uint32_t depth = ilog2(N) - cap_height;
+    if (k == 0 || depth == 0) return VX_OK;
+    VX_CHECK(check_indices(idx, k, N, "merkle_paths"));
+    DevBuf di, ds;
+    VX_CHECK(di.alloc(k * sizeof(u64), ctx->stream));
+    VX_CHECK(ds.alloc((size_t)k * depth * 4 * sizeof(u64), ctx->stream));
+    VX_CHECK(copy_in(ctx, di.p, (const u64*)idx, k * sizeof(u64)));
+    VX_CHECK(merkle_paths_device(ctx, digests, N, cap_height, di.p, k, ds.p));
+    VX_CHECK(copy_out(ctx, (u64*)siblings_out, ds.p, ds.bytes));
+    VX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VX_OK;
+}
+
+extern "C" int32_t vx_batch_leaves(vx_batch* b, const uint64_t* idx, uint32_t k, uint64_t* rows_out) {
+    VX_REQUIRE(b && (k == 0 || (idx && rows_out)), "vx_batch_leaves: NULL argument");
+    CtxGuard g(b->ctx);
+    return query_rows(b->ctx, b->lde.p, true, b->N(), b->c, b->N(), idx, k, rows_out);
+}
+
+extern "C" int32_t vx_batch_merkle_paths(vx_batch* b, const uint64_t* idx, uint32_t k, uint64_t* siblings_out) {
+    VX_REQUIRE(b && (k == 0 || (idx && siblings_out)), "vx_batch_merkle_paths: NULL argument");
+    CtxGuard g(b->ctx);
+    return query_paths(b->ctx, b->digests.p, b->N(), b->cap_height, idx, k, siblings_out);
+}
+
+extern "C" int32_t vx_batch_download(vx_batch* b, uint64_t* leaves_out, uint64_t* digests_out) {
+    VX_REQUIRE(b, "vx_batch_download: NULL batch");
+    CtxGuard g(b->ctx);
+    vx_ctx* ctx = b->ctx;
+    if (leaves_out) {
+        DevBuf rows;
+        VX_CHECK(rows.alloc(b->lde.bytes, ctx->stream));
+        VX_CHECK(transpose_to_rows_device(ctx, b->lde.p, b->N(), b->N(), b->c, rows.p));
+        VX_CHECK(copy_out(ctx, (u64*)leaves_out, rows.p, rows.bytes));
+        VX_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    if (digests_out && b->digests.bytes) {
+        VX_CHECK(copy_out(ctx, (u64*)digests_out, b->digests.p, b->digests.bytes));
+        VX_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return VX_OK;
+}
+
+extern "C" const uint64_t* vx_batch_lde_device(const vx_batch* b) { return b ? (const uint64_t*)b->lde.p : nullptr; }
+extern "C" const uint64_t* vx_batch_coeffs_device(const vx_batch* b) { return b ? (const uint64_t*)b->coeffs.p : nullptr; }
+extern "C" const uint64_t* vx_batch_digests_device(const vx_batch* b) { return b ? (const uint64_t*)b->digests.p : nullptr; }
+
+// ------------------------------------------------------------------------------------------------ MerkleTree
+struct vx_tree {
+    vx_ctx* ctx;
+    uint64_t n;
+    uint32_t w, cap_height;
+    DevBuf leaves, digests, cap;
+};
+
+extern "C" int32_t vx_merkle_new(vx_ctx* ctx, const uint64_t* leaves, uint64_t n, uint32_t w, uint32_t cap_height,
+                                 uint64_t* digests_out, uint64_t* cap_out, vx_tree** tree_out) {
+    VX_REQUIRE(ctx && leaves, "vx_merkle_new: NULL argument");
+    if (tree_out) *tree_out = nullptr;
+    VX_REQUIRE(n >= 1 && (n & (n - 1)) == 0, "vx_merkle_new: leaf count %llu is not a power of two",
+               (unsigned long long)n);
+    VX_REQUIRE(w >= 1, "vx_merkle_new: empty leaves");
+    VX_REQUIRE(cap_height <= ilog2(n), "vx_merkle_new: cap_height %u exceeds tree height %u", cap_height, ilog2(n));
+    CtxGuard g(ctx);
+    vx_tree* t = new (std::nothrow) vx_tree();
+    if (!t) return VX_ENOMEM;
+    t->ctx = ctx; t->n = n; t->w = w; t->cap_height = cap_height;
+    int32_t r = t->leaves.alloc((size_t)n * w * sizeof(u64), ctx->stream);
+    if (r == VX_OK) r = t->digests.alloc((size_t)2 * (n - (1ULL << cap_height)) * 4 * sizeof(u64), ctx->stream);
+    if (r == VX_OK) r = t->cap.alloc((size_t)(1ULL << cap_height) * 4 * sizeof(u64), ctx->stream);
+    if (r == VX_OK) r = copy_in(ctx, t->leaves.p, (const u64*)leaves, t->leaves.bytes);
+    if (r == VX_OK) r = merkle_build_device(ctx, t->leaves.p, false, 0, n, w, cap_height, t->digests.p, t->cap.p);
+    if (r == VX_OK && digests_out && t->digests.bytes) r = copy_out(ctx, (u64*)digests_out, t->digests.p, t->digests.bytes);
+    if (r == VX_OK && cap_out) r = copy_out(ctx, (u64*)cap_out, t->cap.p, t->cap.bytes);
+    if (r == VX_OK) {
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { vx_set_error("vx_merkle_new: %s", cudaGetErrorString(e)); r = VX_ECUDA; }
+    }
+    if (r != VX_OK || !tree_out) {
+        t->leaves.release(); t->digests.release(); t->cap.release();
+        delete t;
+        return r;
+    }
+    *tree_out = t;
+    return VX_OK;
+}
+
+extern "C" int32_t vx_tree_prove(vx_tree* t, const uint64_t* idx, uint32_t k, uint64_t* siblings_out) {
+    VX_REQUIRE(t && (k == 0 || (idx && siblings_out)), "vx_tree_prove: NULL argument");
+    CtxGuard g(t->ctx);
+    return query_paths(t->ctx, t->digests.p, t->n, t->cap_height, idx, k, siblings_out);
+}
+extern "C" int32_t vx_tree_leaves(vx_tree* t, const uint64_t* idx, uint32_t k, uint64_t* rows_out) {
+    VX_REQUIRE(t && (k == 0 || (idx && rows_out)), "vx_tree_leaves: NULL argument");
+    CtxGuard g(t->ctx);
+    return query_rows(t->ctx, t->leaves.p, false, 0, t->w, t->n, idx, k, rows_out);
+}
+extern "C" int32_t vx_tree_cap(vx_tree* t, uint64_t* cap_out) {
+    VX_REQUIRE(t && cap_out, "vx_tree_cap: NULL argument");
+    CtxGuard g(t->ctx);
+    VX_CHECK(copy_out(t->ctx, (u64*)cap_out, t->cap.p, t->cap.bytes));
+    VX_CUDA(cudaStreamSynchronize(t->ctx->stream));
+    return VX_OK;
+}
+extern "C" void vx_tree_free(vx_tree* t) {
+    if (!t) return;
+    {
+        CtxGuard g(t->ctx);
+        t->leaves.release(); t->digests.release(); t->cap.release();
+    }
+    delete t;
+}
+
+// ------------------------------------------------------------------------------------------------ primitives
+extern "C" int32_t vx_poseidon_permute(vx_ctx* ctx, const uint64_t* in, uint64_t count, uint64_t* out) {
+    VX_REQUIRE(ctx && (count == 0 || (in && out)), "vx_poseidon_permute: NULL argument");
+    if (count == 0) return VX_OK;
+    CtxGuard g(ctx);
+    DevBuf a, b;
+    VX_CHECK(a.alloc(count * 12 * sizeof(u64), ctx->stream));
+    VX_CHECK(b.alloc(count * 12 * sizeof(u64), ctx->stream));
+    VX_CHECK(copy_in(ctx, a.p, (const u64*)in, a.bytes));
+    VX_CHECK(poseidon_permute_device(ctx, a.p, count, b.p));
+    VX_CHECK(copy_out(ctx, (u64*)out, b.p, b.bytes));
+    VX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VX_OK;
+}
+
+extern "C" int32_t vx_hash_no_pad(vx_ctx* ctx, const uint64_t* in, uint64_t count, uint32_t len, uint64_t* out) {
+    VX_REQUIRE(ctx && (count == 0 || out), "vx_hash_no_pad: NULL argument");
+    VX_REQUIRE(len == 0 || in, "vx_hash_no_pad: NULL input");
+    if (count == 0) return VX_OK;
+    CtxGuard g(ctx);
+    DevBuf a, b;
+    VX_CHECK(a.alloc((size_t)count * len * sizeof(u64), ctx->stream));
+    VX_CHECK(b.alloc(count * 4 * sizeof(u64), ctx->stream));
+    if (len) VX_CHECK(copy_in(ctx, a.p, (const u64*)in, a.bytes));
+    VX_CHECK(hash_no_pad_device(ctx, a.p, count, len, b.p));
+    VX_CHECK(copy_out(ctx, (u64*)out, b.p, b.bytes));
+    VX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VX_OK;
+}
+
+extern "C" int32_t vx_poseidon_constants(uint64_t out[360]) {
+    if (!out) { vx_set_error("vx_poseidon_constants: NULL"); return VX_EINVAL; }
+    poseidon_round_constants_host((u64*)out);
+    return VX_OK;
+}
+
+extern "C" int32_t vx_ntt(vx_ctx* ctx, const uint64_t* in, uint64_t* out, uint32_t c, uint32_t log_n,
+                          int32_t inverse, uint64_t coset_shift) {
+    VX_REQUIRE(ctx && in && out, "vx_ntt: NULL argument");
+    VX_REQUIRE(c >= 1 && log_n <= 26, "vx_ntt: shape out of range");
+    CtxGuard g(ctx);
+    size_t bytes = ((size_t)c << log_n) * sizeof(u64);
+    DevBuf a, b;
+    VX_CHECK(a.alloc(bytes, ctx->stream));
+    VX_CHECK(b.alloc(bytes, ctx->stream));
+    VX_CHECK(copy_in(ctx, a.p, (const u64*)in, bytes));
+    VX_CHECK(ntt_natural(ctx, a.p, b.p, c, log_n, inverse != 0, coset_shift));
+    VX_CHECK(copy_out(ctx, (u64*)out, b.p, bytes));
+    VX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VX_OK;
+}

@@ -1,0 +1,129 @@
+// Shared host-side plumbing for libvectorx_b200: context, error reporting, device buffers.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/vectorx_b200.h"
+#include "gl.cuh"
+
+// ---- error handling: never throw across the C ABI -----------------------------------------------
+void vx_set_error(const char* fmt, ...);
+
+#define VX_CUDA(expr)                                                                         \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            vx_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return (_e == cudaErrorMemoryAllocation) ? VX_ENOMEM : VX_ECUDA;                  \
+        }                                                                                     \
+    } while (0)
+
+#define VX_CHECK(expr)                 \
+    do {                               \
+        int32_t _r = (expr);           \
+        if (_r != VX_OK) return _r;    \
+    } while (0)
+
+#define VX_REQUIRE(cond, ...)          \
+    do {                               \
+        if (!(cond)) {                 \
+            vx_set_error(__VA_ARGS__); \
+            return VX_EINVAL;          \
+        }                              \
+    } while (0)
+
+// ---- context ----------------------------------------------------------------------------------------
+// Twiddle tables (all canonical):
+//   w_lo/w_hi : powers of W = POWER_OF_TWO_GENERATOR (order 2^32): W^E = w_hi[E>>16] * w_lo[E&0xffff]
+//   wi_lo/wi_hi : same for W^-1
+//   g_lo/g_hi : powers of the coset shift g: g^m = g_hi[m>>12] * g_lo[m&0xfff]  (m < 2^24)
+//   roots12 / iroots12 : w_4096^e, e < 2048, for the in-shared-memory sub-transforms
+struct vx_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;                      // serialises calls on this context's stream
+    std::atomic<uint64_t> launches{0};
+    u64 *w_lo = nullptr, *w_hi = nullptr, *wi_lo = nullptr, *wi_hi = nullptr;
+    u64 *g_lo = nullptr, *g_hi = nullptr, *gi_lo = nullptr, *gi_hi = nullptr;
+    u64 *roots12 = nullptr, *iroots12 = nullptr;
+};
+
+struct TwiddleView {     // passed by value to kernels
+    const u64* lo;       // W^(E & 0xffff)
+    const u64* hi;       // W^((E >> 16) << 16)
+    const u64* roots12;  // w_4096^e
+};
+
+#define VX_LAUNCH_COUNT(ctx, n) (ctx)->launches.fetch_add((n), std::memory_order_relaxed)
+
+// classify a pointer: returns true if it is device memory
+bool vx_is_device_ptr(const void* p);
+
+// RAII device buffer (cudaMallocAsync on the context stream)
+struct DevBuf {
+    u64* p = nullptr;
+    size_t bytes = 0;
+    cudaStream_t s = nullptr;
+    int32_t alloc(size_t nbytes, cudaStream_t stream);
+    void release();
+    ~DevBuf() { release(); }
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+};
+
+static inline unsigned ilog2(uint64_t x) {
+    unsigned r = 0;
+    while ((1ULL << r) < x) r++;
+    return r;
+}
+__host__ __device__ static inline uint64_t bitrev_u64(uint64_t x, unsigned bits) {
+#ifdef __CUDA_ARCH__
+    return bits ? (__brevll(x) >> (64 - bits)) : 0;
+#else
+    uint64_t r = 0;
+    for (unsigned i = 0; i < bits; i++) { r = (r << 1) | (x & 1); x >>= 1; }
+    return r;
+#endif
+}
+
+// ---- module entry points (one per .cu) ------------------------------------------------------------
+int32_t poseidon_module_init(vx_ctx* ctx);                 // merkle.cu: uploads round constants
+void poseidon_round_constants_host(u64 out[360]);          // merkle.cu: ChaCha8Rng(0) derivation
+
+// merkle.cu ---------------------------------------------------------------------------------------
+// Hash N leaves of width c.  col_major: element (row, col) at leaves[col * stride + row];
+// otherwise row-major at leaves[row * c + col].  digests: plonky2 interleaved layout (device),
+// cap: 2^cap_height x 4 (device).
+int32_t merkle_build_device(vx_ctx* ctx, const u64* leaves, bool col_major, uint64_t stride, uint64_t N,
+                            uint32_t c, uint32_t cap_height, u64* digests, u64* cap);
+int32_t merkle_paths_device(vx_ctx* ctx, const u64* digests, uint64_t N, uint32_t cap_height,
+                            const u64* idx_dev, uint32_t k, u64* siblings_dev);
+int32_t gather_rows_device(vx_ctx* ctx, const u64* leaves, bool col_major, uint64_t stride, uint32_t c,
+                           const u64* idx_dev, uint32_t k, u64* rows_dev);
+int32_t transpose_to_rows_device(vx_ctx* ctx, const u64* colmajor, uint64_t stride, uint64_t N, uint32_t c,
+                                 u64* rows_dev);
+int32_t poseidon_permute_device(vx_ctx* ctx, const u64* in, uint64_t count, u64* out);
+int32_t hash_no_pad_device(vx_ctx* ctx, const u64* in, uint64_t count, uint32_t len, u64* out);
+
+// ntt.cu ------------------------------------------------------------------------------------------
+int32_t ntt_module_init(vx_ctx* ctx);
+void ntt_module_destroy(vx_ctx* ctx);
+// In-place forward DIF NTT of `count` contiguous transforms of size 2^log_n starting at data
+// (transform t occupies data[t << log_n ...]); output in bit-reversed order. inverse uses w^-1.
+int32_t ntt_dif_inplace(vx_ctx* ctx, u64* data, uint64_t count, uint32_t log_n, bool inverse);
+// values (c x n natural) -> coefficients (c x n natural): plonky2 ifft. `work` (c x n) is clobbered.
+int32_t intt_batch(vx_ctx* ctx, u64* work, u64* coeffs_out, uint32_t c, uint32_t log_n);
+// coefficients (c x n natural) -> LDE on coset g*<w_N>, leaf (bit-reversed) order, c x N column-major.
+int32_t lde_batch(vx_ctx* ctx, const u64* coeffs, u64* lde_out, uint32_t c, uint32_t log_n, uint32_t rate_bits);
+// generic natural-order transform used by vx_ntt (tests, FRI layers)
+int32_t ntt_natural(vx_ctx* ctx, const u64* in, u64* out, uint32_t c, uint32_t log_n, bool inverse,
+                    uint64_t coset_shift);

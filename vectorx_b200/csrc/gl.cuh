@@ -1,0 +1,161 @@
+// Goldilocks field arithmetic for sm_100a, p = 2^64 - 2^32 + 1.
+//
+// Replaces plonky2_field v0.2.0 goldilocks_field.rs (type bound in the reference at
+// contracts/lib/succinctx/plonky2x/core/src/backend/circuit/config.rs:37).  Values travel as u64
+// holding ANY representative (plonky2 does the same); gl_canon() produces the canonical one and
+// every kernel canonicalises what it stores to HBM.
+//
+// The SM has no 64-bit integer datapath: everything below is written so that ptxas emits
+// IMAD.WIDE.U32 (32x32+64 -> 64 on the FMA pipe) for products and IADD3/.X chains on the ALU pipe
+// for the reductions, keeping both pipes busy.
+#pragma once
+#include <cstdint>
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+#define GL_P 0xFFFFFFFF00000001ULL
+#define GL_EPS 0xFFFFFFFFULL
+#define GL_GENERATOR 14293326489335486720ULL        // MULTIPLICATIVE_GROUP_GENERATOR = coset_shift()
+#define GL_POWER_OF_TWO_GENERATOR 7277203076849721926ULL   // order 2^32
+
+#define GL_HD __host__ __device__ __forceinline__
+#define GL_D __device__ __forceinline__
+
+GL_D u32 lo32(u64 x) { return (u32)x; }
+GL_D u32 hi32(u64 x) { return (u32)(x >> 32); }
+GL_D u64 pack64(u32 lo, u32 hi) { return ((u64)hi << 32) | lo; }
+
+GL_D u64 mad_wide(u32 a, u32 b, u64 c) {     // a*b + c, caller guarantees no 64-bit overflow
+    u64 d;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
+    return d;
+}
+GL_D u64 mul_wide(u32 a, u32 b) {
+    u64 d;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(d) : "r"(a), "r"(b));
+    return d;
+}
+
+GL_D u64 gl_canon(u64 a) { return a >= GL_P ? a - GL_P : a; }
+
+// a + b where b is canonical (< p): single conditional fix-up cannot overflow twice.
+GL_D u64 gl_add_canon(u64 a, u64 b) {
+    u64 s = a + b;
+    return s < a ? s + GL_EPS : s;
+}
+// general a + b (any representatives)
+GL_D u64 gl_add(u64 a, u64 b) { return gl_add_canon(a, gl_canon(b)); }
+// a - b (any representatives)
+GL_D u64 gl_sub(u64 a, u64 b) {
+    u64 bc = gl_canon(b);
+    u64 d = a - bc;
+    return a < bc ? d - GL_EPS : d;
+}
+GL_D u64 gl_neg(u64 a) {
+    u64 c = gl_canon(a);
+    return c ? GL_P - c : 0;
+}
+
+// x = hi*2^64 + lo  ->  x mod p as some u64 representative.
+// 2^64 = 2^32 - 1, 2^96 = -1 (mod p):  x = lo - hi_hi + hi_lo*(2^32-1).
+GL_D u64 gl_reduce128(u64 lo, u64 hi) {
+    u32 hh = hi32(hi), hl = lo32(hi);
+    u64 t = lo - hh;
+    if (lo < (u64)hh) t -= GL_EPS;          // borrow: add p == subtract eps mod 2^64
+    u64 m = mul_wide(hl, 0xFFFFFFFFu);
+    u64 r = t + m;
+    if (r < t) r += GL_EPS;                 // carry: 2^64 = eps
+    return r;
+}
+
+// x = hi32*2^64 + lo (a 96-bit value): cheaper tail for small-constant accumulations
+GL_D u64 gl_reduce96(u64 lo, u32 hi) {
+    u64 m = mul_wide(hi, 0xFFFFFFFFu);
+    u64 r = lo + m;
+    if (r < lo) r += GL_EPS;
+    return r;
+}
+
+// full 64x64 -> 128 product on IMAD.WIDE.U32: 4 multiplies, no carry chains
+// (each partial sum provably fits 64 bits).
+GL_D void gl_mul128(u64 a, u64 b, u64& lo, u64& hi) {
+    u32 a0 = lo32(a), a1 = hi32(a), b0 = lo32(b), b1 = hi32(b);
+    u64 p00 = mul_wide(a0, b0);
+    u64 mid = mad_wide(a0, b1, (u64)hi32(p00));
+    u64 mid2 = mad_wide(a1, b0, (u64)lo32(mid));
+    u64 top = mad_wide(a1, b1, (u64)hi32(mid));
+    hi = top + hi32(mid2);
+    lo = pack64(lo32(p00), lo32(mid2));
+}
+
+GL_D u64 gl_mul(u64 a, u64 b) {
+    u64 lo, hi;
+    gl_mul128(a, b, lo, hi);
+    return gl_reduce128(lo, hi);
+}
+
+GL_D u64 gl_sqr(u64 a) {
+    u32 a0 = lo32(a), a1 = hi32(a);
+    u64 p00 = mul_wide(a0, a0);
+    u64 cross = mul_wide(a0, a1);                     // appears twice
+    u64 p11 = mul_wide(a1, a1);
+    // x = p00 + 2*cross*2^32 + p11*2^64
+    u64 c2lo = cross << 1;                            // low 64 bits of 2*cross
+    u32 c2hi = (u32)(cross >> 63);                    // bit 64
+    u64 mid = c2lo + hi32(p00);
+    u32 carry = mid < c2lo;
+    u64 lo = pack64(lo32(p00), lo32(mid));
+    u64 hi = p11 + hi32(mid) + ((u64)(c2hi + carry) << 32);
+    return gl_reduce128(lo, hi);
+}
+
+GL_D u64 gl_pow7(u64 x) {
+    u64 x2 = gl_sqr(x);
+    u64 x4 = gl_sqr(x2);
+    u64 x3 = gl_mul(x2, x);
+    return gl_mul(x3, x4);
+}
+
+__host__ __device__ inline u64 gl_mul_slow(u64 a, u64 b) {     // host+device helper (tables, setup)
+#ifdef __CUDA_ARCH__
+    return gl_canon(gl_mul(a, b));
+#else
+    unsigned __int128 x = (unsigned __int128)a * b;
+    u64 lo = (u64)x, hi = (u64)(x >> 64);
+    u64 hh = hi >> 32, hl = hi & GL_EPS;
+    u64 t = lo - hh;
+    if (lo < hh) t -= GL_EPS;
+    u64 m = hl * GL_EPS;
+    u64 r = t + m;
+    if (r < t) r += GL_EPS;
+    return r >= GL_P ? r - GL_P : r;
+#endif
+}
+
+inline u64 gl_pow_host(u64 a, u64 e) {
+    u64 r = 1;
+    while (e) {
+        if (e & 1) r = gl_mul_slow(r, a);
+        a = gl_mul_slow(a, a);
+        e >>= 1;
+    }
+    return r;
+}
+inline u64 gl_inv_host(u64 a) { return gl_pow_host(a, GL_P - 2); }
+inline u64 gl_root_of_unity_host(unsigned log_n) {
+    u64 r = GL_POWER_OF_TWO_GENERATOR;
+    for (unsigned i = log_n; i < 32; i++) r = gl_mul_slow(r, r);
+    return r;
+}
+
+GL_D u64 gl_pow(u64 a, u64 e) {
+    u64 r = 1;
+    while (e) {
+        if (e & 1) r = gl_mul(r, a);
+        a = gl_sqr(a);
+        e >>= 1;
+    }
+    return r;
+}
+GL_D u64 gl_inv(u64 a) { return gl_pow(a, GL_P - 2); }

@@ -1,0 +1,282 @@
+// Poseidon Merkle tree on sm_100a.
+//
+// Replaces plonky2 v0.2.0 hash/merkle_tree.rs `MerkleTree::new` / `fill_digests_buf` /
+// `fill_subtree`, hash/hashing.rs `hash_n_to_hash_no_pad` / `compress`, and the Hasher surface
+// shown in-tree at contracts/lib/succinctx/plonky2x/core/src/backend/wrapper/plonky2_config.rs:130-196
+// (hash_or_noop, two_to_one).  API shape exercised in the reference at
+// .../backend/wrapper/poseidon_bn128.rs:217-220.
+//
+// Layout: `digests` is plonky2's interleaved layout -- per cap subtree a block of 2*sub-2 digests
+// where the sibling pair q of layer l (0 = leaf digests) sits at 2*(q*2^(l+1) + 2^l - 1) + {0,1};
+// roots go to `cap` only.  Kernels write straight into that layout so the tree a Rust caller
+// downloads is byte-identical to MerkleTree { leaves, digests, cap }.
+//
+// Leaf hashing is one thread per leaf row.  With the LDE kept column-major in leaf order the
+// per-column loads of a warp are 256 contiguous bytes (fully coalesced) with no transpose pass.
+#include "common.cuh"
+#include "poseidon.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// Round constants: ChaCha8Rng::seed_from_u64(0), 360 x gen_range(0..p) (rand 0.8 widening-multiply
+// rejection).  Derived here, independently of the test oracle, and audited by tests against it.
+static inline uint32_t rotl32(uint32_t x, int n) { return (x << n) | (x >> (32 - n)); }
+
+static void chacha8_block(const uint32_t key[8], uint64_t counter, uint32_t out[16]) {
+    uint32_t in[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u,
+                       key[0], key[1], key[2], key[3], key[4], key[5], key[6], key[7],
+                       (uint32_t)counter, (uint32_t)(counter >> 32), 0u, 0u};
+    uint32_t x[16];
+    memcpy(x, in, sizeof x);
+    auto qr = [&](int a, int b, int c, int d) {
+        x[a] += x[b]; x[d] = rotl32(x[d] ^ x[a], 16);
+        x[c] += x[d]; x[b] = rotl32(x[b] ^ x[c], 12);
+        x[a] += x[b]; x[d] = rotl32(x[d] ^ x[a], 8);
+        x[c] += x[d]; x[b] = rotl32(x[b] ^ x[c], 7);
+    };
+    for (int dr = 0; dr < 4; dr++) {      // 8 rounds = 4 double rounds
+        qr(0, 4, 8, 12); qr(1, 5, 9, 13); qr(2, 6, 10, 14); qr(3, 7, 11, 15);
+        qr(0, 5, 10, 15); qr(1, 6, 11, 12); qr(2, 7, 8, 13); qr(3, 4, 9, 14);
+    }
+    for (int i = 0; i < 16; i++) out[i] = x[i] + in[i];
+}
+
+void poseidon_round_constants_host(u64 out[360]) {
+    uint32_t key[8];
+    uint64_t pcg = 0;                     // rand_core::SeedableRng::seed_from_u64 (PCG32 expansion)
+    for (int i = 0; i < 8; i++) {
+        pcg = pcg * 6364136223846793005ULL + 11634580027462260723ULL;
+        uint32_t xorshifted = (uint32_t)(((pcg >> 18) ^ pcg) >> 27);
+        uint32_t rot = (uint32_t)(pcg >> 59);
+        key[i] = (xorshifted >> rot) | (xorshifted << ((32 - rot) & 31));
+    }
+    uint32_t words[16];
+    int have = 0, used = 0;
+    uint64_t counter = 0;
+    auto next_u32 = [&]() {
+        if (used == have) { chacha8_block(key, counter++, words); have = 16; used = 0; }
+        return words[used++];
+    };
+    int n = 0;
+    while (n < 360) {
+        uint64_t lo = next_u32();
+        uint64_t hi = next_u32();
+        uint64_t v = lo | (hi << 32);
+        unsigned __int128 m = (unsigned __int128)v * GL_P;
+        if ((uint64_t)m <= GL_P - 1) out[n++] = (uint64_t)(m >> 64);
+    }
+}
+
+int32_t poseidon_module_init(vx_ctx* ctx) {
+    u64 rc[360];
+    poseidon_round_constants_host(rc);
+    VX_CUDA(poseidon_upload_constants(rc, ctx->stream));
+    return VX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+GL_D uint64_t pair_pos(uint64_t q, uint32_t lvl) { return 2 * (q * (2ULL << lvl) + (1ULL << lvl) - 1); }
+
+GL_D void store_digest(u64* dst, const u64 s[12]) {
+    ulonglong2 a = make_ulonglong2(gl_canon(s[0]), gl_canon(s[1]));
+    ulonglong2 b = make_ulonglong2(gl_canon(s[2]), gl_canon(s[3]));
+    reinterpret_cast<ulonglong2*>(dst)[0] = a;
+    reinterpret_cast<ulonglong2*>(dst)[1] = b;
+}
+
+// one thread per leaf: hash_or_noop(leaf) -> interleaved slot (or cap when the subtree is 1 leaf)
+template <bool COL_MAJOR>
+__global__ void __launch_bounds__(128) leaf_hash_kernel(const u64* __restrict__ leaves, uint64_t stride,
+                                                        uint64_t N, uint32_t c, uint32_t sub_bits,
+                                                        u64* __restrict__ digests, u64* __restrict__ cap) {
+    uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= N) return;
+    const u64* src = COL_MAJOR ? leaves + row : leaves + row * c;
+    const uint64_t step = COL_MAJOR ? stride : 1;
+    u64 s[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = 0;
+    if (c <= 4) {                         // hash_or_noop: identity, zero padded
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if ((uint32_t)i < c) s[i] = src[i * step];
+    } else {
+        for (uint32_t off = 0; off < c; off += POSEIDON_RATE) {
+#pragma unroll
+            for (int i = 0; i < POSEIDON_RATE; i++)
+                if (off + i < c) s[i] = src[(uint64_t)(off + i) * step];   // overwrite-mode absorb
+            poseidon_permute(s);
+        }
+    }
+    u64* dst;
+    if (sub_bits == 0) {
+        dst = cap + 4 * row;
+    } else {
+        uint64_t sub = 1ULL << sub_bits;
+        uint64_t sidx = row >> sub_bits, jj = row & (sub - 1);
+        dst = digests + 4 * (sidx * (2 * sub - 2) + 4 * (jj >> 1) + (jj & 1));
+    }
+    store_digest(dst, s);
+}
+
+// one thread per sibling pair of layer `lvl`: two_to_one -> parent slot (or cap at the top)
+__global__ void __launch_bounds__(128) level_hash_kernel(u64* __restrict__ digests, u64* __restrict__ cap,
+                                                         uint32_t lvl, uint32_t sub_bits, uint64_t total_pairs) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total_pairs) return;
+    uint32_t pair_bits = sub_bits - lvl - 1;            // pairs per subtree = 2^pair_bits
+    uint64_t sidx = t >> pair_bits, q = t & ((1ULL << pair_bits) - 1);
+    uint64_t sub = 1ULL << sub_bits;
+    u64* blk = digests + 4 * sidx * (2 * sub - 2);
+    const ulonglong2* pr = reinterpret_cast<const ulonglong2*>(blk + 4 * pair_pos(q, lvl));
+    u64 s[12];
+    ulonglong2 v0 = pr[0], v1 = pr[1], v2 = pr[2], v3 = pr[3];
+    s[0] = v0.x; s[1] = v0.y; s[2] = v1.x; s[3] = v1.y;
+    s[4] = v2.x; s[5] = v2.y; s[6] = v3.x; s[7] = v3.y;
+    s[8] = s[9] = s[10] = s[11] = 0;
+    poseidon_permute(s);
+    u64* dst = (pair_bits == 0) ? cap + 4 * sidx : blk + 4 * (pair_pos(q >> 1, lvl + 1) + (q & 1));
+    store_digest(dst, s);
+}
+
+int32_t merkle_build_device(vx_ctx* ctx, const u64* leaves, bool col_major, uint64_t stride, uint64_t N,
+                            uint32_t c, uint32_t cap_height, u64* digests, u64* cap) {
+    uint32_t log_N = ilog2(N);
+    VX_REQUIRE((1ULL << log_N) == N, "merkle: leaf count %llu is not a power of two", (unsigned long long)N);
+    VX_REQUIRE(cap_height <= log_N, "merkle: cap_height %u > log2(leaves) %u", cap_height, log_N);
+    VX_REQUIRE(c >= 1, "merkle: empty leaves");
+    uint32_t sub_bits = log_N - cap_height;
+    unsigned blocks = (unsigned)((N + 127) / 128);
+    if (col_major)
+        leaf_hash_kernel<true><<<blocks, 128, 0, ctx->stream>>>(leaves, stride, N, c, sub_bits, digests, cap);
+    else
+        leaf_hash_kernel<false><<<blocks, 128, 0, ctx->stream>>>(leaves, stride, N, c, sub_bits, digests, cap);
+    VX_LAUNCH_COUNT(ctx, 1);
+    for (uint32_t lvl = 0; lvl < sub_bits; lvl++) {
+        uint64_t total_pairs = N >> (lvl + 1);
+        unsigned b = (unsigned)((total_pairs + 127) / 128);
+        level_hash_kernel<<<b, 128, 0, ctx->stream>>>(digests, cap, lvl, sub_bits, total_pairs);
+        VX_LAUNCH_COUNT(ctx, 1);
+    }
+    VX_CUDA(cudaGetLastError());
+    return VX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ queries
+__global__ void merkle_paths_kernel(const u64* __restrict__ digests, uint32_t sub_bits,
+                                    const u64* __restrict__ idx, uint32_t k, u64* __restrict__ out) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= k * sub_bits) return;
+    uint32_t qi = t / sub_bits, lvl = t % sub_bits;
+    uint64_t leaf = idx[qi];
+    uint64_t sub = 1ULL << sub_bits;
+    uint64_t sidx = leaf >> sub_bits, j = leaf & (sub - 1);
+    uint64_t node = j >> lvl;
+    const u64* src = digests + 4 * (sidx * (2 * sub - 2) + pair_pos(node >> 1, lvl) + ((node & 1) ^ 1));
+    u64* dst = out + 4 * ((uint64_t)qi * sub_bits + lvl);
+    for (int i = 0; i < 4; i++) dst[i] = src[i];
+}
+
+int32_t merkle_paths_device(vx_ctx* ctx, const u64* digests, uint64_t N, uint32_t cap_height,
+                            const u64* idx_dev, uint32_t k, u64* siblings_dev) {
+    uint32_t sub_bits = ilog2(N) - cap_height;
+    if (sub_bits == 0 || k == 0) return VX_OK;
+    uint32_t total = k * sub_bits;
+    merkle_paths_kernel<<<(total + 127) / 128, 128, 0, ctx->stream>>>(digests, sub_bits, idx_dev, k, siblings_dev);
+    VX_LAUNCH_COUNT(ctx, 1);
+    VX_CUDA(cudaGetLastError());
+    return VX_OK;
+}
+
+__global__ void gather_rows_kernel(const u64* __restrict__ leaves, bool col_major, uint64_t stride, uint32_t c,
+                                   const u64* __restrict__ idx, uint32_t k, u64* __restrict__ out) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (uint64_t)k * c) return;
+    uint32_t qi = (uint32_t)(t / c), col = (uint32_t)(t % c);
+    uint64_t row = idx[qi];
+    u64 v = col_major ? leaves[(uint64_t)col * stride + row] : leaves[row * c + col];
+    out[t] = gl_canon(v);
+}
+
+int32_t gather_rows_device(vx_ctx* ctx, const u64* leaves, bool col_major, uint64_t stride, uint32_t c,
+                           const u64* idx_dev, uint32_t k, u64* rows_dev) {
+    if (k == 0) return VX_OK;
+    uint64_t total = (uint64_t)k * c;
+    gather_rows_kernel<<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>(leaves, col_major, stride, c,
+                                                                                 idx_dev, k, rows_dev);
+    VX_LAUNCH_COUNT(ctx, 1);
+    VX_CUDA(cudaGetLastError());
+    return VX_OK;
+}
+
+// column-major (c x stride) -> row-major (N x c), 32x32 tiles through shared memory
+__global__ void transpose_rows_kernel(const u64* __restrict__ in, uint64_t stride, uint64_t N, uint32_t c,
+                                      u64* __restrict__ out) {
+    __shared__ u64 tile[32][33];
+    uint64_t row0 = (uint64_t)blockIdx.x * 32;
+    uint32_t col0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        uint32_t col = col0 + j;
+        uint64_t row = row0 + threadIdx.x;
+        if (col < c && row < N) tile[j][threadIdx.x] = in[(uint64_t)col * stride + row];
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        uint64_t row = row0 + j;
+        uint32_t col = col0 + threadIdx.x;
+        if (col < c && row < N) out[row * c + col] = gl_canon(tile[threadIdx.x][j]);
+    }
+}
+
+int32_t transpose_to_rows_device(vx_ctx* ctx, const u64* colmajor, uint64_t stride, uint64_t N, uint32_t c,
+                                 u64* rows_dev) {
+    dim3 grid((unsigned)((N + 31) / 32), (c + 31) / 32), block(32, 8);
+    transpose_rows_kernel<<<grid, block, 0, ctx->stream>>>(colmajor, stride, N, c, rows_dev);
+    VX_LAUNCH_COUNT(ctx, 1);
+    VX_CUDA(cudaGetLastError());
+    return VX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ primitives
+__global__ void __launch_bounds__(128) permute_kernel(const u64* __restrict__ in, uint64_t count, u64* __restrict__ out) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    u64 s[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = in[t * 12 + i];
+    poseidon_permute(s);
+#pragma unroll
+    for (int i = 0; i < 12; i++) out[t * 12 + i] = gl_canon(s[i]);
+}
+
+int32_t poseidon_permute_device(vx_ctx* ctx, const u64* in, uint64_t count, u64* out) {
+    if (count == 0) return VX_OK;
+    permute_kernel<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(in, count, out);
+    VX_LAUNCH_COUNT(ctx, 1);
+    VX_CUDA(cudaGetLastError());
+    return VX_OK;
+}
+
+__global__ void __launch_bounds__(128) hash_no_pad_kernel(const u64* __restrict__ in, uint64_t count, uint32_t len,
+                                                          u64* __restrict__ out) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    const u64* src = in + t * len;
+    u64 s[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = 0;
+    for (uint32_t off = 0; off < len; off += POSEIDON_RATE) {
+#pragma unroll
+        for (int i = 0; i < POSEIDON_RATE; i++)
+            if (off + i < len) s[i] = src[off + i];
+        poseidon_permute(s);
+    }
+    for (int i = 0; i < 4; i++) out[t * 4 + i] = gl_canon(s[i]);
+}
+
+int32_t hash_no_pad_device(vx_ctx* ctx, const u64* in, uint64_t count, uint32_t len, u64* out) {
+    if (count == 0) return VX_OK;
+    hash_no_pad_kernel<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(in, count, len, out);
+    VX_LAUNCH_COUNT(ctx, 1);
+    VX_CUDA(cudaGetLastError());
+    return VX_OK;
+}
