@@ -166,9 +166,11 @@ int32_t ntt_dif_inplace(vx_ctx* ctx, u64* data, uint64_t count, uint32_t log_n, 
         VX_LAUNCH_COUNT(ctx, 1);
         rem -= A;
     }
+    // a CTA owns 2^chunk_bits contiguous elements = one or more whole 2^rem blocks
     uint32_t chunk_bits = rem < 10 ? 10 : rem;
     uint64_t total = count << log_n;
-    if ((1ULL << chunk_bits) > total) chunk_bits = ilog2(total);
+    uint32_t max_bits = log_n + (uint32_t)__builtin_ctzll(count);     // largest power of two dividing total
+    if (chunk_bits > max_bits) chunk_bits = max_bits;
     uint64_t blocks = total >> chunk_bits;
     VX_REQUIRE(blocks < (1ULL << 31), "ntt: too many blocks");
     ntt_final_pass<<<(unsigned)blocks, 256, (size_t)sizeof(u64) << chunk_bits, ctx->stream>>>(data, rem, chunk_bits, tw);
