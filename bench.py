@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py -- LDE + Poseidon-Merkle commit throughput (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one plonky2 `PolynomialBatch::from_values` commit (iNTT -> coset LDE -> Poseidon Merkle
+tree to the cap) of the workload shape, through the C ABI of include/vectorx_b200.h.
+ * value : whole-job Melem/s (input trace elements n*c per second) with the values already in HBM;
+ * e2e   : the same through the public API with pinned HOST buffers: H2D of the values and D2H of
+           the cap inside the timed region;
+ * N > 1 : ONE commit is sharded over the ranks (strong scaling): column-sharded iNTT, NCCL
+           all-gather of the coefficients, each rank extends and hashes its own cosets / cap
+           subtrees (coset partition), caps gathered with NCCL;
+ * --impl reference : the CPU restatement of the reference path (oracle/, OpenMP over columns /
+           subtrees like plonky2's Rayon) timed on the host cores.  The real Rust prover cannot be
+           built here (no cargo; plonky2 not vendored) -- kind = "port".
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+P = 0xFFFFFFFF00000001
+METRIC = "LDE+Poseidon-Merkle commit throughput"
+UNIT = "Melem/s"
+IMADS_PER_PERMUTATION = 6612        # 1077 full mults x 4 + 1152 small MACs x 2
+N_INPUT_SETS = 4                     # rotate inputs so consecutive steps never hit L2 (4 x 70.8 MB > 126 MB)
+
+
+def workload_from_args(a):
+    return dict(log_n=a.log_n, cols=a.cols, rate_bits=a.rate_bits, cap_height=a.cap_height)
+
+
+def workload_name(w):
+    return f"plonky2 from_values commit 2^{w['log_n']} rows x {w['cols']} cols, rate_bits={w['rate_bits']}, cap_height={w['cap_height']}"
+
+
+def gen_values(c, n, seed):
+    rng = np.random.default_rng(seed)
+    a = rng.integers(0, P, size=(c, n), dtype=np.uint64)       # uniform canonical field elements
+    return a
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def load_int_peak():
+    """thread-level 32-bit IMAD issue rate measured by tools/intpeak on this pool's B200 (profiles/)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "int_peaks_r01.json")) as f:
+            d = json.load(f)
+        return float(d["imad_lo"]["thread_instr_per_s"]) / 1e9, "measured IMAD issue rate (profiles/int_peaks_r01.json)"
+    except Exception:
+        return 148 * 64 * 1.965, "nominal 148 SM x 64 IMAD/clk x 1.965 GHz"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU legs
+def cpu_commit_seconds(w, log_n_sample, repeats=1):
+    """Times the oracle (native build, all host threads) on a bounded sample of the workload."""
+    import oracle                                   # the ONLY place bench.py touches oracle/: the CPU baseline
+    c = w["cols"]
+    cols = gen_values(c, 1 << log_n_sample, seed=99)
+    L = oracle.lib(native=True)
+    threads = L.vxo_num_threads()
+    best = None
+    for _ in range(repeats):
+        t = time.perf_counter()
+        oracle.commit_from_values(cols, w["rate_bits"], w["cap_height"], want_leaves=True, want_digests=True, native=True)
+        dt = time.perf_counter() - t
+        best = dt if best is None else min(best, dt)
+    return best, threads, c * (1 << log_n_sample)
+
+
+def run_reference(a, w, rank):
+    """--impl reference: the reference's CPU path (port) on host cores; rank 0 only."""
+    if rank != 0:
+        return
+    sample_log_n = min(w["log_n"], 14)
+    for _ in range(max(a.warmup, 1) if a.warmup < 2 else 2):     # CPU needs no long warm-up; bound the run
+        cpu_commit_seconds(w, sample_log_n)
+    times = []
+    elems = 0
+    threads = 1
+    for _ in range(a.steps):
+        dt, threads, elems = cpu_commit_seconds(w, sample_log_n)
+        times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    val = elems / (ms * 1e-3) / 1e6
+    sample = f"2^{sample_log_n} rows x {w['cols']} cols (1/{1 << (w['log_n'] - sample_log_n)} of the rows), same rate_bits/cap"
+    line = {"metric": METRIC, "value": val, "unit": UNIT, "impl": "reference", "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u64 (Goldilocks)", "data": "synthetic",
+            "config": {"workload": workload_name(w), "note": "CPU restatement of plonky2 v0.2.0 (oracle/), OpenMP; "
+                       "the Rust reference is unbuildable here (no cargo, plonky2 not vendored)"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--log-n", type=int, default=16)
+    ap.add_argument("--cols", type=int, default=135)
+    ap.add_argument("--rate-bits", type=int, default=3)
+    ap.add_argument("--cap-height", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
+    w = workload_from_args(a)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if a.impl == "reference":
+        run_reference(a, w, rank)
+        return
+
+    import torch
+    import vectorx_b200 as vx
+    from vectorx_b200._lib import check, load, ptr, vp
+    import ctypes
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no GPU visible; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    G = world
+    ctx = vx.Context(local_rank)
+    lib = load()
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
+
+    c, log_n, rate, cap = w["cols"], w["log_n"], w["rate_bits"], w["cap_height"]
+    n = 1 << log_n
+    N = n << rate
+    elems = n * c
+    if G > 1:
+        assert G <= (1 << rate) and G <= (1 << cap), "coset sharding needs G <= 2^rate_bits and 2^cap_height"
+    cpr = (c + G - 1) // G                     # columns per rank for the iNTT stage (last rank zero-padded)
+    col_lo = rank * cpr
+    col_hi = min(c, col_lo + cpr)
+
+    # ---- inputs: N_INPUT_SETS different value matrices, pinned on the host and resident in HBM
+    host_sets, dev_sets = [], []
+    for s in range(N_INPUT_SETS):
+        full = gen_values(c, n, seed=0x5EED0001 + s)
+        mine = np.zeros((cpr, n), dtype=np.uint64)
+        mine[: col_hi - col_lo] = full[col_lo:col_hi]
+        h = torch.from_numpy(mine.view(np.int64)).pin_memory()
+        host_sets.append(h)
+        dev_sets.append(h.to(f"cuda:{local_rank}"))
+    coeff_all = torch.empty((G * cpr, n), dtype=torch.int64, device=f"cuda:{local_rank}")
+    coeff_mine = torch.empty((cpr, n), dtype=torch.int64, device=f"cuda:{local_rank}")
+    caps_loc = (1 << cap) // G
+    cap_loc = torch.empty((caps_loc, 4), dtype=torch.int64, device=f"cuda:{local_rank}")
+    cap_all = torch.empty((1 << cap, 4), dtype=torch.int64, device=f"cuda:{local_rank}")
+    cap_host = torch.empty((1 << cap, 4), dtype=torch.int64).pin_memory()
+    phase_acc = {}
+
+    def one_step(src, from_host):
+        """One commit. src: this rank's (cpr, n) values (host-pinned or device). Returns nothing; cap -> cap_host."""
+        if G == 1:
+            h = vp()
+            check(lib.vx_commit_from_values(ctx.handle, src.data_ptr(), c, log_n, rate, cap, ctypes.byref(h)),
+                  "vx_commit_from_values")
+            for k, v in ctx.phase_ms().items():
+                phase_acc[k] = phase_acc.get(k, 0.0) + v
+            if from_host:
+                check(lib.vx_batch_cap(h, cap_host.data_ptr()), "vx_batch_cap")
+            lib.vx_batch_free(h)
+            return
+        # column-sharded iNTT (device in/out through the same ABI), then NCCL all-gather of coefficients
+        check(lib.vx_ntt(ctx.handle, src.data_ptr(), coeff_mine.data_ptr(), cpr, log_n, 1, 0), "vx_ntt")
+        dist.all_gather_into_tensor(coeff_all, coeff_mine)
+        torch.cuda.current_stream().synchronize()
+        h = vp()
+        check(lib.vx_commit_from_coeffs_shard(ctx.handle, coeff_all.data_ptr(), c, log_n, rate, cap, rank, G,
+                                              ctypes.byref(h)), "vx_commit_from_coeffs_shard")
+        for k, v in ctx.phase_ms().items():
+            phase_acc[k] = phase_acc.get(k, 0.0) + v
+        check(lib.vx_batch_cap(h, cap_loc.data_ptr()), "vx_batch_cap")
+        dist.all_gather_into_tensor(cap_all, cap_loc)              # "merge the subtree caps"
+        if from_host and rank == 0:
+            cap_host.copy_(cap_all, non_blocking=False)
+        torch.cuda.current_stream().synchronize()
+        lib.vx_batch_free(h)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ctx.sync()
+
+    def timed(from_host, steps):
+        sets = host_sets if from_host else dev_sets
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for i in range(steps):
+            one_step(sets[i % N_INPUT_SETS], from_host)
+        e1.record(stream)
+        barrier()
+        wall = (time.perf_counter() - t0) * 1e3
+        dev = e0.elapsed_time(e1)
+        ms = max(dev, 0.0)
+        if G > 1:                       # NCCL legs run on torch's stream: use the wall clock of the bracketed region
+            ms = wall
+        t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), wall
+
+    # ---- warm-up, then the two timed regions
+    for i in range(a.warmup):
+        one_step(dev_sets[i % N_INPUT_SETS], False)
+    for i in range(2):
+        one_step(host_sets[i % N_INPUT_SETS], True)
+    launches0 = ctx.launch_count
+    phase_acc.clear()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    total_ms, wall_ms = timed(False, a.steps)
+    launches = ctx.launch_count - launches0
+    phases = {k: v / a.steps for k, v in phase_acc.items()}
+    e2e_ms, _ = timed(True, a.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    ms_per_step = total_ms / a.steps
+    value = elems / (ms_per_step * 1e-3) / 1e6
+    e2e_value = elems / (e2e_ms / a.steps * 1e-3) / 1e6
+
+    if dist is not None:
+        lt = torch.tensor([launches], dtype=torch.int64, device=f"cuda:{local_rank}")
+        dist.all_reduce(lt)
+        launches = int(lt.item())
+
+    if rank == 0:
+        hbm_peak, hbm_src = load_peaks()
+        int_peak, int_src = load_int_peak()
+        # dominant kernel: leaf hashing (one launch per commit per rank)
+        rows_loc = N // G
+        leaf_ms = phases.get("leaf_hash", float("nan"))
+        perms = rows_loc * ((c + 7) // 8) if c > 4 else 0
+        leaf_bytes = 8 * rows_loc * c + 32 * rows_loc                 # read the LDE rows once, write digests
+        leaf_gops = perms * IMADS_PER_PERMUTATION / (leaf_ms * 1e-3) / 1e9 if leaf_ms > 0 else None
+        leaf_gbs = leaf_bytes / (leaf_ms * 1e-3) / 1e9 if leaf_ms > 0 else None
+        ntt_ms = phases.get("intt", 0.0) + phases.get("lde", 0.0)
+        ntt_bytes = (8 * n * c * 2 if G == 1 else 0) + 8 * n * c + 8 * rows_loc * c   # values->coeffs, coeffs->LDE
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "leaf_hash_traffic_r01.json")) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        roofline = {
+            "kernel": "leaf_hash_kernel<col_major> (Poseidon sponge, one thread per LDE row)",
+            "bound": "int_alu",
+            "achieved": leaf_gops, "peak": int_peak, "unit": "G 32x32 mul-add/s",
+            "frac": (leaf_gops / int_peak) if leaf_gops else None,
+            "peak_source": int_src,
+            "algorithmic_ops_per_launch": perms * IMADS_PER_PERMUTATION,
+            "ms_per_launch": leaf_ms,
+            "traffic": traffic,
+            "hbm": {"bound": "hbm", "achieved": leaf_gbs, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": (leaf_gbs / hbm_peak) if leaf_gbs else None, "algorithmic_bytes_per_launch": leaf_bytes,
+                    "peak_source": hbm_src},
+            "ntt_passes": {"bound": "hbm", "ms": ntt_ms, "algorithmic_bytes": ntt_bytes,
+                           "achieved": ntt_bytes / (ntt_ms * 1e-3) / 1e9 if ntt_ms > 0 else None, "peak": hbm_peak,
+                           "unit": "GB/s", "frac": (ntt_bytes / (ntt_ms * 1e-3) / 1e9 / hbm_peak) if ntt_ms > 0 else None},
+            "phase_ms": phases,
+        }
+        cpu = None
+        if G == 1 and not a.no_cpu_baseline:
+            dt, threads, celems = cpu_commit_seconds(w, min(log_n, 16))
+            cpu = {"value": celems / dt / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": f"one full commit of 2^{min(log_n, 16)} rows x {c} cols ({dt:.1f} s), oracle/ built -march=native, OpenMP"}
+        h2d = cpr * n * 8 * G
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": G, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u64 (Goldilocks field, 32-bit IMAD limbs)", "data": "synthetic",
+            "config": {"workload": workload_name(w),
+                       "parallelism": "single GPU" if G == 1 else f"coset-sharded x{G}: column-sharded iNTT + NCCL all-gather of coefficients + per-rank cosets/cap subtrees",
+                       "l2": f"inputs rotate over {N_INPUT_SETS} sets ({N_INPUT_SETS * elems * 8 / 1e6:.0f} MB) and each step streams a {8 * N * c / 1e6:.0f} MB LDE, both > 126 MB L2",
+                       "elements": "n*c input trace elements per commit"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": (1 << cap) * 32,
+                    "ms_per_step": e2e_ms / a.steps},
+            "gpu_launches": launches,
+            "wall_ms_per_step": wall_ms / a.steps,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

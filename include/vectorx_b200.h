@@ -47,6 +47,10 @@ int32_t vx_device_sync(vx_ctx* ctx);
 void* vx_ctx_stream(vx_ctx* ctx);
 /* number of kernels this library has launched on this context so far */
 uint64_t vx_ctx_launch_count(vx_ctx* ctx);
+/* device time (ms, CUDA events on the context stream) of the phases of the most recent commit on
+ * this context: out[0] staging copy, [1] iNTT, [2] coset LDE, [3] leaf hashing, [4] interior levels.
+ * Plays the role of plonky2's TimingTree scopes ("IFFT", "FFT + blinding", "build Merkle tree"). */
+int32_t vx_ctx_phase_ms(vx_ctx* ctx, float out[5]);
 
 /* ---- PolynomialBatch (plonky2 fri/oracle.rs) ------------------------------------------------
  * vx_commit_from_values replaces PolynomialBatch::from_values(values, rate_bits, blinding=false,
@@ -62,6 +66,16 @@ int32_t vx_commit_from_values(vx_ctx* ctx, const uint64_t* cols, uint32_t c, uin
                               uint32_t rate_bits, uint32_t cap_height, vx_batch** out);
 int32_t vx_commit_from_coeffs(vx_ctx* ctx, const uint64_t* coeffs, uint32_t c, uint32_t log_n,
                               uint32_t rate_bits, uint32_t cap_height, vx_batch** out);
+/* Multi-GPU sharding of one commit (coset partition): shard s of S (S a power of two,
+ * S <= 2^rate_bits, S <= 2^cap_height) holds leaves [s*N/S, (s+1)*N/S) -- whole cosets of the LDE
+ * and whole cap subtrees -- computed from ALL c coefficient columns with no further communication.
+ * Leaf indices passed to vx_batch_leaves / vx_batch_merkle_paths on a shard are LOCAL (0 .. N/S);
+ * vx_batch_cap returns the shard's 2^cap_height/S cap entries. */
+int32_t vx_commit_from_coeffs_shard(vx_ctx* ctx, const uint64_t* coeffs, uint32_t c, uint32_t log_n,
+                                    uint32_t rate_bits, uint32_t cap_height, uint32_t shard_index,
+                                    uint32_t shard_count, vx_batch** out);
+/* out[0] = first global leaf held, out[1] = leaves held, out[2] = cap entries held */
+int32_t vx_batch_shard(const vx_batch* b, uint64_t out[3]);
 void vx_batch_free(vx_batch* b);
 /* shape: out[0]=c, out[1]=log_n, out[2]=rate_bits, out[3]=cap_height */
 int32_t vx_batch_shape(const vx_batch* b, uint32_t out[4]);

@@ -211,3 +211,23 @@ def test_error_behaviour(ctx):
     b = vx.PolynomialBatch.from_values(cols, 1, False, 1)
     with pytest.raises(vx.VxError):
         b.leaves([16])                                      # out of range
+
+
+@pytest.mark.parametrize("shards", [2, 4, 8])
+def test_sharded_commit_matches_whole(ctx, shards):
+    """SURVEY 8e coset partition: the shards' leaves / digests / caps concatenate to the 1-GPU commit."""
+    c, log_n, rate, cap = 21, 9, 3, 4
+    coeffs = oracle.random_field((c, 1 << log_n), seed=55)
+    want = oracle.commit_from_coeffs(coeffs, rate, cap)
+    N = (1 << log_n) << rate
+    caps, leaves, digests = [], [], []
+    for s in range(shards):
+        b = vx.PolynomialBatch.from_coeffs_shard(coeffs, rate, cap, s, shards)
+        assert (b.leaf_first, b.num_leaves, b.num_caps) == (s * N // shards, N // shards, 16 // shards)
+        lv, dg = b.download()
+        caps.append(b.cap.hashes); leaves.append(lv); digests.append(dg)
+        i = 5
+        assert np.array_equal(b.prove([i])[0], oracle.merkle_prove(want["digests"], N, cap, b.leaf_first + i))
+    assert np.array_equal(np.concatenate(caps), want["cap"])
+    assert np.array_equal(np.concatenate(leaves), want["leaves"])
+    assert np.array_equal(np.concatenate(digests), want["digests"])

@@ -26,6 +26,9 @@ SIGNATURES = {
     "vx_device_sync": (c_i32, [vp]),
     "vx_ctx_stream": (vp, [vp]),
     "vx_ctx_launch_count": (c_u64, [vp]),
+    "vx_ctx_phase_ms": (c_i32, [vp, ctypes.POINTER(ctypes.c_float)]),
+    "vx_commit_from_coeffs_shard": (c_i32, [vp, vp, c_u32, c_u32, c_u32, c_u32, c_u32, c_u32, ctypes.POINTER(vp)]),
+    "vx_batch_shard": (c_i32, [vp, u64p]),
     "vx_commit_from_values": (c_i32, [vp, vp, c_u32, c_u32, c_u32, c_u32, ctypes.POINTER(vp)]),
     "vx_commit_from_coeffs": (c_i32, [vp, vp, c_u32, c_u32, c_u32, c_u32, ctypes.POINTER(vp)]),
     "vx_batch_free": (None, [vp]),
@@ -111,6 +114,11 @@ class Context:
     @property
     def stream(self) -> int:
         return load().vx_ctx_stream(self._h) or 0
+
+    def phase_ms(self) -> dict:
+        out = (ctypes.c_float * 5)()
+        check(load().vx_ctx_phase_ms(self._h, out), "vx_ctx_phase_ms")
+        return dict(zip(("stage", "intt", "lde", "leaf_hash", "tree_levels"), (float(x) for x in out)))
 
     @property
     def launch_count(self) -> int:

@@ -70,6 +70,7 @@ extern "C" int32_t vx_ctx_create(int32_t device, vx_ctx** out) {
         uint64_t thresh = UINT64_MAX;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh);
     }
+    for (int i = 0; i < VX_NUM_PHASE_EVENTS; i++) cudaEventCreate(&ctx->ev[i]);
     int32_t r = poseidon_module_init(ctx);
     if (r == VX_OK) r = ntt_module_init(ctx);
     if (r != VX_OK) { vx_ctx_destroy(ctx); return r; }
@@ -82,6 +83,7 @@ extern "C" void vx_ctx_destroy(vx_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     ntt_module_destroy(ctx);
+    for (int i = 0; i < VX_NUM_PHASE_EVENTS; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -89,6 +91,16 @@ extern "C" void vx_ctx_destroy(vx_ctx* ctx) {
 extern "C" int32_t vx_device_sync(vx_ctx* ctx) {
     VX_REQUIRE(ctx, "vx_device_sync: ctx is NULL");
     VX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VX_OK;
+}
+extern "C" int32_t vx_ctx_phase_ms(vx_ctx* ctx, float out[VX_NUM_PHASE_EVENTS - 1]) {
+    VX_REQUIRE(ctx && out, "vx_ctx_phase_ms: NULL argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    for (int i = 0; i + 1 < VX_NUM_PHASE_EVENTS; i++) {
+        out[i] = 0.f;
+        cudaError_t e = cudaEventElapsedTime(&out[i], ctx->ev[i], ctx->ev[i + 1]);
+        if (e != cudaSuccess) { cudaGetLastError(); out[i] = -1.f; }
+    }
     return VX_OK;
 }
 extern "C" void* vx_ctx_stream(vx_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
@@ -113,59 +125,96 @@ static int32_t copy_out(vx_ctx* ctx, u64* dst, const u64* src_dev, size_t bytes)
 struct vx_batch {
     vx_ctx* ctx;
     uint32_t c, log_n, rate_bits, cap_height;
+    uint32_t blk_first, blk_count;      // leaf blocks (cosets) held: all 2^rate_bits unless sharded
     DevBuf coeffs;    // c x n
-    DevBuf lde;       // c x N column-major, leaf order
-    DevBuf digests;   // 2 (N - 2^cap) x 4
-    DevBuf cap;       // 2^cap x 4
+    DevBuf lde;       // c x N_loc column-major, leaf order
+    DevBuf digests;   // 2 (N_loc - caps_loc) x 4
+    DevBuf cap;       // caps_loc x 4
     uint64_t n() const { return 1ULL << log_n; }
     uint64_t N() const { return 1ULL << (log_n + rate_bits); }
+    uint64_t N_loc() const { return (uint64_t)blk_count << log_n; }
+    uint64_t leaf_first() const { return (uint64_t)blk_first << log_n; }
+    uint32_t shard_bits() const { return rate_bits - ilog2(blk_count); }   // log2(number of shards)
+    uint32_t cap_height_loc() const { return cap_height - shard_bits(); }
 };
 
+#define EV(ctx, i) VX_CUDA(cudaEventRecord((ctx)->ev[i], (ctx)->stream))
+
+static int32_t commit_run(vx_ctx* ctx, vx_batch* b, const u64* src, bool is_values) {
+    const uint32_t c = b->c;
+    const uint64_t n = b->n(), N_loc = b->N_loc();
+    const size_t coeff_bytes = (size_t)c * n * sizeof(u64);
+    const uint64_t caps_loc = 1ULL << b->cap_height_loc();
+    VX_CHECK(b->coeffs.alloc(coeff_bytes, ctx->stream));
+    VX_CHECK(b->lde.alloc((size_t)c * N_loc * sizeof(u64), ctx->stream));
+    VX_CHECK(b->digests.alloc((size_t)2 * (N_loc - caps_loc) * 4 * sizeof(u64), ctx->stream));
+    VX_CHECK(b->cap.alloc((size_t)caps_loc * 4 * sizeof(u64), ctx->stream));
+    EV(ctx, VX_EV_START);
+    if (is_values) {
+        // stage the values in the (not yet used) LDE buffer when it is big enough, transform, emit coefficients
+        DevBuf stage;
+        u64* work = b->lde.p;
+        if (b->lde.bytes < coeff_bytes) { VX_CHECK(stage.alloc(coeff_bytes, ctx->stream)); work = stage.p; }
+        VX_CUDA(cudaMemcpyAsync(work, src, coeff_bytes, cudaMemcpyDefault, ctx->stream));
+        EV(ctx, VX_EV_STAGED);
+        VX_CHECK(intt_batch(ctx, work, b->coeffs.p, c, b->log_n));
+    } else {
+        VX_CUDA(cudaMemcpyAsync(b->coeffs.p, src, coeff_bytes, cudaMemcpyDefault, ctx->stream));
+        EV(ctx, VX_EV_STAGED);
+    }
+    EV(ctx, VX_EV_INTT);
+    VX_CHECK(lde_batch(ctx, b->coeffs.p, b->lde.p, c, b->log_n, b->rate_bits, b->blk_first, b->blk_count));
+    EV(ctx, VX_EV_LDE);
+    VX_CHECK(merkle_build_device(ctx, b->lde.p, true, N_loc, N_loc, c, b->cap_height_loc(), b->digests.p, b->cap.p,
+                                 ctx->ev[VX_EV_LEAF]));
+    EV(ctx, VX_EV_TREE);
+    VX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VX_OK;
+}
+
 static int32_t commit_impl(vx_ctx* ctx, const u64* src, bool is_values, uint32_t c, uint32_t log_n,
-                           uint32_t rate_bits, uint32_t cap_height, vx_batch** out) {
+                           uint32_t rate_bits, uint32_t cap_height, uint32_t shard_index, uint32_t shard_count,
+                           vx_batch** out) {
     VX_REQUIRE(ctx && src && out, "commit: NULL argument");
     *out = nullptr;
     VX_REQUIRE(c >= 1 && c < 16384, "commit: column count %u out of range", c);
     VX_REQUIRE(log_n + rate_bits <= 26, "commit: 2^%u LDE points unsupported", log_n + rate_bits);
     VX_REQUIRE(cap_height <= log_n + rate_bits, "commit: cap_height %u exceeds tree height %u", cap_height,
                log_n + rate_bits);
+    VX_REQUIRE(shard_count >= 1 && (shard_count & (shard_count - 1)) == 0 && shard_index < shard_count,
+               "commit: bad shard %u of %u", shard_index, shard_count);
+    uint32_t sbits = ilog2(shard_count);
+    VX_REQUIRE(sbits <= rate_bits && sbits <= cap_height,
+               "commit: %u shards need rate_bits >= %u and cap_height >= %u (whole cosets and whole cap subtrees per shard)",
+               shard_count, sbits, sbits);
     CtxGuard g(ctx);
     vx_batch* b = new (std::nothrow) vx_batch();
     if (!b) return VX_ENOMEM;
     b->ctx = ctx; b->c = c; b->log_n = log_n; b->rate_bits = rate_bits; b->cap_height = cap_height;
-    const uint64_t n = b->n(), N = b->N();
-    const size_t coeff_bytes = (size_t)c * n * sizeof(u64);
-    int32_t r = b->coeffs.alloc(coeff_bytes, ctx->stream);
-    if (r == VX_OK) r = b->lde.alloc((size_t)c * N * sizeof(u64), ctx->stream);
-    if (r == VX_OK) r = b->digests.alloc((size_t)2 * (N - (1ULL << cap_height)) * 4 * sizeof(u64), ctx->stream);
-    if (r == VX_OK) r = b->cap.alloc((size_t)(1ULL << cap_height) * 4 * sizeof(u64), ctx->stream);
-    if (r == VX_OK) {
-        if (is_values) {
-            // stage the values in the (not yet used) LDE buffer, transform there, emit coefficients
-            r = copy_in(ctx, b->lde.p, src, coeff_bytes);
-            if (r == VX_OK) r = intt_batch(ctx, b->lde.p, b->coeffs.p, c, log_n);
-        } else {
-            r = copy_in(ctx, b->coeffs.p, src, coeff_bytes);
-        }
+    b->blk_count = (1u << rate_bits) >> sbits;
+    b->blk_first = shard_index * b->blk_count;
+    int32_t r = commit_run(ctx, b, src, is_values);
+    if (r != VX_OK) {
+        cudaStreamSynchronize(ctx->stream);
+        delete b;
+        return r;
     }
-    if (r == VX_OK) r = lde_batch(ctx, b->coeffs.p, b->lde.p, c, log_n, rate_bits);
-    if (r == VX_OK) r = merkle_build_device(ctx, b->lde.p, true, N, N, c, cap_height, b->digests.p, b->cap.p);
-    if (r == VX_OK) {
-        cudaError_t e = cudaStreamSynchronize(ctx->stream);
-        if (e != cudaSuccess) { vx_set_error("commit: %s", cudaGetErrorString(e)); r = VX_ECUDA; }
-    }
-    if (r != VX_OK) { delete b; return r; }
     *out = b;
     return VX_OK;
 }
 
 extern "C" int32_t vx_commit_from_values(vx_ctx* ctx, const uint64_t* cols, uint32_t c, uint32_t log_n,
                                          uint32_t rate_bits, uint32_t cap_height, vx_batch** out) {
-    return commit_impl(ctx, (const u64*)cols, true, c, log_n, rate_bits, cap_height, out);
+    return commit_impl(ctx, (const u64*)cols, true, c, log_n, rate_bits, cap_height, 0, 1, out);
 }
 extern "C" int32_t vx_commit_from_coeffs(vx_ctx* ctx, const uint64_t* coeffs, uint32_t c, uint32_t log_n,
                                          uint32_t rate_bits, uint32_t cap_height, vx_batch** out) {
-    return commit_impl(ctx, (const u64*)coeffs, false, c, log_n, rate_bits, cap_height, out);
+    return commit_impl(ctx, (const u64*)coeffs, false, c, log_n, rate_bits, cap_height, 0, 1, out);
+}
+extern "C" int32_t vx_commit_from_coeffs_shard(vx_ctx* ctx, const uint64_t* coeffs, uint32_t c, uint32_t log_n,
+                                               uint32_t rate_bits, uint32_t cap_height, uint32_t shard_index,
+                                               uint32_t shard_count, vx_batch** out) {
+    return commit_impl(ctx, (const u64*)coeffs, false, c, log_n, rate_bits, cap_height, shard_index, shard_count, out);
 }
 
 extern "C" void vx_batch_free(vx_batch* b) {
@@ -180,6 +229,12 @@ extern "C" void vx_batch_free(vx_batch* b) {
 extern "C" int32_t vx_batch_shape(const vx_batch* b, uint32_t out[4]) {
     VX_REQUIRE(b && out, "vx_batch_shape: NULL argument");
     out[0] = b->c; out[1] = b->log_n; out[2] = b->rate_bits; out[3] = b->cap_height;
+    return VX_OK;
+}
+
+extern "C" int32_t vx_batch_shard(const vx_batch* b, uint64_t out[3]) {
+    VX_REQUIRE(b && out, "vx_batch_shard: NULL argument");
+    out[0] = b->leaf_first(); out[1] = b->N_loc(); out[2] = 1ULL << b->cap_height_loc();
     return VX_OK;
 }
 
@@ -238,13 +293,13 @@ static int32_t query_paths(vx_ctx* ctx, const u64* digests, uint64_t N, uint32_t
 extern "C" int32_t vx_batch_leaves(vx_batch* b, const uint64_t* idx, uint32_t k, uint64_t* rows_out) {
     VX_REQUIRE(b && (k == 0 || (idx && rows_out)), "vx_batch_leaves: NULL argument");
     CtxGuard g(b->ctx);
-    return query_rows(b->ctx, b->lde.p, true, b->N(), b->c, b->N(), idx, k, rows_out);
+    return query_rows(b->ctx, b->lde.p, true, b->N_loc(), b->c, b->N_loc(), idx, k, rows_out);
 }
 
 extern "C" int32_t vx_batch_merkle_paths(vx_batch* b, const uint64_t* idx, uint32_t k, uint64_t* siblings_out) {
     VX_REQUIRE(b && (k == 0 || (idx && siblings_out)), "vx_batch_merkle_paths: NULL argument");
     CtxGuard g(b->ctx);
-    return query_paths(b->ctx, b->digests.p, b->N(), b->cap_height, idx, k, siblings_out);
+    return query_paths(b->ctx, b->digests.p, b->N_loc(), b->cap_height_loc(), idx, k, siblings_out);
 }
 
 extern "C" int32_t vx_batch_download(vx_batch* b, uint64_t* leaves_out, uint64_t* digests_out) {
@@ -254,7 +309,7 @@ extern "C" int32_t vx_batch_download(vx_batch* b, uint64_t* leaves_out, uint64_t
     if (leaves_out) {
         DevBuf rows;
         VX_CHECK(rows.alloc(b->lde.bytes, ctx->stream));
-        VX_CHECK(transpose_to_rows_device(ctx, b->lde.p, b->N(), b->N(), b->c, rows.p));
+        VX_CHECK(transpose_to_rows_device(ctx, b->lde.p, b->N_loc(), b->N_loc(), b->c, rows.p));
         VX_CHECK(copy_out(ctx, (u64*)leaves_out, rows.p, rows.bytes));
         VX_CUDA(cudaStreamSynchronize(ctx->stream));
     }

@@ -45,6 +45,9 @@ void vx_set_error(const char* fmt, ...);
 //   wi_lo/wi_hi : same for W^-1
 //   g_lo/g_hi : powers of the coset shift g: g^m = g_hi[m>>12] * g_lo[m&0xfff]  (m < 2^24)
 //   roots12 / iroots12 : w_4096^e, e < 2048, for the in-shared-memory sub-transforms
+// commit phases, bracketed by CUDA events on the context stream
+enum { VX_EV_START = 0, VX_EV_STAGED, VX_EV_INTT, VX_EV_LDE, VX_EV_LEAF, VX_EV_TREE, VX_NUM_PHASE_EVENTS };
+
 struct vx_ctx {
     int device = 0;
     int sm_count = 0;
@@ -54,6 +57,8 @@ struct vx_ctx {
     u64 *w_lo = nullptr, *w_hi = nullptr, *wi_lo = nullptr, *wi_hi = nullptr;
     u64 *g_lo = nullptr, *g_hi = nullptr, *gi_lo = nullptr, *gi_hi = nullptr;
     u64 *roots12 = nullptr, *iroots12 = nullptr;
+    // phase events of the most recent commit on this context (see vx_ctx_phase_ms)
+    cudaEvent_t ev[VX_NUM_PHASE_EVENTS] = {};
 };
 
 struct TwiddleView {     // passed by value to kernels
@@ -104,7 +109,8 @@ void poseidon_round_constants_host(u64 out[360]);          // merkle.cu: ChaCha8
 // otherwise row-major at leaves[row * c + col].  digests: plonky2 interleaved layout (device),
 // cap: 2^cap_height x 4 (device).
 int32_t merkle_build_device(vx_ctx* ctx, const u64* leaves, bool col_major, uint64_t stride, uint64_t N,
-                            uint32_t c, uint32_t cap_height, u64* digests, u64* cap);
+                            uint32_t c, uint32_t cap_height, u64* digests, u64* cap,
+                            cudaEvent_t after_leaves = nullptr);
 int32_t merkle_paths_device(vx_ctx* ctx, const u64* digests, uint64_t N, uint32_t cap_height,
                             const u64* idx_dev, uint32_t k, u64* siblings_dev);
 int32_t gather_rows_device(vx_ctx* ctx, const u64* leaves, bool col_major, uint64_t stride, uint32_t c,
@@ -123,7 +129,10 @@ int32_t ntt_dif_inplace(vx_ctx* ctx, u64* data, uint64_t count, uint32_t log_n, 
 // values (c x n natural) -> coefficients (c x n natural): plonky2 ifft. `work` (c x n) is clobbered.
 int32_t intt_batch(vx_ctx* ctx, u64* work, u64* coeffs_out, uint32_t c, uint32_t log_n);
 // coefficients (c x n natural) -> LDE on coset g*<w_N>, leaf (bit-reversed) order, c x N column-major.
-int32_t lde_batch(vx_ctx* ctx, const u64* coeffs, u64* lde_out, uint32_t c, uint32_t log_n, uint32_t rate_bits);
+// Only leaf blocks [blk_first, blk_first + blk_count) of the 2^rate_bits cosets are produced (a block
+// is one coset = n leaves); lde_out is c x (blk_count * n).
+int32_t lde_batch(vx_ctx* ctx, const u64* coeffs, u64* lde_out, uint32_t c, uint32_t log_n, uint32_t rate_bits,
+                  uint32_t blk_first, uint32_t blk_count);
 // generic natural-order transform used by vx_ntt (tests, FRI layers)
 int32_t ntt_natural(vx_ctx* ctx, const u64* in, u64* out, uint32_t c, uint32_t log_n, bool inverse,
                     uint64_t coset_shift);

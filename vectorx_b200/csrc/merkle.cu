@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(128) level_hash_kernel(u64* __restrict__ diges
 }
 
 int32_t merkle_build_device(vx_ctx* ctx, const u64* leaves, bool col_major, uint64_t stride, uint64_t N,
-                            uint32_t c, uint32_t cap_height, u64* digests, u64* cap) {
+                            uint32_t c, uint32_t cap_height, u64* digests, u64* cap, cudaEvent_t after_leaves) {
     uint32_t log_N = ilog2(N);
     VX_REQUIRE((1ULL << log_N) == N, "merkle: leaf count %llu is not a power of two", (unsigned long long)N);
     VX_REQUIRE(cap_height <= log_N, "merkle: cap_height %u > log2(leaves) %u", cap_height, log_N);
@@ -151,6 +151,7 @@ int32_t merkle_build_device(vx_ctx* ctx, const u64* leaves, bool col_major, uint
     else
         leaf_hash_kernel<false><<<blocks, 128, 0, ctx->stream>>>(leaves, stride, N, c, sub_bits, digests, cap);
     VX_LAUNCH_COUNT(ctx, 1);
+    if (after_leaves) VX_CUDA(cudaEventRecord(after_leaves, ctx->stream));
     for (uint32_t lvl = 0; lvl < sub_bits; lvl++) {
         uint64_t total_pairs = N >> (lvl + 1);
         unsigned b = (unsigned)((total_pairs + 127) / 128);

@@ -203,10 +203,10 @@ int32_t intt_batch(vx_ctx* ctx, u64* work, u64* coeffs_out, uint32_t c, uint32_t
     return VX_OK;
 }
 
-// lde[col][bitrev_r(rho) * n + m] = coeffs[col][m] * g^m * w_N^(rho m)
+// lde[col][b * n + m] = coeffs[col][m] * g^m * w_N^(rho m),  rho = bitrev_r(blk_first + b), b < blk_count
 __global__ void lde_scale_kernel(const u64* __restrict__ coeffs, u64* __restrict__ lde, uint32_t log_n,
-                                 uint32_t rate_bits, const u64* __restrict__ g_lo, const u64* __restrict__ g_hi,
-                                 TwiddleView tw) {
+                                 uint32_t rate_bits, uint32_t blk_first, uint32_t blk_count,
+                                 const u64* __restrict__ g_lo, const u64* __restrict__ g_hi, TwiddleView tw) {
     uint64_t n = 1ULL << log_n;
     uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= n) return;
@@ -215,26 +215,26 @@ __global__ void lde_scale_kernel(const u64* __restrict__ coeffs, u64* __restrict
     u64 x = coeffs[((uint64_t)col << log_n) + m];
     u64 gm = gl_mul(__ldg(g_hi + (m >> 12)), __ldg(g_lo + (m & 4095)));
     x = gl_mul(x, gm);
-    u64 step = tw_pow(tw, (u32)(m << (32 - log_N)));          // w_N^m
-    u64* dst = lde + (((uint64_t)col << log_N)) + m;
-    u64 f = x;
-    for (uint32_t rho = 0; rho < (1u << rate_bits); rho++) {
-        uint32_t blk = __brev(rho) >> (32 - rate_bits);
-        if (rate_bits == 0) blk = 0;
-        dst[(uint64_t)blk << log_n] = gl_canon(f);
-        f = gl_mul(f, step);
+    u64* dst = lde + (uint64_t)col * blk_count * n + m;
+    for (uint32_t b = 0; b < blk_count; b++) {
+        uint32_t rho = rate_bits ? (__brev(blk_first + b) >> (32 - rate_bits)) : 0;
+        u32 E = ((u32)m * rho) << (32 - log_N);            // (rho m mod N) scaled to a W exponent
+        u64 f = E ? gl_mul(x, tw_pow(tw, E)) : x;
+        dst[(uint64_t)b << log_n] = gl_canon(f);
     }
 }
 
-int32_t lde_batch(vx_ctx* ctx, const u64* coeffs, u64* lde_out, uint32_t c, uint32_t log_n, uint32_t rate_bits) {
+int32_t lde_batch(vx_ctx* ctx, const u64* coeffs, u64* lde_out, uint32_t c, uint32_t log_n, uint32_t rate_bits,
+                  uint32_t blk_first, uint32_t blk_count) {
     VX_REQUIRE(log_n + rate_bits <= 26, "lde: 2^%u points exceeds the coset table (2^26)", log_n + rate_bits);
+    VX_REQUIRE(blk_count >= 1 && blk_first + blk_count <= (1u << rate_bits), "lde: coset block range out of bounds");
     uint64_t n = 1ULL << log_n;
     dim3 grid((unsigned)((n + 255) / 256), c);
-    lde_scale_kernel<<<grid, 256, 0, ctx->stream>>>(coeffs, lde_out, log_n, rate_bits, ctx->g_lo, ctx->g_hi,
-                                                    tw_view(ctx, false));
+    lde_scale_kernel<<<grid, 256, 0, ctx->stream>>>(coeffs, lde_out, log_n, rate_bits, blk_first, blk_count,
+                                                    ctx->g_lo, ctx->g_hi, tw_view(ctx, false));
     VX_LAUNCH_COUNT(ctx, 1);
     VX_CUDA(cudaGetLastError());
-    return ntt_dif_inplace(ctx, lde_out, (uint64_t)c << rate_bits, log_n, false);
+    return ntt_dif_inplace(ctx, lde_out, (uint64_t)c * blk_count, log_n, false);
 }
 
 // x[m] *= shift^m (arbitrary shift; used by the generic vx_ntt entry point and FRI layers)

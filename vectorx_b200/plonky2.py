@@ -126,6 +126,9 @@ class PolynomialBatch:
         self.num_polys, self.degree_log, self.rate_bits, self.cap_height = (int(x) for x in shape)
         self.blinding = False
         self._cap = None
+        sh = (ctypes.c_uint64 * 3)()
+        check(load().vx_batch_shard(handle, sh), "vx_batch_shard")
+        self.leaf_first, self.num_leaves, self.num_caps = (int(x) for x in sh)   # == (0, N, 2^cap) unless sharded
 
     @classmethod
     def from_values(cls, values, rate_bits: int, blinding: bool, cap_height: int, timing=None,
@@ -137,6 +140,20 @@ class PolynomialBatch:
     def from_coeffs(cls, polynomials, rate_bits: int, blinding: bool, cap_height: int, timing=None,
                     fft_root_table=None, ctx: Context | None = None) -> "PolynomialBatch":
         return cls._commit("vx_commit_from_coeffs", polynomials, rate_bits, blinding, cap_height, ctx)
+
+    @classmethod
+    def from_coeffs_shard(cls, polynomials, rate_bits: int, cap_height: int, shard_index: int, shard_count: int,
+                          ctx: Context | None = None) -> "PolynomialBatch":
+        """One GPU's share of a commit: leaves [s*N/S, (s+1)*N/S) from all coefficient columns."""
+        ctx = ctx or default_context()
+        c, n = int(polynomials.shape[0]), int(polynomials.shape[1])
+        if isinstance(polynomials, np.ndarray):
+            polynomials = np.ascontiguousarray(polynomials, dtype=np.uint64)
+        h = vp()
+        check(load().vx_commit_from_coeffs_shard(ctx.handle, ptr(polynomials), c, n.bit_length() - 1, rate_bits,
+                                                 cap_height, shard_index, shard_count, ctypes.byref(h)),
+              "vx_commit_from_coeffs_shard")
+        return cls(ctx, h)
 
     @classmethod
     def _commit(cls, fn, data, rate_bits, blinding, cap_height, ctx):
@@ -165,7 +182,7 @@ class PolynomialBatch:
     @property
     def cap(self) -> MerkleCap:
         if self._cap is None:
-            out = np.zeros((1 << self.cap_height, 4), dtype=np.uint64)
+            out = np.zeros((self.num_caps, 4), dtype=np.uint64)
             check(load().vx_batch_cap(self._h, ptr(out)), "vx_batch_cap")
             self._cap = MerkleCap(out)
         return self._cap
@@ -191,16 +208,16 @@ class PolynomialBatch:
     def prove(self, idx) -> np.ndarray:
         """merkle_tree.prove(i).siblings for every i in idx: (k, depth, 4)."""
         idx = np.ascontiguousarray(np.array(idx, dtype=np.uint64))
-        depth = self.degree_log + self.rate_bits - self.cap_height
+        depth = (self.num_leaves // self.num_caps).bit_length() - 1
         out = np.zeros((idx.size, depth, 4), dtype=np.uint64)
         check(load().vx_batch_merkle_paths(self._h, ptr(idx), idx.size, ptr(out)), "vx_batch_merkle_paths")
         return out
 
     def download(self, leaves: bool = True, digests: bool = True):
         """Full MerkleTree { leaves, digests } in plonky2's host layout."""
-        N = self.lde_size
+        N = self.num_leaves
         lv = np.zeros((N, self.num_polys), dtype=np.uint64) if leaves else None
-        dg = np.zeros((max(2 * (N - (1 << self.cap_height)), 0), 4), dtype=np.uint64) if digests else None
+        dg = np.zeros((max(2 * (N - self.num_caps), 0), 4), dtype=np.uint64) if digests else None
         check(load().vx_batch_download(self._h, ptr(lv) if leaves else None,
                                        ptr(dg) if (digests and dg.size) else None), "vx_batch_download")
         return lv, dg
