@@ -77,6 +77,105 @@ GL_D u64 gl_reduce96(u64 lo, u32 hi) {
     return r;
 }
 
+// ---- carry-flag versions (PTX add.cc / subc chains): the conditional +-eps fix-ups come straight
+// from the carry flag instead of 64-bit compares + selects, which halves the ALU-pipe work.
+// x = x3*2^96 + x2*2^64 + x1*2^32 + x0  ->  some u64 representative of x mod p
+GL_D u64 gl_reduce128_cc(u32 x0, u32 x1, u32 x2, u32 x3) {
+    u32 r0, r1;
+    asm("{\n\t"
+        ".reg .u32 t0, t1, m, c;\n\t"
+        "sub.cc.u32 t0, %2, %5;\n\t"              // t = (x1:x0) - x3
+        "subc.cc.u32 t1, %3, 0;\n\t"
+        "subc.u32 m, 0, 0;\n\t"                   // m = borrow ? 0xffffffff : 0   (== eps when set)
+        "sub.cc.u32 t0, t0, m;\n\t"               // borrow: t -= eps  (i.e. += p mod 2^64)
+        "subc.u32 t1, t1, 0;\n\t"
+        "mad.lo.cc.u32 t0, %4, 0xffffffff, t0;\n\t"   // t += x2 * eps
+        "madc.hi.cc.u32 t1, %4, 0xffffffff, t1;\n\t"
+        "addc.u32 c, 0, 0;\n\t"                   // c = carry (0/1)
+        "mad.lo.cc.u32 %0, c, 0xffffffff, t0;\n\t"    // carry: += eps (cannot carry again)
+        "addc.u32 %1, t1, 0;\n\t"
+        "}"
+        : "=r"(r0), "=r"(r1)
+        : "r"(x0), "r"(x1), "r"(x2), "r"(x3));
+    return pack64(r0, r1);
+}
+
+// a * b + c (all u64, any representatives) reduced: one 128-bit product, the addend folded into the
+// carry chain, one reduction.  (2^64-1)^2 + 2^64-1 < 2^128, so no overflow.
+GL_D u64 gl_mul_add_cc(u64 a, u64 b, u64 c) {
+    u32 a0 = lo32(a), a1 = hi32(a), b0 = lo32(b), b1 = hi32(b), c0 = lo32(c), c1 = hi32(c);
+    u32 r0, r1, r2, r3;
+    asm("{\n\t"
+        "mad.lo.cc.u32 %0, %4, %6, %8;\n\t"       // (r1:r0) = a0*b0 + c0   [+ carry into r1]
+        "madc.hi.cc.u32 %1, %4, %6, %9;\n\t"      //          + c1 << 32
+        "addc.u32 %2, 0, 0;\n\t"
+        "mad.lo.cc.u32 %1, %4, %7, %1;\n\t"       // += a0*b1 << 32
+        "madc.hi.cc.u32 %2, %4, %7, %2;\n\t"
+        "addc.u32 %3, 0, 0;\n\t"
+        "mad.lo.cc.u32 %1, %5, %6, %1;\n\t"       // += a1*b0 << 32
+        "madc.hi.cc.u32 %2, %5, %6, %2;\n\t"
+        "addc.u32 %3, %3, 0;\n\t"
+        "mad.lo.cc.u32 %2, %5, %7, %2;\n\t"       // += a1*b1 << 64
+        "madc.hi.u32 %3, %5, %7, %3;\n\t"
+        "}"
+        : "=&r"(r0), "=&r"(r1), "=&r"(r2), "=&r"(r3)
+        : "r"(a0), "r"(a1), "r"(b0), "r"(b1), "r"(c0), "r"(c1));
+    return gl_reduce128_cc(r0, r1, r2, r3);
+}
+
+GL_D void gl_mul128_cc(u64 a, u64 b, u32& r0, u32& r1, u32& r2, u32& r3) {
+    u32 a0 = lo32(a), a1 = hi32(a), b0 = lo32(b), b1 = hi32(b);
+    asm("{\n\t"
+        "mul.lo.u32 %0, %4, %6;\n\t"
+        "mul.hi.u32 %1, %4, %6;\n\t"
+        "mad.lo.cc.u32 %1, %4, %7, %1;\n\t"
+        "madc.hi.u32 %2, %4, %7, 0;\n\t"
+        "mad.lo.cc.u32 %1, %5, %6, %1;\n\t"
+        "madc.hi.cc.u32 %2, %5, %6, %2;\n\t"
+        "addc.u32 %3, 0, 0;\n\t"
+        "mad.lo.cc.u32 %2, %5, %7, %2;\n\t"
+        "madc.hi.u32 %3, %5, %7, %3;\n\t"
+        "}"
+        : "=&r"(r0), "=&r"(r1), "=&r"(r2), "=&r"(r3)
+        : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+}
+
+GL_D u64 gl_mul_cc(u64 a, u64 b) {
+    u32 r0, r1, r2, r3;
+    gl_mul128_cc(a, b, r0, r1, r2, r3);
+    return gl_reduce128_cc(r0, r1, r2, r3);
+}
+
+GL_D u64 gl_sqr_cc(u64 a) {
+    u32 a0 = lo32(a), a1 = hi32(a);
+    u32 r0, r1, r2, r3;
+    asm("{\n\t"
+        ".reg .u32 m0, m1, m2;\n\t"
+        "mul.lo.u32 m0, %4, %5;\n\t"              // cross = a0*a1
+        "mul.hi.u32 m1, %4, %5;\n\t"
+        "add.cc.u32 m0, m0, m0;\n\t"              // 2*cross as (m2:m1:m0)
+        "addc.cc.u32 m1, m1, m1;\n\t"
+        "addc.u32 m2, 0, 0;\n\t"
+        "mul.lo.u32 %0, %4, %4;\n\t"              // a0^2
+        "mul.hi.u32 %1, %4, %4;\n\t"
+        "mul.lo.u32 %2, %5, %5;\n\t"              // a1^2
+        "mul.hi.u32 %3, %5, %5;\n\t"
+        "add.cc.u32 %1, %1, m0;\n\t"
+        "addc.cc.u32 %2, %2, m1;\n\t"
+        "addc.u32 %3, %3, m2;\n\t"
+        "}"
+        : "=&r"(r0), "=&r"(r1), "=&r"(r2), "=&r"(r3)
+        : "r"(a0), "r"(a1));
+    return gl_reduce128_cc(r0, r1, r2, r3);
+}
+
+GL_D u64 gl_pow7_cc(u64 x) {
+    u64 x2 = gl_sqr_cc(x);
+    u64 x4 = gl_sqr_cc(x2);
+    u64 x3 = gl_mul_cc(x2, x);
+    return gl_mul_cc(x3, x4);
+}
+
 // full 64x64 -> 128 product on IMAD.WIDE.U32: 4 multiplies, no carry chains
 // (each partial sum provably fits 64 bits).
 GL_D void gl_mul128(u64 a, u64 b, u64& lo, u64& hi) {

@@ -69,7 +69,9 @@ void poseidon_round_constants_host(u64 out[360]) {
 int32_t poseidon_module_init(vx_ctx* ctx) {
     u64 rc[360];
     poseidon_round_constants_host(rc);
-    VX_CUDA(poseidon_upload_constants(rc, ctx->stream));
+    PoseidonTables t;
+    if (!poseidon_derive_tables(rc, &t)) { vx_set_error("poseidon: table derivation failed"); return VX_ECUDA; }
+    VX_CUDA(poseidon_upload_constants(t, ctx->stream));
     return VX_OK;
 }
 
@@ -85,9 +87,10 @@ GL_D void store_digest(u64* dst, const u64 s[12]) {
 
 // one thread per leaf: hash_or_noop(leaf) -> interleaved slot (or cap when the subtree is 1 leaf)
 template <bool COL_MAJOR>
-__global__ void __launch_bounds__(128) leaf_hash_kernel(const u64* __restrict__ leaves, uint64_t stride,
+__global__ void __launch_bounds__(POSEIDON_BLOCK) leaf_hash_kernel(const u64* __restrict__ leaves, uint64_t stride,
                                                         uint64_t N, uint32_t c, uint32_t sub_bits,
                                                         u64* __restrict__ digests, u64* __restrict__ cap) {
+    __shared__ u64 scratch[12 * POSEIDON_BLOCK];
     uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= N) return;
     const u64* src = COL_MAJOR ? leaves + row : leaves + row * c;
@@ -104,7 +107,7 @@ __global__ void __launch_bounds__(128) leaf_hash_kernel(const u64* __restrict__ 
 #pragma unroll
             for (int i = 0; i < POSEIDON_RATE; i++)
                 if (off + i < c) s[i] = src[(uint64_t)(off + i) * step];   // overwrite-mode absorb
-            poseidon_permute(s);
+            poseidon_permute(s, scratch + threadIdx.x);
         }
     }
     u64* dst;
@@ -119,8 +122,9 @@ __global__ void __launch_bounds__(128) leaf_hash_kernel(const u64* __restrict__ 
 }
 
 // one thread per sibling pair of layer `lvl`: two_to_one -> parent slot (or cap at the top)
-__global__ void __launch_bounds__(128) level_hash_kernel(u64* __restrict__ digests, u64* __restrict__ cap,
+__global__ void __launch_bounds__(POSEIDON_BLOCK) level_hash_kernel(u64* __restrict__ digests, u64* __restrict__ cap,
                                                          uint32_t lvl, uint32_t sub_bits, uint64_t total_pairs) {
+    __shared__ u64 scratch[12 * POSEIDON_BLOCK];
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total_pairs) return;
     uint32_t pair_bits = sub_bits - lvl - 1;            // pairs per subtree = 2^pair_bits
@@ -133,7 +137,7 @@ __global__ void __launch_bounds__(128) level_hash_kernel(u64* __restrict__ diges
     s[0] = v0.x; s[1] = v0.y; s[2] = v1.x; s[3] = v1.y;
     s[4] = v2.x; s[5] = v2.y; s[6] = v3.x; s[7] = v3.y;
     s[8] = s[9] = s[10] = s[11] = 0;
-    poseidon_permute(s);
+    poseidon_permute(s, scratch + threadIdx.x);
     u64* dst = (pair_bits == 0) ? cap + 4 * sidx : blk + 4 * (pair_pos(q >> 1, lvl + 1) + (q & 1));
     store_digest(dst, s);
 }
@@ -147,9 +151,9 @@ int32_t merkle_build_device(vx_ctx* ctx, const u64* leaves, bool col_major, uint
     uint32_t sub_bits = log_N - cap_height;
     unsigned blocks = (unsigned)((N + 127) / 128);
     if (col_major)
-        leaf_hash_kernel<true><<<blocks, 128, 0, ctx->stream>>>(leaves, stride, N, c, sub_bits, digests, cap);
+        leaf_hash_kernel<true><<<blocks, POSEIDON_BLOCK, 0, ctx->stream>>>(leaves, stride, N, c, sub_bits, digests, cap);
     else
-        leaf_hash_kernel<false><<<blocks, 128, 0, ctx->stream>>>(leaves, stride, N, c, sub_bits, digests, cap);
+        leaf_hash_kernel<false><<<blocks, POSEIDON_BLOCK, 0, ctx->stream>>>(leaves, stride, N, c, sub_bits, digests, cap);
     VX_LAUNCH_COUNT(ctx, 1);
     if (after_leaves) VX_CUDA(cudaEventRecord(after_leaves, ctx->stream));
     for (uint32_t lvl = 0; lvl < sub_bits; lvl++) {
@@ -238,13 +242,14 @@ int32_t transpose_to_rows_device(vx_ctx* ctx, const u64* colmajor, uint64_t stri
 }
 
 // ------------------------------------------------------------------------------------------------ primitives
-__global__ void __launch_bounds__(128) permute_kernel(const u64* __restrict__ in, uint64_t count, u64* __restrict__ out) {
+__global__ void __launch_bounds__(POSEIDON_BLOCK) permute_kernel(const u64* __restrict__ in, uint64_t count, u64* __restrict__ out) {
+    __shared__ u64 scratch[12 * POSEIDON_BLOCK];
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= count) return;
     u64 s[12];
 #pragma unroll
     for (int i = 0; i < 12; i++) s[i] = in[t * 12 + i];
-    poseidon_permute(s);
+    poseidon_permute(s, scratch + threadIdx.x);
 #pragma unroll
     for (int i = 0; i < 12; i++) out[t * 12 + i] = gl_canon(s[i]);
 }
@@ -257,8 +262,9 @@ int32_t poseidon_permute_device(vx_ctx* ctx, const u64* in, uint64_t count, u64*
     return VX_OK;
 }
 
-__global__ void __launch_bounds__(128) hash_no_pad_kernel(const u64* __restrict__ in, uint64_t count, uint32_t len,
+__global__ void __launch_bounds__(POSEIDON_BLOCK) hash_no_pad_kernel(const u64* __restrict__ in, uint64_t count, uint32_t len,
                                                           u64* __restrict__ out) {
+    __shared__ u64 scratch[12 * POSEIDON_BLOCK];
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= count) return;
     const u64* src = in + t * len;
@@ -269,7 +275,7 @@ __global__ void __launch_bounds__(128) hash_no_pad_kernel(const u64* __restrict_
 #pragma unroll
         for (int i = 0; i < POSEIDON_RATE; i++)
             if (off + i < len) s[i] = src[off + i];
-        poseidon_permute(s);
+        poseidon_permute(s, scratch + threadIdx.x);
     }
     for (int i = 0; i < 4; i++) out[t * 4 + i] = gl_canon(s[i]);
 }

@@ -18,15 +18,17 @@
 #define POSEIDON_WIDTH 12
 #define POSEIDON_RATE 8
 #define POSEIDON_ROUNDS 30
+#define POSEIDON_PARTIAL_ROUNDS 22
+#define POSEIDON_BLOCK 128          // threads per block of every hashing kernel (shared scratch is sized for it)
 
-// RC[30][12] followed by one all-zero row (seed for the last MDS layer).  One copy per translation
-// unit that hashes; each is filled by poseidon_upload_constants() at context creation.
-static __constant__ u64 c_poseidon_rc[(POSEIDON_ROUNDS + 1) * POSEIDON_WIDTH];
+#include "poseidon_tables.h"
 
-static inline cudaError_t poseidon_upload_constants(const u64 rc360[360], cudaStream_t stream) {
-    u64 rc[(POSEIDON_ROUNDS + 1) * POSEIDON_WIDTH] = {0};
-    for (int i = 0; i < 360; i++) rc[i] = rc360[i];
-    cudaError_t e = cudaMemcpyToSymbolAsync(c_poseidon_rc, rc, sizeof rc, 0, cudaMemcpyHostToDevice, stream);
+// All tables (8.3 KB) live in constant memory and are only ever indexed warp-uniformly.  One copy per
+// translation unit that hashes; each is filled by poseidon_upload_constants() at context creation.
+static __constant__ PoseidonTables c_pos;
+
+static inline cudaError_t poseidon_upload_constants(const PoseidonTables& t, cudaStream_t stream) {
+    cudaError_t e = cudaMemcpyToSymbolAsync(c_pos, &t, sizeof t, 0, cudaMemcpyHostToDevice, stream);
     if (e != cudaSuccess) return e;
     return cudaStreamSynchronize(stream);
 }
@@ -60,25 +62,60 @@ GL_D void poseidon_mds_add(u64 s[12], const u64* __restrict__ add) {
     }
 }
 
-GL_D void poseidon_permute(u64 s[12]) {
-    const u64* rc = c_poseidon_rc;
+// s <- D * s + e with D a dense matrix of full-width constants (the MDS layer of full round 3 merged
+// with the partial rounds' initial matrix).  Rows are produced in a rolled loop (small code) and
+// staged through this thread's shared-memory column: scratch[j * POSEIDON_BLOCK].
+GL_D void poseidon_dense_layer(u64 s[12], u64* __restrict__ scratch) {
+#pragma unroll 1
+    for (int j = 0; j < 12; j++) {
+        const u64* row = c_pos.dense_d + 12 * j;
+        u64 acc = c_pos.dense_e[j];
+#pragma unroll
+        for (int i = 0; i < 12; i++) acc = gl_mul_add_cc(row[i], s[i], acc);
+        scratch[j * POSEIDON_BLOCK] = acc;
+    }
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = scratch[i * POSEIDON_BLOCK];
+}
+
+// 22 partial rounds in the sparse form (see poseidon_tables.h)
+GL_D void poseidon_partial_rounds(u64 s[12]) {
+#pragma unroll 1
+    for (int r = 0; r < POSEIDON_PARTIAL_ROUNDS; r++) {
+        const u64* v = c_pos.pv + 11 * r;
+        const u64* w = c_pos.pw + 11 * r;
+        u64 x0 = gl_add_canon(gl_pow7_cc(s[0]), c_pos.pk[r]);
+        // d = 25 * x0 + sum_i v_i s_i   (25 = MDS[0][0])
+        u64 t = mul_wide(lo32(x0), 25u);
+        u64 d = gl_reduce96(mad_wide(hi32(x0), 25u, (u64)hi32(t)) << 32 | lo32(t),
+                            hi32(mad_wide(hi32(x0), 25u, (u64)hi32(t))));
+#pragma unroll
+        for (int i = 1; i < 12; i++) d = gl_mul_add_cc(v[i - 1], s[i], d);
+#pragma unroll
+        for (int i = 1; i < 12; i++) s[i] = gl_mul_add_cc(w[i - 1], x0, s[i]);
+        s[0] = d;
+    }
+}
+
+// scratch: this thread's column of a POSEIDON_BLOCK-wide shared array of 12 rows
+GL_D void poseidon_permute(u64 s[12], u64* __restrict__ scratch) {
+    const u64* rc = c_pos.rc;
 #pragma unroll
     for (int i = 0; i < 12; i++) s[i] = gl_add_canon(s[i], rc[i]);
 #pragma unroll 1
-    for (int r = 0; r < 4; r++) {
-#pragma unroll
-        for (int i = 0; i < 12; i++) s[i] = gl_pow7(s[i]);
-        poseidon_mds_add(s, rc + 12 * (r + 1));
-    }
+    for (int half = 0; half < 2; half++) {
+        const u64* next = rc + (half ? 27 * 12 : 12);       // constants of the round after each full round
 #pragma unroll 1
-    for (int r = 4; r < 26; r++) {
-        s[0] = gl_pow7(s[0]);
-        poseidon_mds_add(s, rc + 12 * (r + 1));
-    }
-#pragma unroll 1
-    for (int r = 26; r < 30; r++) {
+        for (int r = 0; r < 4; r++) {
 #pragma unroll
-        for (int i = 0; i < 12; i++) s[i] = gl_pow7(s[i]);
-        poseidon_mds_add(s, rc + 12 * (r + 1));
+            for (int i = 0; i < 12; i++) s[i] = gl_pow7_cc(s[i]);
+            if (half == 0 && r == 3) poseidon_dense_layer(s, scratch);
+            else poseidon_mds_add(s, next + 12 * r);
+        }
+        if (half == 0) {
+            poseidon_partial_rounds(s);
+#pragma unroll
+            for (int i = 0; i < 12; i++) s[i] = gl_add_canon(s[i], rc[26 * 12 + i]);
+        }
     }
 }
