@@ -60,6 +60,16 @@ __global__ void __launch_bounds__(1024) bench(uint32_t* out, uint32_t seed, unsi
                 asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(t) : "r"(a[i]), "r"(b));
                 asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(u) : "r"(a[i]), "r"(c));
                 asm volatile("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(a[i]) : "r"((uint32_t)t), "r"((uint32_t)(t >> 32)), "r"((uint32_t)u));
+            } else if (MODE == 16) {  // IMAD.WIDE.U32 (RZ addend), result never consumed in the loop
+                asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(w[i]) : "r"(a[i]), "r"(b));
+            } else if (MODE == 17) {  // one accumulating IMAD.WIDE per chain per iteration (mad.lo.cc/madc.hi)
+                uint32_t l = (uint32_t)w[i], h = (uint32_t)(w[i] >> 32);
+                asm volatile("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.u32 %1, %2, %3, %1;" : "+r"(l), "+r"(h) : "r"(a[i]), "r"(b));
+                w[i] = ((unsigned long long)h << 32) | l;
+            } else if (MODE == 18) {  // accumulating IMAD.WIDE with carry-out + carry counter (lazy dot product step)
+                uint32_t l = (uint32_t)w[i], h = (uint32_t)(w[i] >> 32);
+                asm volatile("mad.lo.cc.u32 %0, %3, %4, %0; madc.hi.cc.u32 %1, %3, %4, %1; addc.u32 %2, %2, 0;" : "+r"(l), "+r"(h), "+r"(a[(i + 1) % UNROLL]) : "r"(c), "r"(b));
+                w[i] = ((unsigned long long)h << 32) | l;
             } else if (MODE == 15) {  // mad.lo.cc chain of 2 accumulations + 2 LOP3
                 asm volatile("{ .reg .u32 l, h; mov.b64 {l,h}, %0; mad.lo.cc.u32 l, %1, %2, l; madc.hi.u32 h, %1, %2, h; mad.lo.cc.u32 l, %1, %3, l; madc.hi.u32 h, %1, %3, h; mov.b64 %0, {l,h}; }" : "+l"(w[i]) : "r"(a[i]), "r"(b), "r"(c));
                 asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b), "r"(c));
@@ -76,8 +86,8 @@ __global__ void __launch_bounds__(1024) bench(uint32_t* out, uint32_t seed, unsi
 }
 
 static const char* NAMES[] = {"imad_lo", "imad_wide_acc", "iadd3", "add64_pair", "imad_wide+iadd3", "imad_hi",
-                              "lop3", "shf", "imad_lo+iadd3", "imad_wide+2iadd3", "isetp+sel", "imad_wide_imm", "madcc_pair", "mulwide+lop3", "2mulwide+lop3", "2madcc+2lop3"};
-static const int INSTR_PER_SLOT[] = {1, 1, 1, 2, 2, 1, 1, 1, 2, 3, 2, 1, 1, 2, 3, 4};
+                              "lop3", "shf", "imad_lo+iadd3", "imad_wide+2iadd3", "isetp+sel", "imad_wide_imm", "madcc_pair", "mulwide+lop3", "2mulwide+lop3", "2madcc+2lop3", "mulwide_noconsumer", "madcc_acc", "madcc_acc_carry"};
+static const int INSTR_PER_SLOT[] = {1, 1, 1, 2, 2, 1, 1, 1, 2, 3, 2, 1, 1, 2, 3, 4, 1, 1, 2};
 
 template <int MODE>
 void run(int sms, uint32_t* out, unsigned long long* clk, bool last) {
@@ -110,7 +120,8 @@ int main() {
     run<3>(sms, out, clk, false); run<4>(sms, out, clk, false); run<5>(sms, out, clk, false);
     run<6>(sms, out, clk, false); run<7>(sms, out, clk, false); run<8>(sms, out, clk, false);
     run<9>(sms, out, clk, false); run<10>(sms, out, clk, false); run<11>(sms, out, clk, false);
-    run<12>(sms, out, clk, false); run<13>(sms, out, clk, false); run<14>(sms, out, clk, false); run<15>(sms, out, clk, true);
+    run<12>(sms, out, clk, false); run<13>(sms, out, clk, false); run<14>(sms, out, clk, false); run<15>(sms, out, clk, false);
+    run<16>(sms, out, clk, false); run<17>(sms, out, clk, false); run<18>(sms, out, clk, true);
     printf("}\n");
     return 0;
 }

@@ -51,6 +51,7 @@ enum { VX_EV_START = 0, VX_EV_STAGED, VX_EV_INTT, VX_EV_LDE, VX_EV_LEAF, VX_EV_T
 struct vx_ctx {
     int device = 0;
     int sm_count = 0;
+    int poseidon_variant = 0;           // VX_POSEIDON_VARIANT (A/B switch for profiling): 0 = default, 1 = shared-memory state, 2 = 128-register form
     cudaStream_t stream = nullptr;
     std::mutex mu;                      // serialises calls on this context's stream
     std::atomic<uint64_t> launches{0};

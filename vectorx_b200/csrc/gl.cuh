@@ -176,6 +176,66 @@ GL_D u64 gl_pow7_cc(u64 x) {
     return gl_mul_cc(x3, x4);
 }
 
+// ---- lazy dot products: sum_i a_i * b_i accumulated UNREDUCED in three column accumulators
+//   T0 += a0*b0,  T1 += a0*b1 + a1*b0,  T2 += a1*b1      (value = T0 + T1*2^32 + T2*2^64)
+// each a 64-bit IMAD.WIDE accumulator plus a carry counter, so a term costs 4 multiply-adds and 4
+// carry adds and the whole sum is reduced once (a reduced multiply costs ~3x that on the ALU pipe).
+struct GlAcc {
+    u32 l0, h0, c0, l1, h1, c1, l2, h2, c2;
+};
+GL_D void gl_acc_init(GlAcc& t, u64 init) {
+    t.l0 = lo32(init); t.h0 = hi32(init);
+    t.c0 = t.l1 = t.h1 = t.c1 = t.l2 = t.h2 = t.c2 = 0;
+}
+GL_D void gl_acc_mad(GlAcc& t, u64 a, u64 b) {
+    u32 a0 = lo32(a), a1 = hi32(a), b0 = lo32(b), b1 = hi32(b);
+    asm("{\n\t"
+        "mad.lo.cc.u32 %0, %9, %11, %0;\n\t"  "madc.hi.cc.u32 %1, %9, %11, %1;\n\t"  "addc.u32 %2, %2, 0;\n\t"
+        "mad.lo.cc.u32 %3, %9, %12, %3;\n\t"  "madc.hi.cc.u32 %4, %9, %12, %4;\n\t"  "addc.u32 %5, %5, 0;\n\t"
+        "mad.lo.cc.u32 %3, %10, %11, %3;\n\t" "madc.hi.cc.u32 %4, %10, %11, %4;\n\t" "addc.u32 %5, %5, 0;\n\t"
+        "mad.lo.cc.u32 %6, %10, %12, %6;\n\t" "madc.hi.cc.u32 %7, %10, %12, %7;\n\t" "addc.u32 %8, %8, 0;\n\t"
+        "}"
+        : "+r"(t.l0), "+r"(t.h0), "+r"(t.c0), "+r"(t.l1), "+r"(t.h1), "+r"(t.c1), "+r"(t.l2), "+r"(t.h2), "+r"(t.c2)
+        : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+}
+// small-constant term: a * k, k < 2^32
+GL_D void gl_acc_mad_small(GlAcc& t, u64 a, u32 k) {
+    u32 a0 = lo32(a), a1 = hi32(a);
+    asm("{\n\t"
+        "mad.lo.cc.u32 %0, %6, %8, %0;\n\t"  "madc.hi.cc.u32 %1, %6, %8, %1;\n\t"  "addc.u32 %2, %2, 0;\n\t"
+        "mad.lo.cc.u32 %3, %7, %8, %3;\n\t"  "madc.hi.cc.u32 %4, %7, %8, %4;\n\t"  "addc.u32 %5, %5, 0;\n\t"
+        "}"
+        : "+r"(t.l0), "+r"(t.h0), "+r"(t.c0), "+r"(t.l1), "+r"(t.h1), "+r"(t.c1)
+        : "r"(a0), "r"(a1), "r"(k));
+}
+// value = w0 + w1 2^32 + w2 2^64 + w3 2^96 + w4 2^128 = (w1:w0) - (w4:w3) + w2*eps  (2^96 = -1, 2^128 = -2^32)
+GL_D u64 gl_acc_reduce(const GlAcc& t) {
+    u32 r0, r1;
+    asm("{\n\t"
+        ".reg .u32 w1, w2, w3, w4, t0, t1, m, c;\n\t"
+        "add.cc.u32 w1, %3, %5;\n\t"            // w1 = h0 + l1
+        "addc.cc.u32 w2, %4, %6;\n\t"           // w2 = c0 + h1 + cy
+        "addc.cc.u32 w3, %7, %9;\n\t"           // w3 = c1 + h2 + cy
+        "addc.u32 w4, %10, 0;\n\t"              // w4 = c2 + cy
+        "add.cc.u32 w2, w2, %8;\n\t"            // w2 += l2
+        "addc.cc.u32 w3, w3, 0;\n\t"
+        "addc.u32 w4, w4, 0;\n\t"
+        "sub.cc.u32 t0, %2, w3;\n\t"            // t = (w1:w0) - (w4:w3)
+        "subc.cc.u32 t1, w1, w4;\n\t"
+        "subc.u32 m, 0, 0;\n\t"
+        "sub.cc.u32 t0, t0, m;\n\t"             // borrow: -= eps
+        "subc.u32 t1, t1, 0;\n\t"
+        "mad.lo.cc.u32 t0, w2, 0xffffffff, t0;\n\t"   // += w2 * eps
+        "madc.hi.cc.u32 t1, w2, 0xffffffff, t1;\n\t"
+        "addc.u32 c, 0, 0;\n\t"
+        "mad.lo.cc.u32 %0, c, 0xffffffff, t0;\n\t"    // carry: += eps
+        "addc.u32 %1, t1, 0;\n\t"
+        "}"
+        : "=r"(r0), "=r"(r1)
+        : "r"(t.l0), "r"(t.h0), "r"(t.c0), "r"(t.l1), "r"(t.h1), "r"(t.c1), "r"(t.l2), "r"(t.h2), "r"(t.c2));
+    return pack64(r0, r1);
+}
+
 // full 64x64 -> 128 product on IMAD.WIDE.U32: 4 multiplies, no carry chains
 // (each partial sum provably fits 64 bits).
 GL_D void gl_mul128(u64 a, u64 b, u64& lo, u64& hi) {

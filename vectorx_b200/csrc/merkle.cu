@@ -86,8 +86,9 @@ GL_D void store_digest(u64* dst, const u64 s[12]) {
 }
 
 // one thread per leaf: hash_or_noop(leaf) -> interleaved slot (or cap when the subtree is 1 leaf)
-template <bool COL_MAJOR>
-__global__ void __launch_bounds__(POSEIDON_BLOCK) leaf_hash_kernel(const u64* __restrict__ leaves, uint64_t stride,
+// V = 0: state in registers, unrolled rounds.  V = 1: state in shared memory, rolled lane loops.
+template <bool COL_MAJOR, int V, int MINB>
+__global__ void __launch_bounds__(POSEIDON_BLOCK, MINB) leaf_hash_kernel(const u64* __restrict__ leaves, uint64_t stride,
                                                         uint64_t N, uint32_t c, uint32_t sub_bits,
                                                         u64* __restrict__ digests, u64* __restrict__ cap) {
     __shared__ u64 scratch[12 * POSEIDON_BLOCK];
@@ -95,19 +96,35 @@ __global__ void __launch_bounds__(POSEIDON_BLOCK) leaf_hash_kernel(const u64* __
     if (row >= N) return;
     const u64* src = COL_MAJOR ? leaves + row : leaves + row * c;
     const uint64_t step = COL_MAJOR ? stride : 1;
+    u64* st = scratch + threadIdx.x;
     u64 s[12];
+    if (V == 0) {
 #pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = 0;
+        for (int i = 0; i < 12; i++) s[i] = 0;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 12; i++) PS(i) = 0;
+    }
     if (c <= 4) {                         // hash_or_noop: identity, zero padded
 #pragma unroll
-        for (int i = 0; i < 4; i++)
-            if ((uint32_t)i < c) s[i] = src[i * step];
+        for (int i = 0; i < 4; i++) s[i] = ((uint32_t)i < c) ? src[i * step] : 0;
     } else {
         for (uint32_t off = 0; off < c; off += POSEIDON_RATE) {
+            if (V == 0) {
 #pragma unroll
-            for (int i = 0; i < POSEIDON_RATE; i++)
-                if (off + i < c) s[i] = src[(uint64_t)(off + i) * step];   // overwrite-mode absorb
-            poseidon_permute(s, scratch + threadIdx.x);
+                for (int i = 0; i < POSEIDON_RATE; i++)
+                    if (off + i < c) s[i] = src[(uint64_t)(off + i) * step];   // overwrite-mode absorb
+                poseidon_permute(s, st);
+            } else {
+#pragma unroll
+                for (int i = 0; i < POSEIDON_RATE; i++)
+                    if (off + i < c) PS(i) = src[(uint64_t)(off + i) * step];
+                poseidon_s_permute(st);
+            }
+        }
+        if (V != 0) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) s[i] = PS(i);
         }
     }
     u64* dst;
@@ -150,10 +167,18 @@ int32_t merkle_build_device(vx_ctx* ctx, const u64* leaves, bool col_major, uint
     VX_REQUIRE(c >= 1, "merkle: empty leaves");
     uint32_t sub_bits = log_N - cap_height;
     unsigned blocks = (unsigned)((N + 127) / 128);
-    if (col_major)
-        leaf_hash_kernel<true><<<blocks, POSEIDON_BLOCK, 0, ctx->stream>>>(leaves, stride, N, c, sub_bits, digests, cap);
-    else
-        leaf_hash_kernel<false><<<blocks, POSEIDON_BLOCK, 0, ctx->stream>>>(leaves, stride, N, c, sub_bits, digests, cap);
+    const int pv = ctx->poseidon_variant;
+#define LEAF(CM, V, MB) leaf_hash_kernel<CM, V, MB><<<blocks, POSEIDON_BLOCK, 0, ctx->stream>>>(leaves, stride, N, c, sub_bits, digests, cap)
+    if (col_major) {
+        switch (pv) {
+            case 1: LEAF(true, 1, 4); break;      // state in shared memory, rolled lane loops
+            case 2: LEAF(true, 0, 4); break;      // state in registers, up to 128 registers
+            default: LEAF(true, 0, 8); break;     // state in registers, 64 registers / 8 blocks per SM (fastest measured)
+        }
+    } else {
+        if (pv % 10 == 1) LEAF(false, 1, 4); else LEAF(false, 0, 4);
+    }
+#undef LEAF
     VX_LAUNCH_COUNT(ctx, 1);
     if (after_leaves) VX_CUDA(cudaEventRecord(after_leaves, ctx->stream));
     for (uint32_t lvl = 0; lvl < sub_bits; lvl++) {

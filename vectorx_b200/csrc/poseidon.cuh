@@ -69,10 +69,11 @@ GL_D void poseidon_dense_layer(u64 s[12], u64* __restrict__ scratch) {
 #pragma unroll 1
     for (int j = 0; j < 12; j++) {
         const u64* row = c_pos.dense_d + 12 * j;
-        u64 acc = c_pos.dense_e[j];
+        GlAcc acc;
+        gl_acc_init(acc, c_pos.dense_e[j]);
 #pragma unroll
-        for (int i = 0; i < 12; i++) acc = gl_mul_add_cc(row[i], s[i], acc);
-        scratch[j * POSEIDON_BLOCK] = acc;
+        for (int i = 0; i < 12; i++) gl_acc_mad(acc, row[i], s[i]);
+        scratch[j * POSEIDON_BLOCK] = gl_acc_reduce(acc);
     }
 #pragma unroll
     for (int i = 0; i < 12; i++) s[i] = scratch[i * POSEIDON_BLOCK];
@@ -86,14 +87,14 @@ GL_D void poseidon_partial_rounds(u64 s[12]) {
         const u64* w = c_pos.pw + 11 * r;
         u64 x0 = gl_add_canon(gl_pow7_cc(s[0]), c_pos.pk[r]);
         // d = 25 * x0 + sum_i v_i s_i   (25 = MDS[0][0])
-        u64 t = mul_wide(lo32(x0), 25u);
-        u64 d = gl_reduce96(mad_wide(hi32(x0), 25u, (u64)hi32(t)) << 32 | lo32(t),
-                            hi32(mad_wide(hi32(x0), 25u, (u64)hi32(t))));
+        GlAcc d;
+        gl_acc_init(d, 0);
+        gl_acc_mad_small(d, x0, 25u);
 #pragma unroll
-        for (int i = 1; i < 12; i++) d = gl_mul_add_cc(v[i - 1], s[i], d);
+        for (int i = 1; i < 12; i++) gl_acc_mad(d, v[i - 1], s[i]);
 #pragma unroll
         for (int i = 1; i < 12; i++) s[i] = gl_mul_add_cc(w[i - 1], x0, s[i]);
-        s[0] = d;
+        s[0] = gl_acc_reduce(d);
     }
 }
 
@@ -116,6 +117,120 @@ GL_D void poseidon_permute(u64 s[12], u64* __restrict__ scratch) {
             poseidon_partial_rounds(s);
 #pragma unroll
             for (int i = 0; i < 12; i++) s[i] = gl_add_canon(s[i], rc[26 * 12 + i]);
+        }
+    }
+}
+
+// =================================================================================================
+// Variant S ("state in shared memory"): the same permutation with every lane loop rolled, so the
+// whole hot code is a few KB and stays in the instruction cache (ncu showed ~30% of warp time in
+// stall_no_instruction for the fully unrolled form), and so that a thread needs few registers.
+// The state of thread t lives in its column of a 12 x POSEIDON_BLOCK shared array: lane i at
+// st[i * POSEIDON_BLOCK].  The MDS layer works on 22-bit limbs with plain 32-bit IMADs
+// (3 limbs x 12 terms; 22 + 9 bits of growth < 2^31) instead of IMAD.WIDE halves.
+// =================================================================================================
+#define PS(i) st[(i) * POSEIDON_BLOCK]
+
+GL_D void poseidon_s_sbox_all(u64* __restrict__ st) {
+#pragma unroll 1
+    for (int i = 0; i < 12; i += 2) {
+        u64 a = PS(i), b = PS(i + 1);
+        a = gl_pow7_cc(a);
+        b = gl_pow7_cc(b);
+        PS(i) = a;
+        PS(i + 1) = b;
+    }
+}
+
+GL_D u32 imad32(u32 a, u32 b, u32 c) { return a * b + c; }
+
+// st <- MDS * st + k,  k given as 22-bit limbs (kl: 12 x 3 u32, warp-uniform constant pointer)
+GL_D void poseidon_s_mds_add(u64* __restrict__ st, const u32* __restrict__ kl) {
+    constexpr u32 C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+    u32 l0[12], l1[12], l2[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        u64 x = PS(i);
+        u32 lo = lo32(x), hi = hi32(x);
+        l0[i] = lo & 0x3fffffu;
+        l1[i] = __funnelshift_r(lo, hi, 22) & 0x3fffffu;
+        l2[i] = hi >> 12;
+    }
+#pragma unroll
+    for (int r = 0; r < 12; r++) {
+        u32 a0 = kl[3 * r], a1 = kl[3 * r + 1], a2 = kl[3 * r + 2];
+#pragma unroll
+        for (int i = 0; i < 12; i++) {
+            a0 = imad32(l0[(i + r) % 12], C[i], a0);
+            a1 = imad32(l1[(i + r) % 12], C[i], a1);
+            a2 = imad32(l2[(i + r) % 12], C[i], a2);
+        }
+        if (r == 0) {
+            a0 = imad32(l0[0], 8u, a0);
+            a1 = imad32(l1[0], 8u, a1);
+            a2 = imad32(l2[0], 8u, a2);
+        }
+        // value = a0 + a1*2^22 + a2*2^44  (< 2^76)
+        u64 t = mad_wide(a1, 1u << 22, (u64)a0);
+        u64 u = mad_wide(a2, 1u << 12, (u64)hi32(t));
+        PS(r) = gl_reduce96(pack64(lo32(t), lo32(u)), hi32(u));
+    }
+}
+
+GL_D void poseidon_s_dense_layer(u64* __restrict__ st) {
+    u64 s[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = PS(i);
+#pragma unroll 1
+    for (int j = 0; j < 12; j++) {
+        const u64* row = c_pos.dense_d + 12 * j;
+        GlAcc acc;
+        gl_acc_init(acc, c_pos.dense_e[j]);
+#pragma unroll
+        for (int i = 0; i < 12; i++) gl_acc_mad(acc, row[i], s[i]);
+        PS(j) = gl_acc_reduce(acc);
+    }
+}
+
+GL_D void poseidon_s_partial_rounds(u64* __restrict__ st) {
+    u64 s0 = PS(0);
+#pragma unroll 1
+    for (int r = 0; r < POSEIDON_PARTIAL_ROUNDS; r++) {
+        const u64* v = c_pos.pv + 11 * r;
+        const u64* w = c_pos.pw + 11 * r;
+        u64 x0 = gl_add_canon(gl_pow7_cc(s0), c_pos.pk[r]);
+        GlAcc d;
+        gl_acc_init(d, 0);
+        gl_acc_mad_small(d, x0, 25u);
+#pragma unroll 1
+        for (int i = 1; i < 12; i++) {
+            u64 si = PS(i);
+            gl_acc_mad(d, v[i - 1], si);
+            PS(i) = gl_mul_add_cc(w[i - 1], x0, si);
+        }
+        s0 = gl_acc_reduce(d);
+    }
+    PS(0) = s0;
+}
+
+// permutes the state held in this thread's shared-memory column
+GL_D void poseidon_s_permute(u64* __restrict__ st) {
+    const u64* rc = c_pos.rc;
+#pragma unroll 1
+    for (int i = 0; i < 12; i++) PS(i) = gl_add_canon(PS(i), rc[i]);
+#pragma unroll 1
+    for (int half = 0; half < 2; half++) {
+        const u32* next = c_pos.rc22 + 36 * (half ? 27 : 1);
+#pragma unroll 1
+        for (int r = 0; r < 4; r++) {
+            poseidon_s_sbox_all(st);
+            if (half == 0 && r == 3) poseidon_s_dense_layer(st);
+            else poseidon_s_mds_add(st, next + 36 * r);
+        }
+        if (half == 0) {
+            poseidon_s_partial_rounds(st);
+#pragma unroll 1
+            for (int i = 0; i < 12; i++) PS(i) = gl_add_canon(PS(i), rc[26 * 12 + i]);
         }
     }
 }

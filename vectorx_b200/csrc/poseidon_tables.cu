@@ -64,7 +64,12 @@ bool poseidon_derive_tables(const unsigned long long rc360[360], PoseidonTables*
     static const uint64_t CIRC[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
     const int R = 22, FIRST_PARTIAL = 4;
     memset(t, 0, sizeof *t);
-    for (int i = 0; i < 360; i++) t->rc[i] = rc360[i];
+    for (int i = 0; i < 360; i++) {
+        t->rc[i] = rc360[i];
+        t->rc22[3 * i] = (unsigned)(rc360[i] & 0x3fffff);
+        t->rc22[3 * i + 1] = (unsigned)((rc360[i] >> 22) & 0x3fffff);
+        t->rc22[3 * i + 2] = (unsigned)(rc360[i] >> 44);
+    }
     Mat M(12, std::vector<uint64_t>(12));
     for (int r = 0; r < 12; r++)
         for (int c = 0; c < 12; c++) M[r][c] = CIRC[(c - r + 12) % 12] + ((r == 0 && c == 0) ? 8 : 0);

@@ -16,6 +16,7 @@
 
 struct PoseidonTables {
     unsigned long long rc[31 * 12];        // RC[30][12] + one zero row
+    unsigned int rc22[31 * 12 * 3];        // the same constants as 22/22/20-bit limbs (variant S MDS layer)
     unsigned long long dense_d[12 * 12];   // D = INIT * M   (replaces the MDS layer of full round 3)
     unsigned long long dense_e[12];        // e = INIT * first
     unsigned long long pk[22];             // post-S-box lane-0 constants (last is 0)
