@@ -98,6 +98,77 @@ const uint64_t* vx_batch_lde_device(const vx_batch* b);
 const uint64_t* vx_batch_coeffs_device(const vx_batch* b);
 const uint64_t* vx_batch_digests_device(const vx_batch* b);
 
+/* ---- constraint evaluation (plonky2 plonk/prover.rs compute_quotient_polys +
+ *      plonk/vanishing_poly.rs eval_vanishing_poly_base_batch + Gate::eval_unfiltered_base_batch;
+ *      reached from P2X/backend/circuit/build.rs:69-75) ---------------------------------------
+ * The circuit is described by plain data the Rust shim serialises from CommonCircuitData once per
+ * circuit.  Gate constraints travel as a small register bytecode (one program for all gates, in
+ * plonky2's sorted gate order); the shim obtains it by tracing Gate::eval_unfiltered_circuit, so
+ * every registered gate (P2X/backend/circuit/serialization/gates.rs:85-107) is expressible.
+ * Word layout: bits 0-7 opcode, 8-15 dst, 16-23 a, 24-31 b, 32-63 imm32; *_K ops read a 64-bit
+ * immediate from the following word. */
+enum {
+    VX_OP_END = 0, VX_OP_LOADW = 1, VX_OP_LOADC = 2, VX_OP_LOADPI = 3, VX_OP_LOADK = 4,
+    VX_OP_ADD = 5, VX_OP_SUB = 6, VX_OP_MUL = 7, VX_OP_ADDK = 8, VX_OP_MULK = 9, VX_OP_RSUBK = 10,
+    VX_OP_SUBK = 11, VX_OP_EMIT = 12, VX_OP_BEGINGATE = 13, VX_OP_ENDGATE = 14
+};
+#define VX_PROGRAM_REGS 64
+typedef struct vx_circuit_desc {
+    uint32_t degree_bits, rate_bits;
+    uint32_t num_wires, num_routed_wires;
+    uint32_t num_constants;          /* columns of constants_sigmas before the sigmas (selectors + gate constants) */
+    uint32_t num_selectors;
+    uint32_t num_challenges;
+    uint32_t num_partial_products;   /* per challenge */
+    uint32_t max_degree;             /* chunk size of the permutation argument */
+    uint32_t num_gate_constraints;
+    const uint64_t* k_is;            /* num_routed_wires coset shifts (host) */
+    const uint64_t* program;         /* gate bytecode (host) */
+    uint64_t program_len;            /* in 64-bit words */
+} vx_circuit_desc;
+
+/* Z and partial-product polynomials over the trace domain (plonky2 plonk/prover.rs
+ * all_wires_permutation_partial_products / wires_permutation_partial_products_and_zs).
+ * wires: num_wires x n, sigmas: num_routed x n (values, host or device);
+ * out: (num_challenges * (1 + num_partial_products)) x n, columns [Z_0.., pp_{0,*}, pp_{1,*}..]. */
+int32_t vx_zs_partial_products(vx_ctx* ctx, const vx_circuit_desc* desc, const uint64_t* wires,
+                               const uint64_t* sigmas, const uint64_t* betas, const uint64_t* gammas,
+                               uint64_t* out);
+/* compute_quotient_polys: evaluates the vanishing polynomial at every LDE point, divides by Z_H,
+ * coset-iNTTs; quotient_coeffs_out: num_challenges x N coefficients (host or device) -- viewed as
+ * (num_challenges * 2^rate_bits) x n it is the input of vx_commit_from_coeffs. */
+int32_t vx_quotient(vx_ctx* ctx, const vx_circuit_desc* desc, vx_batch* constants_sigmas, vx_batch* wires,
+                    vx_batch* zs_partial_products, const uint64_t pi_hash[4], const uint64_t* betas,
+                    const uint64_t* gammas, const uint64_t* alphas, uint64_t* quotient_coeffs_out);
+/* OpeningSet::new: every polynomial of the batch evaluated at an extension point; out: c x 2 */
+int32_t vx_batch_eval_ext(vx_batch* b, const uint64_t point[2], uint64_t* out);
+
+/* ---- FRI (plonky2 fri/oracle.rs prove_openings, fri/prover.rs fri_committed_trees /
+ *      fri_proof_of_work / fri_prover_query_rounds) ---------------------------------------------
+ * vx_fri_begin builds the batched opening polynomial
+ *   final = sum_b alpha-shifted (sum_i alpha^i p_i - eval) / (X - point_b)
+ * for the listed batches (ranges of polynomials of the given oracles), extends it over the coset and
+ * keeps coefficients + values on the device.  The host challenger drives the layers:
+ *   vx_fri_commit_layer -> cap (observe, draw beta) -> vx_fri_fold(beta) ... -> vx_fri_final_poly. */
+typedef struct vx_fri vx_fri;
+typedef struct vx_fri_range { uint32_t oracle, first, count; } vx_fri_range;
+typedef struct vx_fri_batch { uint64_t point[2]; const vx_fri_range* ranges; uint32_t num_ranges; } vx_fri_batch;
+int32_t vx_fri_begin(vx_ctx* ctx, vx_batch* const* oracles, uint32_t num_oracles, const vx_fri_batch* batches,
+                     uint32_t num_batches, const uint64_t alpha[2], vx_fri** out);
+/* Merkle tree over the current layer's bit-reversed values, `2^arity_bits` extension values per leaf */
+int32_t vx_fri_commit_layer(vx_fri* f, uint32_t arity_bits, uint32_t cap_height, uint64_t* cap_out);
+int32_t vx_fri_fold(vx_fri* f, const uint64_t beta[2]);
+/* truncated final polynomial: out holds (len >> rate_bits) x 2 */
+int32_t vx_fri_final_poly(vx_fri* f, uint64_t* out, uint32_t* len_out);
+/* query openings of committed layer `layer`: leaf rows (k x 2*arity) and paths (k x depth x 4) */
+int32_t vx_fri_query(vx_fri* f, uint32_t layer, const uint64_t* idx, uint32_t k, uint64_t* rows_out,
+                     uint64_t* paths_out);
+void vx_fri_free(vx_fri* f);
+/* fri_proof_of_work: smallest w such that permute(state with state[pos] = w)[7] has >= min_zeros
+ * leading zero bits (equals the reference's witness under RAYON_NUM_THREADS=1; upstream find_any
+ * is nondeterministic). */
+int32_t vx_pow_grind(vx_ctx* ctx, const uint64_t state[12], uint32_t pos, uint32_t min_zeros, uint64_t* witness_out);
+
 /* ---- MerkleTree (plonky2 hash/merkle_tree.rs; API use in-tree at
  *      P2X/backend/wrapper/poseidon_bn128.rs:217-220) -----------------------------------------
  * vx_merkle_new replaces MerkleTree::<F, PoseidonHash>::new(leaves, cap_height).
@@ -118,6 +189,19 @@ int32_t vx_poseidon_permute(vx_ctx* ctx, const uint64_t* states_in, uint64_t cou
 int32_t vx_hash_no_pad(vx_ctx* ctx, const uint64_t* inputs, uint64_t count, uint32_t len, uint64_t* out);
 /* the 360 round constants the device uses (for audit against the reference table) */
 int32_t vx_poseidon_constants(uint64_t out[360]);
+/* the derived "fast partial round" tables (same refactoring as plonky2's FAST_PARTIAL_*): dense 12x12
+ * matrix D and vector e replacing the MDS layer of full round 3, then per partial round r: post-S-box
+ * constant k[r], first-row entries v[r][11], first-column entries w[r][11]. Used by the PoseidonGate
+ * constraint program. */
+int32_t vx_poseidon_fast_tables(uint64_t dense_d[144], uint64_t dense_e[12], uint64_t k[22], uint64_t v[242],
+                                uint64_t w[242]);
+
+/* ---- field primitives (plonky2_field goldilocks_field.rs, extension/quadratic.rs), elementwise on the
+ *      device over n elements (host in/out): the unit-test surface of the device arithmetic.
+ *      op: 0 a*b, 1 a*b (compiler 64-bit path), 2 a^-1, 3 a*b+c, 4 a+b, 5 a-b, 6 a^7,
+ *          7 extension a*b (pairs), 8 extension a^-1 (pairs; n counts pairs) */
+int32_t vx_field_op(vx_ctx* ctx, uint32_t op, const uint64_t* a, const uint64_t* b, const uint64_t* c, uint64_t n,
+                    uint64_t* out);
 
 /* ---- NTT primitives (plonky2_field fft.rs) on c x n column-major batches, host or device
  *      in/out; natural order in and out ------------------------------------------------------- */

@@ -231,3 +231,38 @@ def test_sharded_commit_matches_whole(ctx, shards):
     assert np.array_equal(np.concatenate(caps), want["cap"])
     assert np.array_equal(np.concatenate(leaves), want["leaves"])
     assert np.array_equal(np.concatenate(digests), want["digests"])
+
+
+def test_field_primitives(ctx):
+    """Goldilocks / quadratic-extension device arithmetic against Python big ints, incl. edge representatives."""
+    from vectorx_b200._lib import check, load, ptr
+    rng = np.random.default_rng(77)
+    n = 4096
+    edge = np.array([0, 1, 2, P - 1, P, P + 1, 2**64 - 1, 0xFFFFFFFF, 0x100000000, 0xFFFFFFFF00000000], dtype=np.uint64)
+    a = rng.integers(0, 2**64, size=n, dtype=np.uint64); b = rng.integers(0, 2**64, size=n, dtype=np.uint64)
+    c = rng.integers(0, 2**64, size=n, dtype=np.uint64)
+    a[:10] = edge; b[:10] = edge[::-1]; a[10:20] = edge; b[10:20] = edge; c[:10] = edge
+    A, B, C = [int(x) for x in a], [int(x) for x in b], [int(x) for x in c]
+
+    def run(op, x, y=None, z=None, words=n):
+        out = np.zeros(words, dtype=np.uint64)
+        check(load().vx_field_op(ctx.handle, op, ptr(x), ptr(y) if y is not None else None,
+                                 ptr(z) if z is not None else None, words if op < 7 else words // 2, ptr(out)), "vx_field_op")
+        return [int(v) for v in out]
+    assert run(0, a, b) == [x * y % P for x, y in zip(A, B)]
+    assert run(1, a, b) == [x * y % P for x, y in zip(A, B)]
+    assert run(3, a, b, c) == [(x * y + z) % P for x, y, z in zip(A, B, C)]
+    assert run(4, a, b) == [(x + y) % P for x, y in zip(A, B)]
+    assert run(5, a, b) == [(x - y) % P for x, y in zip(A, B)]
+    assert run(6, a) == [pow(x, 7, P) for x in A]
+    nz = np.where(a % np.uint64(P) == 0, np.uint64(5), a)
+    assert run(2, nz) == [pow(int(x), P - 2, P) for x in nz]
+    from oracle.field import E2
+    got = run(7, a, b)
+    for i in range(0, n, 2):
+        w = E2(A[i], A[i + 1]) * E2(B[i], B[i + 1])
+        assert got[i:i + 2] == [w.a, w.b]
+    got = run(8, nz)
+    for i in range(0, n, 2):
+        w = E2(int(nz[i]), int(nz[i + 1])).inv()
+        assert got[i:i + 2] == [w.a, w.b]

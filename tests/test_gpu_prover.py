@@ -1,0 +1,149 @@
+"""GPU parity tests (-m gpu) for the rest of the proving path: Z / partial products, quotient evaluation,
+opening evaluation, FRI fold-and-commit, proof-of-work, and the whole proof -- each bit-for-bit against the
+oracle prover (oracle/plonk.py), and the GPU proof must verify under the oracle's independent verifier."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import oracle
+import vectorx_b200 as vx
+from oracle import P, plonk, pyref, synth
+from oracle.field import E2
+from vectorx_b200._lib import check, load, ptr
+
+pytestmark = pytest.mark.gpu
+
+
+def product_circuit(circ, ctx):
+    """Plain data out of the oracle's circuit object -> the product's CircuitData (what the Rust shim serialises)."""
+    return vx.CircuitData(circ.d, [g.id() for g in circ.gates], circ.selector_index, circ.groups, circ.constants,
+                          circ.sigmas, ctx=ctx)
+
+
+@pytest.fixture(scope="module")
+def case(ctx):
+    circ, wires, pis = synth.build(7, seed=3)
+    tr = {}
+    proof = plonk.prove(circ, wires, pis, trace=tr)
+    assert plonk.verify(circ, proof)
+    return circ, wires, pis, proof, tr, product_circuit(circ, ctx)
+
+
+def e2l(e):
+    return [e.a, e.b]
+
+
+def test_circuit_digest_and_constants_sigmas(case):
+    circ, wires, pis, proof, tr, pc = case
+    assert pc.circuit_digest == circ.circuit_digest
+    assert np.array_equal(pc.constants_sigmas_commitment.cap.hashes, circ.cs_commit["cap"])
+    lv, dg = pc.constants_sigmas_commitment.download()        # what CircuitBuild::serialize stores (build.rs:187-242)
+    assert np.array_equal(lv, circ.cs_commit["leaves"]) and np.array_equal(dg, circ.cs_commit["digests"])
+
+
+def test_zs_partial_products(case, ctx):
+    circ, wires, pis, proof, tr, pc = case
+    out = np.zeros_like(tr["zpp"])
+    betas, gammas = np.array(tr["betas"], dtype=np.uint64), np.array(tr["gammas"], dtype=np.uint64)
+    check(load().vx_zs_partial_products(ctx.handle, ctypes.byref(pc.desc), ptr(wires), ptr(pc.sigmas),
+                                        ptr(betas), ptr(gammas), ptr(out)), "zpp")
+    assert np.array_equal(out, tr["zpp"])
+    assert (out[:2, 0] == 1).all()
+
+
+def test_quotient_polys(case, ctx):
+    circ, wires, pis, proof, tr, pc = case
+    rate, cap = pc.rate_bits, pc.cap_height
+    wb = vx.PolynomialBatch.from_values(wires, rate, False, cap, ctx=ctx)
+    zb = vx.PolynomialBatch.from_values(tr["zpp"], rate, False, cap, ctx=ctx)
+    N = pc.n << rate
+    q = np.zeros((2, N), dtype=np.uint64)
+    u = lambda xs: np.array([int(x) for x in xs], dtype=np.uint64)
+    pi, betas, gammas, alphas = u(tr["pi_hash"]), u(tr["betas"]), u(tr["gammas"]), u(tr["alphas"])
+    check(load().vx_quotient(ctx.handle, ctypes.byref(pc.desc), pc.constants_sigmas_commitment.handle, wb.handle,
+                             zb.handle, ptr(pi), ptr(betas), ptr(gammas), ptr(alphas), ptr(q)), "vx_quotient")
+    for k in range(2):
+        assert np.array_equal(q[k], tr["quotient_full"][k])
+    assert np.array_equal(q.reshape(16, pc.n), tr["quotient_coeffs"])
+
+
+def test_opening_evaluation(case, ctx):
+    circ, wires, pis, proof, tr, pc = case
+    b = vx.PolynomialBatch.from_values(wires[:9], pc.rate_bits, False, pc.cap_height, ctx=ctx)
+    z = tr["zeta"]
+    out = np.zeros((9, 2), dtype=np.uint64)
+    zz = np.array(e2l(z), dtype=np.uint64)
+    check(load().vx_batch_eval_ext(b.handle, ptr(zz), ptr(out)), "eval")
+    coeffs = b.polynomials
+    for j in range(9):
+        want = plonk.eval_base_poly_ext(coeffs[j], z)
+        assert [int(out[j, 0]), int(out[j, 1])] == e2l(want)
+
+
+@pytest.mark.parametrize("pos", [0, 3, 7])
+def test_pow_grind_smallest_witness(ctx, pos):
+    rng = np.random.default_rng(pos)
+    st = oracle.random_field((12,), seed=40 + pos)
+    w = ctypes.c_uint64(0)
+    check(load().vx_pow_grind(ctx.handle, ptr(st), pos, 12, ctypes.byref(w)), "pow")
+    s = [int(x) for x in st]
+    cand = 0
+    while True:
+        t = s[:]; t[pos] = cand
+        if int(oracle.poseidon(t)[7]) >> 52 == 0:
+            break
+        cand += 1
+    assert w.value == cand
+
+
+def normalise(proof):
+    """Oracle proofs hold E2 objects, product proofs hold [a, b] lists: bring both to plain nested lists."""
+    def ext(e):
+        return e2l(e) if isinstance(e, E2) else [int(e[0]), int(e[1])]
+    out = {"caps": [np.asarray(proof[k]).tolist() for k in ("wires_cap", "zs_pp_cap", "quotient_cap")],
+           "openings": {k: [ext(e) for e in v] for k, v in proof["openings"].items()},
+           "fri_caps": [np.asarray(c).tolist() for c in proof["fri_caps"]],
+           "final_poly": [ext(e) for e in proof["final_poly"]], "pow_witness": int(proof["pow_witness"]),
+           "queries": [{"x_index": int(q["x_index"]),
+                        "initial": [(np.asarray(r).tolist(), np.asarray(p).tolist()) for r, p in q["initial"]],
+                        "steps": [(np.asarray(r).tolist(), np.asarray(p).tolist()) for r, p in q["steps"]]}
+                       for q in proof["queries"]]}
+    return out
+
+
+def to_oracle_proof(proof):
+    p = dict(proof)
+    p["openings"] = {k: [E2(int(e[0]), int(e[1])) for e in v] for k, v in proof["openings"].items()}
+    p["final_poly"] = [E2(int(e[0]), int(e[1])) for e in proof["final_poly"]]
+    return p
+
+
+def test_full_proof_equals_oracle_and_verifies(case):
+    circ, wires, pis, proof, tr, pc = case
+    gtr = {}
+    gp = vx.prove(pc, wires, pis, trace=gtr)
+    assert gtr["betas"] == tr["betas"] and gtr["gammas"] == tr["gammas"] and gtr["alphas"] == tr["alphas"]
+    assert np.array_equal(gtr["zpp"], tr["zpp"])
+    assert np.array_equal(gtr["quotient_coeffs"], tr["quotient_coeffs"])
+    assert gtr["zeta"] == e2l(tr["zeta"])
+    a, b = normalise(gp), normalise(proof)
+    for key in ("caps", "openings", "fri_caps", "final_poly", "pow_witness"):
+        assert a[key] == b[key], key
+    assert a["queries"] == b["queries"]
+    assert plonk.verify(circ, to_oracle_proof(gp))              # the unchanged (oracle) verifier accepts the GPU proof
+    bad = to_oracle_proof(gp)
+    bad["final_poly"][0] = bad["final_poly"][0] + 1
+    assert not plonk.verify(circ, bad)
+
+
+@pytest.mark.parametrize("degree_bits,mix", [(5, ("arith", "const")), (6, ("poseidon",)), (8, ("u32arith", "u32sub", "u32range", "basesum")),
+                                             (9, ("poseidon", "arith", "const", "u32arith", "u32sub", "u32range", "basesum"))])
+def test_proofs_of_other_shapes_verify(ctx, degree_bits, mix):
+    circ, wires, pis = synth.build(degree_bits, seed=degree_bits, mix=mix)
+    pc = product_circuit(circ, ctx)
+    gp = vx.prove(pc, wires, pis)
+    assert plonk.verify(circ, to_oracle_proof(gp))
+    if degree_bits <= 6:
+        op = plonk.prove(circ, wires, pis)
+        assert normalise(gp) == normalise(op)

@@ -49,6 +49,18 @@ SIGNATURES = {
     "vx_poseidon_permute": (c_i32, [vp, vp, c_u64, vp]),
     "vx_hash_no_pad": (c_i32, [vp, vp, c_u64, c_u32, vp]),
     "vx_poseidon_constants": (c_i32, [vp]),
+    "vx_poseidon_fast_tables": (c_i32, [vp, vp, vp, vp, vp]),
+    "vx_zs_partial_products": (c_i32, [vp, vp, vp, vp, vp, vp, vp]),
+    "vx_quotient": (c_i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "vx_batch_eval_ext": (c_i32, [vp, vp, vp]),
+    "vx_fri_begin": (c_i32, [vp, vp, c_u32, vp, c_u32, vp, ctypes.POINTER(vp)]),
+    "vx_fri_commit_layer": (c_i32, [vp, c_u32, c_u32, vp]),
+    "vx_fri_fold": (c_i32, [vp, vp]),
+    "vx_fri_final_poly": (c_i32, [vp, vp, u32p]),
+    "vx_fri_query": (c_i32, [vp, c_u32, vp, c_u32, vp, vp]),
+    "vx_fri_free": (None, [vp]),
+    "vx_pow_grind": (c_i32, [vp, vp, c_u32, c_u32, vp]),
+    "vx_field_op": (c_i32, [vp, c_u32, vp, vp, vp, c_u64, vp]),
     "vx_ntt": (c_i32, [vp, vp, vp, c_u32, c_u32, c_i32, c_u64]),
 }
 

@@ -1,0 +1,88 @@
+"""Host-side Fiat-Shamir challenger (plonky2 iop/challenger.rs `Challenger<F, PoseidonHash>`).
+
+north_star keeps the challenger on the host: it absorbs a few hundred elements per proof.  The duplex
+sponge needs a scalar Poseidon permutation, implemented here with Python integers from the library's
+own round constants (vx_poseidon_constants)."""
+from __future__ import annotations
+
+from .plonky2 import poseidon_round_constants
+
+P = 0xFFFFFFFF00000001
+_CIRC = [17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20]
+_RC = None
+
+
+def poseidon_host(state):
+    global _RC
+    if _RC is None:
+        _RC = [int(x) for x in poseidon_round_constants()]
+    s = [int(x) % P for x in state]
+    for r in range(30):
+        s = [(s[i] + _RC[12 * r + i]) % P for i in range(12)]
+        if r < 4 or r >= 26:
+            s = [pow(x, 7, P) for x in s]
+        else:
+            s[0] = pow(s[0], 7, P)
+        s = [(sum(s[(i + j) % 12] * _CIRC[i] for i in range(12)) + (8 * s[0] if j == 0 else 0)) % P for j in range(12)]
+    return s
+
+
+def hash_no_pad_host(inputs):
+    st = [0] * 12
+    for off in range(0, len(inputs), 8):
+        chunk = inputs[off:off + 8]
+        st[:len(chunk)] = [int(x) % P for x in chunk]
+        st = poseidon_host(st)
+    return st[:4]
+
+
+class Challenger:
+    def __init__(self):
+        self.sponge_state = [0] * 12
+        self.input_buffer = []
+        self.output_buffer = []
+
+    def _duplexing(self):
+        for i, x in enumerate(self.input_buffer):
+            self.sponge_state[i] = x
+        self.input_buffer = []
+        self.sponge_state = poseidon_host(self.sponge_state)
+        self.output_buffer = self.sponge_state[:8]
+
+    def observe_element(self, x):
+        self.output_buffer = []
+        self.input_buffer.append(int(x) % P)
+        if len(self.input_buffer) == 8:
+            self._duplexing()
+
+    def observe_elements(self, xs):
+        for x in xs:
+            self.observe_element(x)
+
+    def observe_hash(self, h):
+        self.observe_elements(h)
+
+    def observe_cap(self, cap):
+        for h in cap:
+            self.observe_elements(h)
+
+    def observe_extension_element(self, e):
+        self.observe_elements(e)
+
+    def get_challenge(self):
+        if self.input_buffer or not self.output_buffer:
+            self._duplexing()
+        return self.output_buffer.pop()
+
+    def get_n_challenges(self, n):
+        return [self.get_challenge() for _ in range(n)]
+
+    def get_extension_challenge(self):
+        return [self.get_challenge(), self.get_challenge()]
+
+    def pow_state(self):
+        """(state with pending inputs written, position of the witness) for fri_proof_of_work."""
+        st = list(self.sponge_state)
+        for i, x in enumerate(self.input_buffer):
+            st[i] = x
+        return st, len(self.input_buffer)

@@ -1,5 +1,6 @@
 // C ABI of libvectorx_b200 (see include/vectorx_b200.h for what each entry point replaces).
 #include "common.cuh"
+#include "poseidon_tables.h"
 
 // ------------------------------------------------------------------------------------------------ errors
 static thread_local char g_err[512] = "";
@@ -74,6 +75,7 @@ extern "C" int32_t vx_ctx_create(int32_t device, vx_ctx** out) {
     for (int i = 0; i < VX_NUM_PHASE_EVENTS; i++) cudaEventCreate(&ctx->ev[i]);
     int32_t r = poseidon_module_init(ctx);
     if (r == VX_OK) r = ntt_module_init(ctx);
+    if (r == VX_OK) r = fri_module_init(ctx);
     if (r != VX_OK) { vx_ctx_destroy(ctx); return r; }
     *out = ctx;
     return VX_OK;
@@ -106,38 +108,6 @@ extern "C" int32_t vx_ctx_phase_ms(vx_ctx* ctx, float out[VX_NUM_PHASE_EVENTS - 
 }
 extern "C" void* vx_ctx_stream(vx_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 extern "C" uint64_t vx_ctx_launch_count(vx_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
-
-struct CtxGuard {       // one call at a time per context; binds the device to the calling thread
-    std::lock_guard<std::mutex> lk;
-    explicit CtxGuard(vx_ctx* c) : lk(c->mu) { cudaSetDevice(c->device); }
-};
-
-// copy helpers that accept host or device memory on either side
-static int32_t copy_in(vx_ctx* ctx, u64* dst_dev, const u64* src, size_t bytes) {
-    VX_CUDA(cudaMemcpyAsync(dst_dev, src, bytes, cudaMemcpyDefault, ctx->stream));
-    return VX_OK;
-}
-static int32_t copy_out(vx_ctx* ctx, u64* dst, const u64* src_dev, size_t bytes) {
-    VX_CUDA(cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDefault, ctx->stream));
-    return VX_OK;
-}
-
-// ------------------------------------------------------------------------------------------------ PolynomialBatch
-struct vx_batch {
-    vx_ctx* ctx;
-    uint32_t c, log_n, rate_bits, cap_height;
-    uint32_t blk_first, blk_count;      // leaf blocks (cosets) held: all 2^rate_bits unless sharded
-    DevBuf coeffs;    // c x n
-    DevBuf lde;       // c x N_loc column-major, leaf order
-    DevBuf digests;   // 2 (N_loc - caps_loc) x 4
-    DevBuf cap;       // caps_loc x 4
-    uint64_t n() const { return 1ULL << log_n; }
-    uint64_t N() const { return 1ULL << (log_n + rate_bits); }
-    uint64_t N_loc() const { return (uint64_t)blk_count << log_n; }
-    uint64_t leaf_first() const { return (uint64_t)blk_first << log_n; }
-    uint32_t shard_bits() const { return rate_bits - ilog2(blk_count); }   // log2(number of shards)
-    uint32_t cap_height_loc() const { return cap_height - shard_bits(); }
-};
 
 #define EV(ctx, i) VX_CUDA(cudaEventRecord((ctx)->ev[i], (ctx)->stream))
 
@@ -424,6 +394,20 @@ extern "C" int32_t vx_hash_no_pad(vx_ctx* ctx, const uint64_t* in, uint64_t coun
 extern "C" int32_t vx_poseidon_constants(uint64_t out[360]) {
     if (!out) { vx_set_error("vx_poseidon_constants: NULL"); return VX_EINVAL; }
     poseidon_round_constants_host((u64*)out);
+    return VX_OK;
+}
+
+extern "C" int32_t vx_poseidon_fast_tables(uint64_t dense_d[144], uint64_t dense_e[12], uint64_t k[22], uint64_t v[242],
+                                           uint64_t w[242]) {
+    if (!dense_d || !dense_e || !k || !v || !w) { vx_set_error("vx_poseidon_fast_tables: NULL"); return VX_EINVAL; }
+    u64 rc[360];
+    poseidon_round_constants_host(rc);
+    PoseidonTables t;
+    if (!poseidon_derive_tables(rc, &t)) { vx_set_error("poseidon: table derivation failed"); return VX_EINVAL; }
+    for (int i = 0; i < 144; i++) dense_d[i] = t.dense_d[i];
+    for (int i = 0; i < 12; i++) dense_e[i] = t.dense_e[i];
+    for (int i = 0; i < 22; i++) k[i] = t.pk[i];
+    for (int i = 0; i < 242; i++) { v[i] = t.pv[i]; w[i] = t.pw[i]; }
     return VX_OK;
 }
 

@@ -68,6 +68,15 @@ struct TwiddleView {     // passed by value to kernels
     const u64* roots12;  // w_4096^e
 };
 
+// W^E for a 32-bit exponent (W of order 2^32): w_M^e = W^(e << (32 - log M))
+#ifdef __CUDACC__
+GL_D u64 tw_pow_view(const TwiddleView& tw, u32 E) {
+    u64 h = __ldg(tw.hi + (E >> 16));
+    u32 l = E & 0xffffu;
+    return l ? gl_mul_cc(h, __ldg(tw.lo + l)) : h;
+}
+#endif
+
 #define VX_LAUNCH_COUNT(ctx, n) (ctx)->launches.fetch_add((n), std::memory_order_relaxed)
 
 // classify a pointer: returns true if it is device memory
@@ -101,6 +110,38 @@ __host__ __device__ static inline uint64_t bitrev_u64(uint64_t x, unsigned bits)
 #endif
 }
 
+struct CtxGuard {       // one call at a time per context; binds the device to the calling thread
+    std::lock_guard<std::mutex> lk;
+    explicit CtxGuard(vx_ctx* c) : lk(c->mu) { cudaSetDevice(c->device); }
+};
+
+// copy helpers that accept host or device memory on either side
+static inline int32_t copy_in(vx_ctx* ctx, u64* dst_dev, const u64* src, size_t bytes) {
+    VX_CUDA(cudaMemcpyAsync(dst_dev, src, bytes, cudaMemcpyDefault, ctx->stream));
+    return VX_OK;
+}
+static inline int32_t copy_out(vx_ctx* ctx, u64* dst, const u64* src_dev, size_t bytes) {
+    VX_CUDA(cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDefault, ctx->stream));
+    return VX_OK;
+}
+
+struct vx_batch {
+    vx_ctx* ctx;
+    uint32_t c, log_n, rate_bits, cap_height;
+    uint32_t blk_first, blk_count;      // leaf blocks (cosets) held: all 2^rate_bits unless sharded
+    DevBuf coeffs;    // c x n
+    DevBuf lde;       // c x N_loc column-major, leaf order
+    DevBuf digests;   // 2 (N_loc - caps_loc) x 4
+    DevBuf cap;       // caps_loc x 4
+    uint64_t n() const { return 1ULL << log_n; }
+    uint64_t N() const { return 1ULL << (log_n + rate_bits); }
+    uint64_t N_loc() const { return (uint64_t)blk_count << log_n; }
+    uint64_t leaf_first() const { return (uint64_t)blk_first << log_n; }
+    uint32_t shard_bits() const { return rate_bits - ilog2(blk_count); }   // log2(number of shards)
+    uint32_t cap_height_loc() const { return cap_height - shard_bits(); }
+};
+
+
 // ---- module entry points (one per .cu) ------------------------------------------------------------
 int32_t poseidon_module_init(vx_ctx* ctx);                 // merkle.cu: uploads round constants
 void poseidon_round_constants_host(u64 out[360]);          // merkle.cu: ChaCha8Rng(0) derivation
@@ -123,6 +164,7 @@ int32_t hash_no_pad_device(vx_ctx* ctx, const u64* in, uint64_t count, uint32_t 
 
 // ntt.cu ------------------------------------------------------------------------------------------
 int32_t ntt_module_init(vx_ctx* ctx);
+int32_t fri_module_init(vx_ctx* ctx);                      // fri.cu: its own copy of the Poseidon tables
 void ntt_module_destroy(vx_ctx* ctx);
 // In-place forward DIF NTT of `count` contiguous transforms of size 2^log_n starting at data
 // (transform t occupies data[t << log_n ...]); output in bit-reversed order. inverse uses w^-1.
@@ -137,3 +179,5 @@ int32_t lde_batch(vx_ctx* ctx, const u64* coeffs, u64* lde_out, uint32_t c, uint
 // generic natural-order transform used by vx_ntt (tests, FRI layers)
 int32_t ntt_natural(vx_ctx* ctx, const u64* in, u64* out, uint32_t c, uint32_t log_n, bool inverse,
                     uint64_t coset_shift);
+// in place: data[col][m] *= shift^m, then DIF NTT -> evaluations on shift*<w_n> in bit-reversed order
+int32_t coset_ntt_bitrev_inplace(vx_ctx* ctx, u64* data, uint32_t c, uint32_t log_n, uint64_t shift);

@@ -318,3 +318,39 @@ GL_D u64 gl_pow(u64 a, u64 e) {
     return r;
 }
 GL_D u64 gl_inv(u64 a) { return gl_pow(a, GL_P - 2); }
+
+// ---- quadratic extension F[x]/(x^2 - 7) (plonky2_field extension/quadratic.rs; bound at
+// contracts/lib/succinctx/plonky2x/core/src/backend/circuit/config.rs:41) --------------------------
+struct gl2 {
+    u64 a, b;       // a + b x
+};
+__host__ __device__ __forceinline__ gl2 gl2_make(u64 a, u64 b) { gl2 r; r.a = a; r.b = b; return r; }
+GL_D gl2 gl2_add(gl2 x, gl2 y) { return gl2_make(gl_add(x.a, y.a), gl_add(x.b, y.b)); }
+GL_D gl2 gl2_sub(gl2 x, gl2 y) { return gl2_make(gl_sub(x.a, y.a), gl_sub(x.b, y.b)); }
+GL_D gl2 gl2_mul(gl2 x, gl2 y) {
+    // (a0 b0 + 7 a1 b1) + (a0 b1 + a1 b0) x, two lazy dot products
+    GlAcc t0, t1;
+    gl_acc_init(t0, 0); gl_acc_init(t1, 0);
+    u64 b7 = gl_mul_cc(y.b, 7);
+    gl_acc_mad(t0, x.a, y.a); gl_acc_mad(t0, x.b, b7);
+    gl_acc_mad(t1, x.a, y.b); gl_acc_mad(t1, x.b, y.a);
+    return gl2_make(gl_acc_reduce(t0), gl_acc_reduce(t1));
+}
+GL_D gl2 gl2_mul_base(gl2 x, u64 k) { return gl2_make(gl_mul_cc(x.a, k), gl_mul_cc(x.b, k)); }
+GL_D gl2 gl2_add_base(gl2 x, u64 k) { return gl2_make(gl_add(x.a, k), x.b); }
+GL_D gl2 gl2_canon(gl2 x) { return gl2_make(gl_canon(x.a), gl_canon(x.b)); }
+GL_D gl2 gl2_pow(gl2 x, u64 e) {
+    gl2 r = gl2_make(1, 0);
+    while (e) {
+        if (e & 1) r = gl2_mul(r, x);
+        x = gl2_mul(x, x);
+        e >>= 1;
+    }
+    return r;
+}
+GL_D gl2 gl2_inv(gl2 x) {
+    // 1/(a + b x) = (a - b x) / (a^2 - 7 b^2)
+    u64 norm = gl_sub(gl_mul_cc(x.a, x.a), gl_mul_cc(7, gl_mul_cc(x.b, x.b)));
+    u64 ni = gl_inv(norm);
+    return gl2_make(gl_mul_cc(x.a, ni), gl_mul_cc(gl_neg(x.b), ni));
+}

@@ -270,3 +270,14 @@ int32_t ntt_natural(vx_ctx* ctx, const u64* in, u64* out, uint32_t c, uint32_t l
     VX_CUDA(cudaGetLastError());
     return VX_OK;
 }
+
+int32_t coset_ntt_bitrev_inplace(vx_ctx* ctx, u64* data, uint32_t c, uint32_t log_n, uint64_t shift) {
+    uint64_t n = 1ULL << log_n;
+    if (shift > 1) {
+        dim3 grid((unsigned)((n + 255) / 256), c);
+        coset_scale_kernel<<<grid, 256, 0, ctx->stream>>>(data, log_n, shift);
+        VX_LAUNCH_COUNT(ctx, 1);
+        VX_CUDA(cudaGetLastError());
+    }
+    return ntt_dif_inplace(ctx, data, c, log_n, false);
+}

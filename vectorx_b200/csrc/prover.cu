@@ -1,0 +1,394 @@
+// Constraint evaluation over the LDE domain, Z / partial products, and opening evaluation.
+//
+// Replaces plonky2 v0.2.0 plonk/prover.rs `compute_quotient_polys`, plonk/vanishing_poly.rs
+// `eval_vanishing_poly_base_batch`, every registered `Gate::eval_unfiltered_base_batch`
+// (contracts/lib/succinctx/plonky2x/core/src/backend/circuit/serialization/gates.rs:85-107), the
+// permutation-argument part of `prove_with_partition_witness`
+// (.../backend/circuit/build.rs:69-75 is the reference call site) and `OpeningSet::new`.
+//
+// Layout: the three committed batches keep their LDE column-major in leaf (bit-reversed) order, so
+// thread j evaluates LDE point bitrev(j) and every column load of a warp is 256 contiguous bytes.
+// Gate constraints run as a register bytecode (include/vectorx_b200.h) whose register file is a
+// [VX_PROGRAM_REGS][blockDim] shared-memory array; instruction words are warp-uniform loads.
+// Constraint terms are alpha-reduced with lazy 128-bit dot products (one reduction per challenge).
+#include "common.cuh"
+
+#define QBLOCK 128
+
+struct QuotParams {
+    const u64 *cs, *wires, *zpp;       // LDE column-major, leaf order, stride N
+    uint64_t N;
+    uint32_t bits, rate_bits, degree_bits;
+    uint32_t num_wires, num_routed, num_constants, num_selectors, num_challenges, num_pp, max_degree;
+    const u64* program;
+    const u64* beta_k;                 // [challenge][routed]  beta_k * k_j
+    const u64* apow;                   // [challenge][num_terms] alpha_k^j
+    uint32_t num_terms, num_perm_terms;
+    u64 betas[4], gammas[4];
+    u64 pi_hash[4];
+    u64 zh_inv[64];                    // 1 / Z_H on the 2^rate_bits cosets of the subgroup
+    u64 zh[64];
+    u64 n_inv;
+    u64* out;                          // [challenge][N], leaf order
+    TwiddleView tw;
+};
+
+__global__ void __launch_bounds__(QBLOCK) quotient_kernel(const QuotParams p) {
+    extern __shared__ u64 regfile[];
+    u64* R = regfile + threadIdx.x;
+#define REG(i) R[(i) * QBLOCK]
+    const uint64_t j = (uint64_t)blockIdx.x * QBLOCK + threadIdx.x;
+    if (j >= p.N) return;
+    const uint64_t N = p.N;
+    const uint32_t i = (uint32_t)bitrev_u64(j, p.bits);                 // natural LDE index
+    const u64 x = gl_mul_cc(GL_GENERATOR, tw_pow_view(p.tw, i << (32 - p.bits)));
+    const uint32_t coset = i & ((1u << p.rate_bits) - 1);
+    const u64 zh = p.zh[coset];
+    // L_0(x) = Z_H(x) / (n (x - 1))
+    const u64 l0 = gl_mul_cc(gl_mul_cc(zh, p.n_inv), gl_inv(gl_sub(x, 1)));
+    const uint64_t jn = bitrev_u64((i + (1u << p.rate_bits)) & (N - 1), p.bits);   // leaf of g_n * x
+
+    GlAcc tot[2];
+    for (uint32_t k = 0; k < p.num_challenges; k++) gl_acc_init(tot[k], 0);
+    const uint32_t nch = p.num_challenges;
+    const u64* apow0 = p.apow;
+    const u64* apow1 = p.apow + p.num_terms;
+#define ADD_TERM(idx, val)                                        \
+    do {                                                          \
+        u64 _v = (val);                                           \
+        gl_acc_mad(tot[0], _v, __ldg(apow0 + (idx)));             \
+        if (nch > 1) gl_acc_mad(tot[1], _v, __ldg(apow1 + (idx))); \
+    } while (0)
+
+    // ---- Z(1) = 1 and the permutation argument
+    const uint32_t chunks = (p.num_routed + p.max_degree - 1) / p.max_degree;
+    for (uint32_t k = 0; k < nch; k++) {
+        u64 z = p.zpp[(uint64_t)k * N + j];
+        ADD_TERM(k, gl_mul_cc(l0, gl_sub(z, 1)));
+        u64 prev = z;
+        const u64 beta = p.betas[k], gamma = p.gammas[k];
+        for (uint32_t c = 0; c < chunks; c++) {
+            u64 num = 1, den = 1;
+            uint32_t hi = min(p.num_routed, (c + 1) * p.max_degree);
+            for (uint32_t w = c * p.max_degree; w < hi; w++) {
+                u64 wv = p.wires[(uint64_t)w * N + j];
+                u64 sg = p.cs[(uint64_t)(p.num_constants + w) * N + j];
+                u64 a = gl_add(gl_mul_add_cc(x, __ldg(p.beta_k + k * p.num_routed + w), wv), gamma);
+                u64 b = gl_add(gl_mul_add_cc(sg, beta, wv), gamma);
+                num = gl_mul_cc(num, a);
+                den = gl_mul_cc(den, b);
+            }
+            u64 next = (c + 1 < chunks) ? p.zpp[(uint64_t)(nch + k * p.num_pp + c) * N + j]
+                                        : p.zpp[(uint64_t)k * N + jn];
+            ADD_TERM(nch + k * chunks + c, gl_sub(gl_mul_cc(prev, num), gl_mul_cc(next, den)));
+            prev = next;
+        }
+    }
+
+    // ---- gate constraints: bytecode interpreter
+    const u64* pc = p.program;
+    GlAcc h[2];
+    uint32_t cidx = 0;
+    for (;;) {
+        const u64 ins = __ldg(pc++);
+        const uint32_t op = (uint32_t)ins & 0xff, dst = (uint32_t)(ins >> 8) & 0xff;
+        const uint32_t ra = (uint32_t)(ins >> 16) & 0xff, rb = (uint32_t)(ins >> 24) & 0xff;
+        const uint32_t imm = (uint32_t)(ins >> 32);
+        if (op == VX_OP_END) break;
+        switch (op) {
+            case VX_OP_LOADW: REG(dst) = p.wires[(uint64_t)imm * N + j]; break;
+            case VX_OP_LOADC: REG(dst) = p.cs[(uint64_t)imm * N + j]; break;
+            case VX_OP_LOADPI: REG(dst) = p.pi_hash[imm & 3]; break;
+            case VX_OP_LOADK: REG(dst) = __ldg(pc++); break;
+            case VX_OP_ADD: REG(dst) = gl_add(REG(ra), REG(rb)); break;
+            case VX_OP_SUB: REG(dst) = gl_sub(REG(ra), REG(rb)); break;
+            case VX_OP_MUL: REG(dst) = gl_mul_cc(REG(ra), REG(rb)); break;
+            case VX_OP_ADDK: REG(dst) = gl_add(REG(ra), __ldg(pc++)); break;
+            case VX_OP_MULK: REG(dst) = gl_mul_cc(REG(ra), __ldg(pc++)); break;
+            case VX_OP_RSUBK: REG(dst) = gl_sub(__ldg(pc++), REG(ra)); break;
+            case VX_OP_SUBK: REG(dst) = gl_sub(REG(ra), __ldg(pc++)); break;
+            case VX_OP_BEGINGATE:
+                gl_acc_init(h[0], 0); gl_acc_init(h[1], 0);
+                cidx = p.num_perm_terms;
+                break;
+            case VX_OP_EMIT: {
+                u64 v = REG(ra);
+                gl_acc_mad(h[0], v, __ldg(apow0 + cidx));
+                if (nch > 1) gl_acc_mad(h[1], v, __ldg(apow1 + cidx));
+                cidx++;
+                break;
+            }
+            case VX_OP_ENDGATE: {
+                u64 f = (ra == 255) ? 1 : REG(ra);
+                gl_acc_mad(tot[0], f, gl_acc_reduce(h[0]));
+                if (nch > 1) gl_acc_mad(tot[1], f, gl_acc_reduce(h[1]));
+                break;
+            }
+            default: break;
+        }
+    }
+    const u64 zi = p.zh_inv[coset];
+    for (uint32_t k = 0; k < nch; k++) p.out[(uint64_t)k * N + j] = gl_canon(gl_mul_cc(gl_acc_reduce(tot[k]), zi));
+#undef REG
+#undef ADD_TERM
+}
+
+// out[col][bitrev(p)] = in[col][p]
+__global__ void bitrev_permute_kernel(const u64* __restrict__ in, u64* __restrict__ out, uint32_t bits) {
+    uint64_t pidx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pidx >= (1ULL << bits)) return;
+    uint64_t base = (uint64_t)blockIdx.y << bits;
+    out[base + bitrev_u64(pidx, bits)] = in[base + pidx];
+}
+
+extern "C" int32_t vx_quotient(vx_ctx* ctx, const vx_circuit_desc* d, vx_batch* cs, vx_batch* wires, vx_batch* zpp,
+                               const uint64_t pi_hash[4], const uint64_t* betas, const uint64_t* gammas,
+                               const uint64_t* alphas, uint64_t* out) {
+    VX_REQUIRE(ctx && d && cs && wires && zpp && pi_hash && betas && gammas && alphas && out, "vx_quotient: NULL argument");
+    VX_REQUIRE(d->num_challenges >= 1 && d->num_challenges <= 2, "vx_quotient: num_challenges %u unsupported", d->num_challenges);
+    VX_REQUIRE(d->rate_bits <= 6, "vx_quotient: rate_bits %u unsupported", d->rate_bits);
+    const uint32_t bits = d->degree_bits + d->rate_bits;
+    const uint64_t N = 1ULL << bits, n = 1ULL << d->degree_bits;
+    VX_REQUIRE(cs->N_loc() == N && wires->N_loc() == N && zpp->N_loc() == N &&
+               cs->log_n == d->degree_bits && wires->log_n == d->degree_bits && zpp->log_n == d->degree_bits,
+               "vx_quotient: batches must be whole (unsharded) commitments of degree 2^%u, rate %u", d->degree_bits, d->rate_bits);
+    VX_REQUIRE(wires->c == d->num_wires && cs->c == d->num_constants + d->num_routed_wires &&
+               zpp->c == d->num_challenges * (1 + d->num_partial_products), "vx_quotient: batch widths do not match the circuit");
+    const uint32_t chunks = (d->num_routed_wires + d->max_degree - 1) / d->max_degree;
+    VX_REQUIRE(chunks == d->num_partial_products + 1, "vx_quotient: num_partial_products inconsistent with max_degree");
+    CtxGuard g(ctx);
+    const uint32_t nch = d->num_challenges;
+    const uint32_t perm_terms = nch + nch * chunks;
+    const uint32_t num_terms = perm_terms + d->num_gate_constraints;
+    std::vector<u64> h_apow((size_t)nch * num_terms), h_betak((size_t)nch * d->num_routed_wires);
+    for (uint32_t k = 0; k < nch; k++) {
+        u64 acc = 1, al = alphas[k] % GL_P;
+        for (uint32_t t = 0; t < num_terms; t++) { h_apow[(size_t)k * num_terms + t] = acc; acc = gl_mul_slow(acc, al); }
+        for (uint32_t w = 0; w < d->num_routed_wires; w++)
+            h_betak[(size_t)k * d->num_routed_wires + w] = gl_mul_slow(betas[k] % GL_P, d->k_is[w] % GL_P);
+    }
+    DevBuf d_apow, d_betak, d_prog, d_q, d_qnat;
+    VX_CHECK(d_apow.alloc(h_apow.size() * 8, ctx->stream));
+    VX_CHECK(d_betak.alloc(h_betak.size() * 8, ctx->stream));
+    VX_CHECK(d_prog.alloc((d->program_len + 1) * 8, ctx->stream));
+    VX_CHECK(d_q.alloc((size_t)nch * N * 8, ctx->stream));
+    VX_CHECK(d_qnat.alloc((size_t)nch * N * 8, ctx->stream));
+    VX_CUDA(cudaMemcpyAsync(d_apow.p, h_apow.data(), h_apow.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    VX_CUDA(cudaMemcpyAsync(d_betak.p, h_betak.data(), h_betak.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<u64> prog(d->program, d->program + d->program_len);
+    prog.push_back(VX_OP_END);
+    VX_CUDA(cudaMemcpyAsync(d_prog.p, prog.data(), prog.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+
+    QuotParams p;
+    memset(&p, 0, sizeof p);
+    p.cs = cs->lde.p; p.wires = wires->lde.p; p.zpp = zpp->lde.p;
+    p.N = N; p.bits = bits; p.rate_bits = d->rate_bits; p.degree_bits = d->degree_bits;
+    p.num_wires = d->num_wires; p.num_routed = d->num_routed_wires; p.num_constants = d->num_constants;
+    p.num_selectors = d->num_selectors; p.num_challenges = nch; p.num_pp = d->num_partial_products;
+    p.max_degree = d->max_degree;
+    p.program = d_prog.p; p.beta_k = d_betak.p; p.apow = d_apow.p;
+    p.num_terms = num_terms; p.num_perm_terms = perm_terms;
+    for (uint32_t k = 0; k < nch; k++) { p.betas[k] = betas[k] % GL_P; p.gammas[k] = gammas[k] % GL_P; }
+    for (int t = 0; t < 4; t++) p.pi_hash[t] = pi_hash[t] % GL_P;
+    // Z_H(g w_N^i) = g^n * (w_N^n)^i - 1 depends on i mod 2^rate_bits only
+    u64 gn = gl_pow_host(GL_GENERATOR, n), wr = gl_root_of_unity_host(d->rate_bits), acc = 1;
+    for (uint32_t c = 0; c < (1u << d->rate_bits); c++) {
+        u64 v = gl_mul_slow(gn, acc);
+        v = v ? v - 1 : GL_P - 1;
+        VX_REQUIRE(v != 0, "vx_quotient: Z_H vanishes on the coset");
+        p.zh[c] = v;
+        p.zh_inv[c] = gl_inv_host(v);
+        acc = gl_mul_slow(acc, wr);
+    }
+    p.n_inv = gl_inv_host(n % GL_P);
+    p.out = d_q.p;
+    p.tw.lo = ctx->w_lo; p.tw.hi = ctx->w_hi; p.tw.roots12 = ctx->roots12;
+    size_t smem = (size_t)VX_PROGRAM_REGS * QBLOCK * sizeof(u64);
+    VX_CUDA(cudaFuncSetAttribute(quotient_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    quotient_kernel<<<(unsigned)((N + QBLOCK - 1) / QBLOCK), QBLOCK, smem, ctx->stream>>>(p);
+    VX_LAUNCH_COUNT(ctx, 1);
+    VX_CUDA(cudaGetLastError());
+    // leaf order -> natural order, then coset iNTT (transpose + coset_ifft(g) upstream)
+    dim3 grid((unsigned)((N + 255) / 256), nch);
+    bitrev_permute_kernel<<<grid, 256, 0, ctx->stream>>>(d_q.p, d_qnat.p, bits);
+    VX_LAUNCH_COUNT(ctx, 1);
+    VX_CHECK(ntt_natural(ctx, d_qnat.p, d_q.p, nch, bits, true, GL_GENERATOR));
+    VX_CUDA(cudaMemcpyAsync(out, d_q.p, (size_t)nch * N * 8, cudaMemcpyDefault, ctx->stream));
+    VX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ Z / partial products
+// phase 1: per (challenge, row): chunk quotients q_c = prod num / prod den and their row product
+__global__ void zpp_rows_kernel(const u64* __restrict__ wires, const u64* __restrict__ sigmas, uint64_t n,
+                                uint32_t log_n, uint32_t num_routed, uint32_t max_degree, uint32_t chunks,
+                                const u64* __restrict__ beta_k, u64 beta, u64 gamma, TwiddleView tw,
+                                u64* __restrict__ q /* [chunks][n] */, u64* __restrict__ rowprod /* [n] */) {
+    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    u64 s = tw_pow_view(tw, (u32)(r << (32 - log_n)));          // w_n^r
+    u64 rp = 1;
+    for (uint32_t c = 0; c < chunks; c++) {
+        u64 num = 1, den = 1;
+        uint32_t hi = min(num_routed, (c + 1) * max_degree);
+        for (uint32_t w = c * max_degree; w < hi; w++) {
+            u64 wv = wires[(uint64_t)w * n + r];
+            u64 a = gl_add(gl_mul_add_cc(s, __ldg(beta_k + w), wv), gamma);
+            u64 b = gl_add(gl_mul_add_cc(sigmas[(uint64_t)w * n + r], beta, wv), gamma);
+            num = gl_mul_cc(num, a);
+            den = gl_mul_cc(den, b);
+        }
+        u64 qc = gl_canon(gl_mul_cc(num, gl_inv(den)));
+        q[(uint64_t)c * n + r] = qc;
+        rp = gl_mul_cc(rp, qc);
+    }
+    rowprod[r] = gl_canon(rp);
+}
+
+// phase 2: exclusive prefix product over rows, one block; thread t owns a contiguous run of rows
+__global__ void __launch_bounds__(1024) zpp_scan_kernel(const u64* __restrict__ rowprod, uint64_t n, u64* __restrict__ z) {
+    __shared__ u64 part[1024];
+    uint64_t per = (n + blockDim.x - 1) / blockDim.x;
+    uint64_t lo = min(n, (uint64_t)threadIdx.x * per), hi = min(n, lo + per);
+    u64 acc = 1;
+    for (uint64_t r = lo; r < hi; r++) acc = gl_mul_cc(acc, rowprod[r]);
+    part[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u64 run = 1;
+        for (uint32_t t = 0; t < blockDim.x; t++) { u64 v = part[t]; part[t] = run; run = gl_mul_cc(run, v); }
+    }
+    __syncthreads();
+    acc = part[threadIdx.x];
+    for (uint64_t r = lo; r < hi; r++) { z[r] = gl_canon(acc); acc = gl_mul_cc(acc, rowprod[r]); }
+}
+
+// phase 3: partial products inside each row
+__global__ void zpp_fill_kernel(const u64* __restrict__ q, const u64* __restrict__ z, uint64_t n, uint32_t chunks,
+                                u64* __restrict__ pp /* [chunks-1][n] */) {
+    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    u64 acc = z[r];
+    for (uint32_t c = 0; c + 1 < chunks; c++) {
+        acc = gl_mul_cc(acc, q[(uint64_t)c * n + r]);
+        pp[(uint64_t)c * n + r] = gl_canon(acc);
+    }
+}
+
+extern "C" int32_t vx_zs_partial_products(vx_ctx* ctx, const vx_circuit_desc* d, const uint64_t* wires,
+                                          const uint64_t* sigmas, const uint64_t* betas, const uint64_t* gammas,
+                                          uint64_t* out) {
+    VX_REQUIRE(ctx && d && wires && sigmas && betas && gammas && out, "vx_zs_partial_products: NULL argument");
+    CtxGuard g(ctx);
+    const uint64_t n = 1ULL << d->degree_bits;
+    const uint32_t nch = d->num_challenges, R = d->num_routed_wires;
+    const uint32_t chunks = (R + d->max_degree - 1) / d->max_degree;
+    VX_REQUIRE(chunks == d->num_partial_products + 1, "vx_zs_partial_products: num_partial_products inconsistent");
+    DevBuf dw, ds, dq, drp, dout, dbk;
+    VX_CHECK(dw.alloc((size_t)R * n * 8, ctx->stream));           // only routed wires take part
+    VX_CHECK(ds.alloc((size_t)R * n * 8, ctx->stream));
+    VX_CHECK(dq.alloc((size_t)chunks * n * 8, ctx->stream));
+    VX_CHECK(drp.alloc(n * 8, ctx->stream));
+    VX_CHECK(dout.alloc((size_t)nch * chunks * n * 8, ctx->stream));
+    VX_CHECK(dbk.alloc((size_t)R * 8, ctx->stream));
+    VX_CUDA(cudaMemcpyAsync(dw.p, wires, (size_t)R * n * 8, cudaMemcpyDefault, ctx->stream));
+    VX_CUDA(cudaMemcpyAsync(ds.p, sigmas, (size_t)R * n * 8, cudaMemcpyDefault, ctx->stream));
+    TwiddleView tw; tw.lo = ctx->w_lo; tw.hi = ctx->w_hi; tw.roots12 = ctx->roots12;
+    std::vector<u64> bk(R);
+    for (uint32_t k = 0; k < nch; k++) {
+        for (uint32_t w = 0; w < R; w++) bk[w] = gl_mul_slow(betas[k] % GL_P, d->k_is[w] % GL_P);
+        VX_CUDA(cudaMemcpyAsync(dbk.p, bk.data(), R * 8, cudaMemcpyHostToDevice, ctx->stream));
+        VX_CUDA(cudaStreamSynchronize(ctx->stream));               // bk is reused next iteration
+        unsigned blocks = (unsigned)((n + 127) / 128);
+        u64* z = dout.p + (size_t)k * n;
+        u64* pp = dout.p + (size_t)nch * n + (size_t)k * (chunks - 1) * n;
+        zpp_rows_kernel<<<blocks, 128, 0, ctx->stream>>>(dw.p, ds.p, n, d->degree_bits, R, d->max_degree, chunks,
+                                                         dbk.p, betas[k] % GL_P, gammas[k] % GL_P, tw, dq.p, drp.p);
+        zpp_scan_kernel<<<1, 1024, 0, ctx->stream>>>(drp.p, n, z);
+        zpp_fill_kernel<<<blocks, 128, 0, ctx->stream>>>(dq.p, z, n, chunks, pp);
+        VX_LAUNCH_COUNT(ctx, 3);
+    }
+    VX_CUDA(cudaGetLastError());
+    VX_CUDA(cudaMemcpyAsync(out, dout.p, (size_t)nch * chunks * n * 8, cudaMemcpyDefault, ctx->stream));
+    VX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ openings
+// One block per polynomial: thread t evaluates its contiguous run of coefficients by Horner, scales it by
+// point^(t*run) and the block sums the pieces.  out[col] = sum_m coeffs[col][m] * point^m  (extension value).
+__global__ void __launch_bounds__(256) eval_ext_kernel(const u64* __restrict__ coeffs, uint32_t log_n, gl2 point,
+                                                       u64* __restrict__ out) {
+    __shared__ u64 sa[256], sb[256];
+    const uint64_t n = 1ULL << log_n;
+    const u64* col = coeffs + ((uint64_t)blockIdx.x << log_n);
+    uint64_t per = (n + 255) / 256;
+    uint64_t lo = min(n, (uint64_t)threadIdx.x * per), hi = min(n, lo + per);
+    gl2 acc = gl2_make(0, 0);
+    for (uint64_t m = hi; m > lo; m--) acc = gl2_add_base(gl2_mul(acc, point), col[m - 1]);
+    acc = gl2_mul(acc, gl2_pow(point, lo));
+    sa[threadIdx.x] = gl_canon(acc.a); sb[threadIdx.x] = gl_canon(acc.b);
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) {
+            sa[threadIdx.x] = gl_canon(gl_add(sa[threadIdx.x], sa[threadIdx.x + s]));
+            sb[threadIdx.x] = gl_canon(gl_add(sb[threadIdx.x], sb[threadIdx.x + s]));
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { out[2 * blockIdx.x] = sa[0]; out[2 * blockIdx.x + 1] = sb[0]; }
+}
+
+extern "C" int32_t vx_batch_eval_ext(vx_batch* b, const uint64_t point[2], uint64_t* out) {
+    VX_REQUIRE(b && point && out, "vx_batch_eval_ext: NULL argument");
+    vx_ctx* ctx = b->ctx;
+    CtxGuard g(ctx);
+    DevBuf d;
+    VX_CHECK(d.alloc((size_t)b->c * 2 * 8, ctx->stream));
+    eval_ext_kernel<<<b->c, 256, 0, ctx->stream>>>(b->coeffs.p, b->log_n, gl2_make(point[0] % GL_P, point[1] % GL_P), d.p);
+    VX_LAUNCH_COUNT(ctx, 1);
+    VX_CUDA(cudaGetLastError());
+    VX_CUDA(cudaMemcpyAsync(out, d.p, d.bytes, cudaMemcpyDefault, ctx->stream));
+    VX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ field self-test surface
+__global__ void field_op_kernel(uint32_t op, const u64* __restrict__ a, const u64* __restrict__ b, const u64* __restrict__ c,
+                                uint64_t n, u64* __restrict__ out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    switch (op) {
+        case 0: out[i] = gl_canon(gl_mul_cc(a[i], b[i])); break;
+        case 1: out[i] = gl_canon(gl_mul(a[i], b[i])); break;
+        case 2: out[i] = gl_canon(gl_inv(a[i])); break;
+        case 3: out[i] = gl_canon(gl_mul_add_cc(a[i], b[i], c[i])); break;
+        case 4: out[i] = gl_canon(gl_add(a[i], b[i])); break;
+        case 5: out[i] = gl_canon(gl_sub(a[i], b[i])); break;
+        case 6: out[i] = gl_canon(gl_pow7_cc(a[i])); break;
+        case 7: { gl2 r = gl2_canon(gl2_mul(gl2_make(a[2 * i], a[2 * i + 1]), gl2_make(b[2 * i], b[2 * i + 1])));
+                  out[2 * i] = r.a; out[2 * i + 1] = r.b; break; }
+        case 8: { gl2 r = gl2_canon(gl2_inv(gl2_make(a[2 * i], a[2 * i + 1]))); out[2 * i] = r.a; out[2 * i + 1] = r.b; break; }
+        default: break;
+    }
+}
+
+extern "C" int32_t vx_field_op(vx_ctx* ctx, uint32_t op, const uint64_t* a, const uint64_t* b, const uint64_t* c, uint64_t n,
+                               uint64_t* out) {
+    VX_REQUIRE(ctx && a && out && op <= 8, "vx_field_op: bad argument");
+    if (n == 0) return VX_OK;
+    CtxGuard g(ctx);
+    const uint64_t words = (op >= 7) ? 2 * n : n;
+    DevBuf da, db, dc, dout;
+    VX_CHECK(da.alloc(words * 8, ctx->stream)); VX_CHECK(db.alloc(words * 8, ctx->stream));
+    VX_CHECK(dc.alloc(words * 8, ctx->stream)); VX_CHECK(dout.alloc(words * 8, ctx->stream));
+    VX_CUDA(cudaMemcpyAsync(da.p, a, words * 8, cudaMemcpyDefault, ctx->stream));
+    if (b) VX_CUDA(cudaMemcpyAsync(db.p, b, words * 8, cudaMemcpyDefault, ctx->stream));
+    if (c) VX_CUDA(cudaMemcpyAsync(dc.p, c, words * 8, cudaMemcpyDefault, ctx->stream));
+    field_op_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(op, da.p, db.p, dc.p, n, dout.p);
+    VX_LAUNCH_COUNT(ctx, 1);
+    VX_CUDA(cudaGetLastError());
+    VX_CUDA(cudaMemcpyAsync(out, dout.p, words * 8, cudaMemcpyDefault, ctx->stream));
+    VX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VX_OK;
+}

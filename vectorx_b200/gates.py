@@ -1,0 +1,386 @@
+"""Gate constraint programs for the device interpreter (host side of vx_quotient).
+
+What the Rust shim would obtain by tracing `Gate::eval_unfiltered_circuit` for every gate in
+`CommonCircuitData.gates` (registry: contracts/lib/succinctx/plonky2x/core/src/backend/circuit/
+serialization/gates.rs:85-107) is built here by tracing Python statements of the same formulas over
+symbolic values: arithmetic on `Sym` objects records SSA ops, which are register-allocated into the
+bytecode of include/vectorx_b200.h.
+
+Formulas: U32* gates follow the in-tree sources (frontend/uint/num/u32/gates/arithmetic_u32.rs:290-349,
+subtraction_u32.rs:235-271, range_check_u32.rs:93-115); the upstream plonky2 v0.2.0 gates follow
+SURVEY.md Appendix B.  PoseidonGate uses the fast partial-round tables exported by the library
+(vx_poseidon_fast_tables), like upstream's gate does.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from ._lib import check, load, ptr
+
+P = 0xFFFFFFFF00000001
+OP = dict(END=0, LOADW=1, LOADC=2, LOADPI=3, LOADK=4, ADD=5, SUB=6, MUL=7, ADDK=8, MULK=9, RSUBK=10, SUBK=11,
+          EMIT=12, BEGINGATE=13, ENDGATE=14)
+NUM_REGS = 64
+MDS_CIRC = [17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20]
+MDS_DIAG0 = 8
+
+
+class Trace:
+    """Records SSA operations; values are indices into self.ops."""
+
+    def __init__(self):
+        self.ops = []            # (opname, a, b, imm)  a/b are value ids or None
+        self.emits = []
+
+    def new(self, op, a=None, b=None, imm=None):
+        self.ops.append((op, a, b, imm))
+        return Sym(self, len(self.ops) - 1)
+
+    def wire(self, i):
+        return self.new("LOADW", imm=i)
+
+    def const_col(self, col):
+        return self.new("LOADC", imm=col)
+
+    def pi(self, i):
+        return self.new("LOADPI", imm=i)
+
+    def konst(self, k):
+        return self.new("LOADK", imm=k % P)
+
+    def emit(self, s):
+        s = _val(s)
+        s = s if isinstance(s, Sym) else self.konst(s)
+        self.ops.append(("EMIT", s.id, None, None))
+
+
+class Sym:
+    __slots__ = ("t", "id")
+
+    def __init__(self, t, i):
+        self.t, self.id = t, i
+
+    def _bin(self, o, op, opk, swap=False):
+        o = _val(o)
+        if isinstance(o, Sym):
+            return self.t.new(op, o.id, self.id) if swap else self.t.new(op, self.id, o.id)
+        return self.t.new(opk, self.id, None, int(o) % P)
+
+    def __add__(self, o):
+        o = _val(o)
+        if not isinstance(o, Sym) and int(o) % P == 0:
+            return self
+        return self._bin(o, "ADD", "ADDK")
+    __radd__ = __add__
+
+    def __sub__(self, o):
+        o = _val(o)
+        if not isinstance(o, Sym) and int(o) % P == 0:
+            return self
+        return self._bin(o, "SUB", "SUBK")
+
+    def __rsub__(self, o):
+        return self.t.new("RSUBK", self.id, None, int(o) % P)
+
+    def __mul__(self, o):
+        o = _val(o)
+        if not isinstance(o, Sym) and int(o) % P == 1:
+            return self
+        return self._bin(o, "MUL", "MULK")
+    __rmul__ = __mul__
+
+
+class Ref:
+    """A wire / constant / public-input reference that is (re)loaded at every use, so a formula that
+    mentions 60 wires does not keep 60 registers live."""
+    __slots__ = ("load",)
+
+    def __init__(self, load):
+        self.load = load
+
+    def __add__(self, o): return self.load() + _val(o)
+    def __radd__(self, o): return self.load() + _val(o)
+    def __sub__(self, o): return self.load() - _val(o)
+    def __rsub__(self, o): return _val(o) - self.load() if isinstance(_val(o), Sym) else (o - self.load())
+    def __mul__(self, o): return self.load() * _val(o)
+    def __rmul__(self, o): return self.load() * _val(o)
+
+
+def _val(o):
+    return o.load() if isinstance(o, Ref) else o
+
+
+# ------------------------------------------------------------------------------------------------ gate formulas
+def _horner(limbs, base):
+    acc = limbs[-1]
+    for l in reversed(limbs[:-1]):
+        acc = acc * base + l
+    return acc
+
+
+def _range4(x):
+    x = _val(x)
+    return x * (x - 1) * (x - 2) * (x - 3)
+
+
+def gate_noop(t, w, c, pi, params):
+    pass
+
+
+def gate_constant(t, w, c, pi, params):
+    for i in range(params["num_consts"]):
+        t.emit(c(i) - w(i))
+
+
+def gate_public_input(t, w, c, pi, params):
+    for i in range(4):
+        t.emit(w(i) - pi(i))
+
+
+def gate_arithmetic(t, w, c, pi, params):
+    c0, c1 = _val(c(0)), _val(c(1))
+    for i in range(params["num_ops"]):
+        m0, m1, addend, out = w(4 * i), w(4 * i + 1), w(4 * i + 2), w(4 * i + 3)
+        t.emit(out - (m0 * m1 * c0 + addend * c1))
+
+
+def gate_base_sum(t, w, c, pi, params):
+    limbs = [w(1 + i) for i in range(params["num_limbs"])]
+    t.emit(_horner(limbs, 2) - w(0))
+    for l in limbs:
+        l = _val(l)
+        t.emit(l * (l - 1))
+
+
+def gate_u32_arithmetic(t, w, c, pi, params):
+    n = params["num_ops"]
+    for i in range(n):
+        m0, m1, addend = w(6 * i), w(6 * i + 1), w(6 * i + 2)
+        lo, hi, inv = w(6 * i + 3), w(6 * i + 4), w(6 * i + 5)
+        computed = m0 * m1 + addend
+        hi_not_max = inv * (0xFFFFFFFF - hi) - 1
+        t.emit(hi_not_max * lo)
+        t.emit(hi * (1 << 32) + lo - computed)
+        low = high = None
+        for j in reversed(range(32)):
+            limb = w(6 * n + 32 * i + j)
+            t.emit(_range4(limb))
+            if j < 16:
+                low = limb if low is None else low * 4 + limb
+            else:
+                high = limb if high is None else high * 4 + limb
+        t.emit(low - lo)
+        t.emit(high - hi)
+
+
+def gate_u32_subtraction(t, w, c, pi, params):
+    n = params["num_ops"]
+    for i in range(n):
+        x, y, b_in, res, b_out = (w(5 * i + k) for k in range(5))
+        t.emit(res - (x - y - b_in + b_out * (1 << 32)))
+        comb = None
+        for j in reversed(range(16)):
+            limb = w(5 * n + 16 * i + j)
+            t.emit(_range4(limb))
+            comb = limb if comb is None else comb * 4 + limb
+        t.emit(comb - res)
+        b_out = _val(b_out)
+        t.emit(b_out * (1 - b_out))
+
+
+def gate_u32_range_check(t, w, c, pi, params):
+    k = params["num_input_limbs"]
+    for i in range(k):
+        aux = [w(k + 16 * i + j) for j in range(16)]
+        t.emit(_horner(aux, 4) - w(i))
+        for l in aux:
+            t.emit(_range4(l))
+
+
+_FAST = None
+
+
+def poseidon_fast_tables():
+    global _FAST
+    if _FAST is None:
+        d, e = np.zeros(144, dtype=np.uint64), np.zeros(12, dtype=np.uint64)
+        k, v, w = np.zeros(22, dtype=np.uint64), np.zeros(242, dtype=np.uint64), np.zeros(242, dtype=np.uint64)
+        check(load().vx_poseidon_fast_tables(ptr(d), ptr(e), ptr(k), ptr(v), ptr(w)), "vx_poseidon_fast_tables")
+        rc = np.zeros(360, dtype=np.uint64)
+        check(load().vx_poseidon_constants(ptr(rc)), "vx_poseidon_constants")
+        _FAST = dict(d=[int(x) for x in d], e=[int(x) for x in e], k=[int(x) for x in k], v=[int(x) for x in v],
+                     w=[int(x) for x in w], rc=[int(x) for x in rc])
+    return _FAST
+
+
+def gate_poseidon(t, w, c, pi, params):
+    T = poseidon_fast_tables()
+    rc = T["rc"]
+    swap = _val(w(24))
+    t.emit(swap * (swap - 1))
+    delta = [w(25 + i) for i in range(4)]
+    for i in range(4):
+        t.emit(swap * (w(i + 4) - w(i)) - delta[i])
+    st = [w(i) + delta[i] for i in range(4)] + [w(i + 4) - delta[i] for i in range(4)] + [w(i) for i in range(8, 12)]
+
+    def sbox(x):
+        x2 = x * x
+        x3 = x2 * x
+        x4 = x2 * x2
+        return x3 * x4
+
+    def mds(s):
+        out = []
+        for r in range(12):
+            acc = s[r] * (MDS_CIRC[0] + (MDS_DIAG0 if r == 0 else 0))
+            for i in range(1, 12):
+                acc = acc + s[(i + r) % 12] * MDS_CIRC[i]
+            out.append(acc)
+        return out
+
+    for r in range(4):                               # first full rounds
+        st = [st[i] + rc[12 * r + i] for i in range(12)]
+        if r != 0:
+            for i in range(12):
+                sin = w(29 + 12 * (r - 1) + i)
+                t.emit(st[i] - sin)
+                st[i] = sin
+        st = [sbox(x) for x in st]
+        if r < 3:
+            st = mds(st)
+        else:                                        # MDS layer merged with the partial rounds' initial matrix
+            new = []
+            for j in range(12):
+                acc = st[0] * T["d"][12 * j]
+                for i in range(1, 12):
+                    acc = acc + st[i] * T["d"][12 * j + i]
+                new.append(acc + T["e"][j])
+            st = new
+    for r in range(22):                              # partial rounds, sparse form
+        sin = w(65 + r)
+        t.emit(st[0] - sin)
+        x0 = sbox(sin) + T["k"][r]
+        d = x0 * 25
+        for i in range(1, 12):
+            d = d + st[i] * T["v"][11 * r + i - 1]
+        st = [d] + [st[i] + x0 * T["w"][11 * r + i - 1] for i in range(1, 12)]
+    for r in range(4):                               # second full rounds
+        st = [st[i] + rc[12 * (26 + r) + i] for i in range(12)]
+        for i in range(12):
+            sin = w(87 + 12 * r + i)
+            t.emit(st[i] - sin)
+            st[i] = sin
+        st = mds([sbox(x) for x in st])
+    for i in range(12):
+        t.emit(st[i] - w(12 + i))
+
+
+# id prefix -> (formula, parameter parser, degree, num_constants, num_constraints)
+def _p(name, key):
+    import re
+    m = re.search(key + r": (\d+)", name)
+    return int(m.group(1))
+
+
+GATES = {
+    "NoopGate": (gate_noop, lambda s: {}, lambda p: (0, 0, 0)),
+    "ConstantGate": (gate_constant, lambda s: {"num_consts": _p(s, "num_consts")}, lambda p: (1, p["num_consts"], p["num_consts"])),
+    "PublicInputGate": (gate_public_input, lambda s: {}, lambda p: (1, 0, 4)),
+    "ArithmeticGate": (gate_arithmetic, lambda s: {"num_ops": _p(s, "num_ops")}, lambda p: (3, 2, p["num_ops"])),
+    "BaseSumGate": (gate_base_sum, lambda s: {"num_limbs": _p(s, "num_limbs")}, lambda p: (2, 0, 1 + p["num_limbs"])),
+    "U32ArithmeticGate": (gate_u32_arithmetic, lambda s: {"num_ops": _p(s, "num_ops")}, lambda p: (4, 0, 36 * p["num_ops"])),
+    "U32SubtractionGate": (gate_u32_subtraction, lambda s: {"num_ops": _p(s, "num_ops")}, lambda p: (4, 0, 19 * p["num_ops"])),
+    "U32RangeCheckGate": (gate_u32_range_check, lambda s: {"num_input_limbs": _p(s, "num_input_limbs")},
+                          lambda p: (4, 0, 17 * p["num_input_limbs"])),
+    "PoseidonGate": (gate_poseidon, lambda s: {}, lambda p: (7, 0, 123)),
+}
+
+
+def lookup(gate_id: str):
+    for prefix, entry in GATES.items():
+        if gate_id.startswith(prefix):
+            fn, parse, meta = entry
+            params = parse(gate_id)
+            degree, num_constants, num_constraints = meta(params)
+            return fn, params, degree, num_constants, num_constraints
+    raise KeyError(f"gate {gate_id!r} has no constraint program (see DESIGN.md: gate coverage)")
+
+
+# ------------------------------------------------------------------------------------------------ assembler
+def assemble(trace: Trace, filter_id):
+    """Linear-scan register allocation of one gate's SSA trace -> (bytecode words, filter register)."""
+    ops = trace.ops
+    last = {}
+    for idx, (op, a, b, imm) in enumerate(ops):
+        for v in (a, b):
+            if v is not None:
+                last[v] = idx
+    if filter_id is not None:
+        last[filter_id] = len(ops)                 # stays live until ENDGATE
+    free = list(range(NUM_REGS - 1, -1, -1))
+    reg = {}
+    words = []
+
+    def enc(op, dst=0, a=0, b=0, imm=0):
+        return OP[op] | (dst << 8) | (a << 16) | (b << 24) | ((imm & 0xFFFFFFFF) << 32)
+
+    for idx, (op, a, b, imm) in enumerate(ops):
+        ra = reg[a] if a is not None else 0
+        rb = reg[b] if b is not None else 0
+        for v in {a, b}:                           # operands dying here free their register first:
+            if v is not None and last[v] == idx:   # the interpreter reads operands before it writes dst
+                free.append(reg[v])
+        if op == "EMIT":
+            words.append(enc("EMIT", 0, ra))
+            continue
+        if not free:
+            raise RuntimeError("gate program needs more than %d registers" % NUM_REGS)
+        rd = free.pop()
+        reg[idx] = rd
+        if op in ("LOADW", "LOADC", "LOADPI"):
+            words.append(enc(op, rd, 0, 0, imm))
+        elif op == "LOADK":
+            words += [enc(op, rd), imm]
+        elif op in ("ADD", "SUB", "MUL"):
+            words.append(enc(op, rd, ra, rb))
+        else:                                      # ADDK / MULK / RSUBK / SUBK: immediate in the next word
+            words += [enc(op, rd, ra), imm]
+        if idx not in last:                        # dead value
+            free.append(rd)
+    return words, (reg[filter_id] if filter_id is not None else 255)
+
+
+def build_program(gate_ids: list[str], selector_index: list[int], groups: list[tuple], num_selectors: int) -> np.ndarray:
+    """One program for all gates (already in plonky2's sorted order).  The gate-local constant i is column
+    num_selectors + i of the constants_sigmas batch; the filter follows compute_filter()."""
+    words = []
+    many = num_selectors > 1
+    for gi, gid in enumerate(gate_ids):
+        fn, params, degree, ncst, ncons = lookup(gid)
+        if ncons == 0:
+            continue
+        t = Trace()
+
+        def w(i, t=t):
+            return Ref(lambda: t.wire(i))
+
+        def c(i, t=t):
+            return Ref(lambda: t.const_col(num_selectors + i))
+
+        def pi(i, t=t):
+            return Ref(lambda: t.pi(i))
+        fn(t, w, c, pi, params)
+        # filter = prod_{j in group, j != gi} (j - s) [* (UNUSED - s)]
+        lo, hi = groups[selector_index[gi]]
+        s = t.const_col(selector_index[gi])
+        f = None
+        for j in range(lo, hi):
+            if j != gi:
+                term = j - s
+                f = term if f is None else f * term
+        if many:
+            term = 0xFFFFFFFF - s
+            f = term if f is None else f * term
+        body, freg = assemble(t, f.id if f is not None else None)
+        words += [OP["BEGINGATE"]] + body + [OP["ENDGATE"] | (freg << 16)]
+    return np.array(words, dtype=np.uint64)

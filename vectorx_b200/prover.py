@@ -1,0 +1,206 @@
+"""Host-side mirror of plonky2 v0.2.0 `prove_with_partition_witness` (plonk/prover.rs), the function the
+reference calls at contracts/lib/succinctx/plonky2x/core/src/backend/circuit/build.rs:69-75.
+
+Same phase order and transcript as upstream; every heavy phase is one C-ABI call:
+  wires commit            vx_commit_from_values          ("FFT + blinding", "build Merkle tree")
+  Z / partial products    vx_zs_partial_products
+  quotient                vx_quotient + vx_commit_from_coeffs  ("compute quotient polys")
+  openings                vx_batch_eval_ext
+  FRI                     vx_fri_begin / commit_layer / fold / final_poly / pow_grind / query
+The challenger and the proof assembly stay on the host.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import gates as gate_lib
+from ._lib import Context, check, default_context, load, ptr, vp
+from .challenger import Challenger, hash_no_pad_host
+from .plonky2 import PolynomialBatch
+
+P = 0xFFFFFFFF00000001
+GENERATOR = 14293326489335486720
+
+
+class VxCircuitDesc(ctypes.Structure):
+    _fields_ = [("degree_bits", ctypes.c_uint32), ("rate_bits", ctypes.c_uint32), ("num_wires", ctypes.c_uint32),
+                ("num_routed_wires", ctypes.c_uint32), ("num_constants", ctypes.c_uint32),
+                ("num_selectors", ctypes.c_uint32), ("num_challenges", ctypes.c_uint32),
+                ("num_partial_products", ctypes.c_uint32), ("max_degree", ctypes.c_uint32),
+                ("num_gate_constraints", ctypes.c_uint32), ("k_is", ctypes.c_void_p), ("program", ctypes.c_void_p),
+                ("program_len", ctypes.c_uint64)]
+
+
+class FriRange(ctypes.Structure):
+    _fields_ = [("oracle", ctypes.c_uint32), ("first", ctypes.c_uint32), ("count", ctypes.c_uint32)]
+
+
+class FriBatch(ctypes.Structure):
+    _fields_ = [("point", ctypes.c_uint64 * 2), ("ranges", ctypes.POINTER(FriRange)), ("num_ranges", ctypes.c_uint32)]
+
+
+class CircuitData:
+    """CommonCircuitData + the prover-only parts this path needs (plain data, as the Rust shim would pass it)."""
+
+    def __init__(self, degree_bits, gate_ids, selector_index, groups, constants, sigmas, *, num_wires=135,
+                 num_routed_wires=80, rate_bits=3, cap_height=4, num_challenges=2, max_degree=8,
+                 quotient_degree_factor=8, num_query_rounds=28, proof_of_work_bits=16, arity_bits=4,
+                 final_poly_bits=5, ctx: Context | None = None):
+        self.ctx = ctx or default_context()
+        self.degree_bits, self.n = degree_bits, 1 << degree_bits
+        self.gate_ids, self.selector_index, self.groups = list(gate_ids), list(selector_index), [tuple(g) for g in groups]
+        self.num_selectors = len(self.groups)
+        self.num_wires, self.num_routed_wires = num_wires, num_routed_wires
+        self.rate_bits, self.cap_height, self.num_challenges = rate_bits, cap_height, num_challenges
+        self.max_degree, self.quotient_degree_factor = max_degree, quotient_degree_factor
+        self.num_query_rounds, self.proof_of_work_bits = num_query_rounds, proof_of_work_bits
+        self.arity_bits, self.final_poly_bits = arity_bits, final_poly_bits
+        self.constants = np.ascontiguousarray(constants, dtype=np.uint64)
+        self.sigmas = np.ascontiguousarray(sigmas, dtype=np.uint64)
+        self.num_constants = self.constants.shape[0]
+        self.num_partial_products = (num_routed_wires + max_degree - 1) // max_degree - 1
+        self.k_is = np.array([pow(GENERATOR, j, P) for j in range(num_routed_wires)], dtype=np.uint64)
+        meta = [gate_lib.lookup(g) for g in self.gate_ids]
+        self.num_gate_constraints = max(m[4] for m in meta)
+        self.program = gate_lib.build_program(self.gate_ids, self.selector_index, self.groups, self.num_selectors)
+        # CircuitBuilder::build: constants_sigmas commitment and the circuit digest
+        cs = np.concatenate([self.constants, self.sigmas])
+        self.constants_sigmas_commitment = PolynomialBatch.from_values(cs, rate_bits, False, cap_height, ctx=self.ctx)
+        cap = self.constants_sigmas_commitment.cap.hashes
+        self.circuit_digest = hash_no_pad_host([int(x) for x in cap.reshape(-1)] + [0, 0, 0, 0] + [degree_bits])
+        self.desc = VxCircuitDesc(degree_bits, rate_bits, num_wires, num_routed_wires, self.num_constants,
+                                  self.num_selectors, num_challenges, self.num_partial_products, max_degree,
+                                  self.num_gate_constraints, self.k_is.ctypes.data, self.program.ctypes.data,
+                                  len(self.program))
+
+    def fri_reduction_arity_bits(self):
+        out, d = [], self.degree_bits
+        while d > self.final_poly_bits and d + self.rate_bits - self.arity_bits >= self.cap_height:
+            out.append(self.arity_bits)
+            d -= self.arity_bits
+        return out
+
+
+def _u64(xs):
+    return np.ascontiguousarray(np.array([int(x) % P for x in xs], dtype=np.uint64))
+
+
+def prove(circ: CircuitData, wires: np.ndarray, public_inputs, trace: dict | None = None) -> dict:
+    """prove_with_partition_witness: wires is the (num_wires, n) witness matrix. Returns the proof as a dict."""
+    lib, ctx = load(), circ.ctx
+    T = trace if trace is not None else {}
+    n, d, rate, cap_h = circ.n, circ.degree_bits, circ.rate_bits, circ.cap_height
+    N, bits, nch = n << rate, d + rate, circ.num_challenges
+    wires = np.ascontiguousarray(wires, dtype=np.uint64)
+    pi_hash = hash_no_pad_host(list(public_inputs))
+    ch = Challenger()
+    ch.observe_hash(circ.circuit_digest)
+    ch.observe_hash(pi_hash)
+    wires_c = PolynomialBatch.from_values(wires, rate, False, cap_h, ctx=ctx)
+    ch.observe_cap(wires_c.cap.hashes.tolist())
+    betas = ch.get_n_challenges(nch)
+    gammas = ch.get_n_challenges(nch)
+    zpp = np.zeros((nch * (1 + circ.num_partial_products), n), dtype=np.uint64)
+    a_betas, a_gammas = _u64(betas), _u64(gammas)        # keep the arrays alive across the FFI calls
+    check(lib.vx_zs_partial_products(ctx.handle, ctypes.byref(circ.desc), ptr(wires), ptr(circ.sigmas),
+                                     ptr(a_betas), ptr(a_gammas), ptr(zpp)), "vx_zs_partial_products")
+    zpp_c = PolynomialBatch.from_values(zpp, rate, False, cap_h, ctx=ctx)
+    ch.observe_cap(zpp_c.cap.hashes.tolist())
+    alphas = ch.get_n_challenges(nch)
+    qcoeffs = np.zeros((nch, N), dtype=np.uint64)
+    cs_c = circ.constants_sigmas_commitment
+    a_pi, a_alphas = _u64(pi_hash), _u64(alphas)
+    check(lib.vx_quotient(ctx.handle, ctypes.byref(circ.desc), cs_c.handle, wires_c.handle, zpp_c.handle,
+                          ptr(a_pi), ptr(a_betas), ptr(a_gammas), ptr(a_alphas), ptr(qcoeffs)), "vx_quotient")
+    qchunks = qcoeffs.reshape(nch * circ.quotient_degree_factor, n)
+    q_c = PolynomialBatch.from_coeffs(qchunks, rate, False, cap_h, ctx=ctx)
+    ch.observe_cap(q_c.cap.hashes.tolist())
+    zeta = ch.get_extension_challenge()
+    g_n = pow(7277203076849721926, 1 << (32 - d), P)
+    zeta_next = [zeta[0] * g_n % P, zeta[1] * g_n % P]
+    T.update(betas=betas, gammas=gammas, alphas=alphas, zpp=zpp, quotient_coeffs=qchunks, zeta=zeta, pi_hash=pi_hash)
+
+    def ev(batch, point):
+        out = np.zeros((batch.num_polys, 2), dtype=np.uint64)
+        a_point = _u64(point)
+        check(lib.vx_batch_eval_ext(batch.handle, ptr(a_point), ptr(out)), "vx_batch_eval_ext")
+        return [[int(a), int(b)] for a, b in out]
+    cs_open, z_open = ev(cs_c, zeta), ev(zpp_c, zeta)
+    openings = {
+        "constants": cs_open[:circ.num_constants], "plonk_sigmas": cs_open[circ.num_constants:],
+        "wires": ev(wires_c, zeta), "plonk_zs": z_open[:nch], "partial_products": z_open[nch:],
+        "quotient_polys": ev(q_c, zeta), "plonk_zs_next": ev(zpp_c, zeta_next)[:nch],
+    }
+    for key in ("constants", "plonk_sigmas", "wires", "plonk_zs", "partial_products", "quotient_polys", "plonk_zs_next"):
+        for e in openings[key]:
+            ch.observe_extension_element(e)
+
+    # ---- FRI
+    alpha = ch.get_extension_challenge()
+    oracles = [cs_c, wires_c, zpp_c, q_c]
+    handles = (ctypes.c_void_p * 4)(*[o.handle.value for o in oracles])
+    r0 = (FriRange * 4)(*[FriRange(i, 0, o.num_polys) for i, o in enumerate(oracles)])
+    r1 = (FriRange * 1)(FriRange(2, 0, nch))
+    batches = (FriBatch * 2)()
+    batches[0].point[0], batches[0].point[1] = zeta
+    batches[0].ranges, batches[0].num_ranges = r0, 4
+    batches[1].point[0], batches[1].point[1] = zeta_next
+    batches[1].ranges, batches[1].num_ranges = r1, 1
+    fri = vp()
+    a_alpha = _u64(alpha)
+    check(lib.vx_fri_begin(ctx.handle, handles, 4, batches, 2, ptr(a_alpha), ctypes.byref(fri)), "vx_fri_begin")
+    try:
+        arities = circ.fri_reduction_arity_bits()
+        fri_caps = []
+        for ab in arities:
+            cap = np.zeros((1 << cap_h, 4), dtype=np.uint64)
+            check(lib.vx_fri_commit_layer(fri, ab, cap_h, ptr(cap)), "vx_fri_commit_layer")
+            fri_caps.append(cap)
+            ch.observe_cap(cap.tolist())
+            a_beta = _u64(ch.get_extension_challenge())
+            check(lib.vx_fri_fold(fri, ptr(a_beta)), "vx_fri_fold")
+        flen = ctypes.c_uint32(0)
+        fbuf = np.zeros((n, 2), dtype=np.uint64)
+        check(lib.vx_fri_final_poly(fri, ptr(fbuf), ctypes.byref(flen)), "vx_fri_final_poly")
+        final_poly = [[int(a), int(b)] for a, b in fbuf[:flen.value]]
+        for c in final_poly:
+            ch.observe_extension_element(c)
+        st, pos = ch.pow_state()
+        wit = ctypes.c_uint64(0)
+        a_st = _u64(st)
+        check(lib.vx_pow_grind(ctx.handle, ptr(a_st), pos, circ.proof_of_work_bits, ctypes.byref(wit)), "vx_pow_grind")
+        pow_witness = int(wit.value)
+        ch.observe_element(pow_witness)
+        ch.get_challenge()
+        x_indices = [ch.get_challenge() % N for _ in range(circ.num_query_rounds)]
+        k = len(x_indices)
+        init_rows = [o.leaves(x_indices) for o in oracles]
+        init_paths = [o.prove(x_indices) for o in oracles]
+        layer_rows, layer_paths = [], []
+        idx = list(x_indices)
+        size = N
+        for li, ab in enumerate(arities):
+            idx = [x >> ab for x in idx]
+            size >>= ab
+            depth = max((size.bit_length() - 1) - cap_h, 0)
+            rows = np.zeros((k, 2 << ab), dtype=np.uint64)
+            paths = np.zeros((k, max(depth, 1), 4), dtype=np.uint64)
+            a_idx = _u64(idx)
+            check(lib.vx_fri_query(fri, li, ptr(a_idx), k, ptr(rows), ptr(paths)), "vx_fri_query")
+            layer_rows.append(rows)
+            layer_paths.append(paths[:, :depth])
+    finally:
+        lib.vx_fri_free(fri)
+    queries = []
+    for qi, x in enumerate(x_indices):
+        queries.append({"x_index": x,
+                        "initial": [(init_rows[o][qi], init_paths[o][qi]) for o in range(4)],
+                        "steps": [(layer_rows[li][qi], layer_paths[li][qi]) for li in range(len(arities))]})
+    proof = {"wires_cap": wires_c.cap.hashes, "zs_pp_cap": zpp_c.cap.hashes, "quotient_cap": q_c.cap.hashes,
+             "openings": openings, "fri_caps": fri_caps, "final_poly": final_poly, "pow_witness": pow_witness,
+             "queries": queries, "public_inputs": list(public_inputs)}
+    for b in (wires_c, zpp_c, q_c):
+        b.close()
+    return proof
