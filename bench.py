@@ -324,8 +324,10 @@ def main():
         ntt_ms = phases.get("intt", 0.0) + phases.get("lde", 0.0)
         ntt_bytes = (8 * n * c * 2 if G == 1 else 0) + 8 * n * c + 8 * rows_loc * c   # values->coeffs, coeffs->LDE
         traffic = None
-        try:
-            with open(os.path.join(ROOT, "profiles", "leaf_hash_traffic_r01.json")) as f:
+        try:                                # dram read+write bytes of this kernel from the newest committed ncu --set full digest
+            import glob
+            cand = sorted(glob.glob(os.path.join(ROOT, "profiles", "*leaf_hash_ncu_traffic.json")))
+            with open(cand[-1]) as f:
                 traffic = json.load(f).get("dram_bytes_per_launch")
         except Exception:
             pass
