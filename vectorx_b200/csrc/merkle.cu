@@ -86,7 +86,8 @@ GL_D void store_digest(u64* dst, const u64 s[12]) {
 }
 
 // one thread per leaf: hash_or_noop(leaf) -> interleaved slot (or cap when the subtree is 1 leaf)
-// V = 0: state in registers, unrolled rounds.  V = 1: state in shared memory, rolled lane loops.
+// V = 0: state in registers, frequency-domain MDS.  V = 1: state in shared memory, rolled lane loops.
+// V = 2: state in registers, IMAD.WIDE MDS (the round-1a kernel, kept for A/B runs).
 template <bool COL_MAJOR, int V, int MINB>
 __global__ void __launch_bounds__(POSEIDON_BLOCK, MINB) leaf_hash_kernel(const u64* __restrict__ leaves, uint64_t stride,
                                                         uint64_t N, uint32_t c, uint32_t sub_bits,
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(POSEIDON_BLOCK, MINB) leaf_hash_kernel(const u
     const uint64_t step = COL_MAJOR ? stride : 1;
     u64* st = scratch + threadIdx.x;
     u64 s[12];
-    if (V == 0) {
+    if (V != 1) {
 #pragma unroll
         for (int i = 0; i < 12; i++) s[i] = 0;
     } else {
@@ -110,11 +111,11 @@ __global__ void __launch_bounds__(POSEIDON_BLOCK, MINB) leaf_hash_kernel(const u
         for (int i = 0; i < 4; i++) s[i] = ((uint32_t)i < c) ? src[i * step] : 0;
     } else {
         for (uint32_t off = 0; off < c; off += POSEIDON_RATE) {
-            if (V == 0) {
+            if (V != 1) {
 #pragma unroll
                 for (int i = 0; i < POSEIDON_RATE; i++)
                     if (off + i < c) s[i] = src[(uint64_t)(off + i) * step];   // overwrite-mode absorb
-                poseidon_permute(s, st);
+                poseidon_permute<V == 2 ? 1 : 0>(s, st);
             } else {
 #pragma unroll
                 for (int i = 0; i < POSEIDON_RATE; i++)
@@ -122,7 +123,7 @@ __global__ void __launch_bounds__(POSEIDON_BLOCK, MINB) leaf_hash_kernel(const u
                 poseidon_s_permute(st);
             }
         }
-        if (V != 0) {
+        if (V == 1) {
 #pragma unroll
             for (int i = 0; i < 4; i++) s[i] = PS(i);
         }
@@ -172,8 +173,10 @@ int32_t merkle_build_device(vx_ctx* ctx, const u64* leaves, bool col_major, uint
     if (col_major) {
         switch (pv) {
             case 1: LEAF(true, 1, 4); break;      // state in shared memory, rolled lane loops
-            case 2: LEAF(true, 0, 4); break;      // state in registers, up to 128 registers
-            default: LEAF(true, 0, 8); break;     // state in registers, 64 registers / 8 blocks per SM (fastest measured)
+            case 2: LEAF(true, 2, 8); break;      // round-1a kernel: IMAD.WIDE MDS layer
+            case 3: LEAF(true, 0, 4); break;      // up to 128 registers
+            case 4: LEAF(true, 0, 6); break;      // up to 80 registers
+            default: LEAF(true, 0, 8); break;     // state in registers, 64 registers / 8 blocks per SM
         }
     } else {
         if (pv % 10 == 1) LEAF(false, 1, 4); else LEAF(false, 0, 4);

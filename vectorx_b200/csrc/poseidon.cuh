@@ -62,6 +62,65 @@ GL_D void poseidon_mds_add(u64 s[12], const u64* __restrict__ add) {
     }
 }
 
+// ---- frequency-domain MDS layer --------------------------------------------------------------------------------
+// The circulant part y[r] = sum_i CIRC[i] x[(r+i) % 12] is a cyclic correlation over Z/12 = Z/4 x Z/3
+// (index j = 3a + 4b).  A 4-point DFT along `a` (roots +-1, +-i: additions only) turns it into three 3-point
+// correlations whose constants are DFT(CIRC)/4 = {16,16,32}, {2+i, -16+i, -1+4i} (doubled, conjugate pair folded)
+// and {-1,2,8}: every product is a shift.  plonky2 ships the same idea as `mds_multiply_freq` for its CPU code; the
+// constants here are re-derived (tools/mds_freq_derive.py).  One call works on one 32-bit "plane" of 22-bit limbs
+// with wrap-around arithmetic: intermediates may overflow 32 bits, the final value (< 2^22 * 272 + 2^22) cannot.
+// k (warp-uniform) holds the constants to add, stride 3 (limb planes interleaved).
+GL_D void poseidon_mds_plane(const u32 x[12], u32 y[12], const u32* __restrict__ k) {
+    constexpr int G[3][4] = {{0, 3, 6, 9}, {4, 7, 10, 1}, {8, 11, 2, 5}};
+    u32 X0[3], X2[3], r[3], s[3];
+#pragma unroll
+    for (int b = 0; b < 3; b++) {
+        u32 x0 = x[G[b][0]], x1 = x[G[b][1]], x2 = x[G[b][2]], x3 = x[G[b][3]];
+        u32 p = x0 + x2, q = x1 + x3;
+        r[b] = x0 - x2;
+        s[b] = x1 - x3;
+        X0[b] = p + q;
+        X2[b] = p - q;
+    }
+    u32 T = X0[0] + X0[1] + X0[2];
+#pragma unroll
+    for (int b = 0; b < 3; b++) {
+        const int b1 = (b + 1) % 3, b2 = (b + 2) % 3;
+        u32 Y0 = (T + X0[b2]) << 4;
+        u32 Y2 = (X2[b1] << 1) + (X2[b2] << 3) - X2[b];
+        u32 Y1r = (r[b] << 1) - (r[b1] << 4) - r[b2] - s[b] - s[b1] - (s[b2] << 2);
+        u32 Y1i = (s[b] << 1) - (s[b1] << 4) - s[b2] + r[b] + r[b1] + (r[b2] << 2);
+        u32 P = Y0 + Y2, Q = Y0 - Y2;
+        y[G[b][0]] = P + Y1r + k[3 * G[b][0]];
+        y[G[b][2]] = P - Y1r + k[3 * G[b][2]];
+        y[G[b][1]] = Q + Y1i + k[3 * G[b][1]];
+        y[G[b][3]] = Q - Y1i + k[3 * G[b][3]];
+    }
+    y[0] += x[0] << 3;          // DIAG[0] = 8
+}
+
+// out = MDS * s + add, add given as 22/22/20-bit limbs (kl: 12 x 3 u32, warp-uniform pointer into constant memory)
+GL_D void poseidon_mds_add_freq(u64 s[12], const u32* __restrict__ kl) {
+    u32 l0[12], l1[12], l2[12], y0[12], y1[12], y2[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        u32 lo = lo32(s[i]), hi = hi32(s[i]);
+        l0[i] = lo & 0x3fffffu;
+        l1[i] = __funnelshift_r(lo, hi, 22) & 0x3fffffu;
+        l2[i] = hi >> 12;
+    }
+    poseidon_mds_plane(l0, y0, kl);
+    poseidon_mds_plane(l1, y1, kl + 1);
+    poseidon_mds_plane(l2, y2, kl + 2);
+#pragma unroll
+    for (int r = 0; r < 12; r++) {
+        // value = y0 + y1 2^22 + y2 2^44 (< 2^76)
+        u64 t = mad_wide(y1[r], 1u << 22, (u64)y0[r]);
+        u64 u = mad_wide(y2[r], 1u << 12, (u64)hi32(t));
+        s[r] = gl_reduce96(pack64(lo32(t), lo32(u)), hi32(u));
+    }
+}
+
 // s <- D * s + e with D a dense matrix of full-width constants (the MDS layer of full round 3 merged
 // with the partial rounds' initial matrix).  Rows are produced in a rolled loop (small code) and
 // staged through this thread's shared-memory column: scratch[j * POSEIDON_BLOCK].
@@ -99,19 +158,22 @@ GL_D void poseidon_partial_rounds(u64 s[12]) {
 }
 
 // scratch: this thread's column of a POSEIDON_BLOCK-wide shared array of 12 rows
+// MV = 0: frequency-domain MDS layer (shifts/adds on 22-bit limb planes); MV = 1: IMAD.WIDE MDS on 32-bit halves (A/B)
+template <int MV = 0>
 GL_D void poseidon_permute(u64 s[12], u64* __restrict__ scratch) {
     const u64* rc = c_pos.rc;
 #pragma unroll
     for (int i = 0; i < 12; i++) s[i] = gl_add_canon(s[i], rc[i]);
 #pragma unroll 1
     for (int half = 0; half < 2; half++) {
-        const u64* next = rc + (half ? 27 * 12 : 12);       // constants of the round after each full round
+        const int first = half ? 27 : 1;                    // constants of the round after each full round
 #pragma unroll 1
         for (int r = 0; r < 4; r++) {
 #pragma unroll
             for (int i = 0; i < 12; i++) s[i] = gl_pow7_cc(s[i]);
             if (half == 0 && r == 3) poseidon_dense_layer(s, scratch);
-            else poseidon_mds_add(s, next + 12 * r);
+            else if (MV == 0) poseidon_mds_add_freq(s, c_pos.rc22 + 36 * (first + r));
+            else poseidon_mds_add(s, rc + 12 * (first + r));
         }
         if (half == 0) {
             poseidon_partial_rounds(s);
