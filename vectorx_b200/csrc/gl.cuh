@@ -77,66 +77,56 @@ GL_D u64 gl_reduce96(u64 lo, u32 hi) {
     return r;
 }
 
-// ---- carry-flag versions (PTX add.cc / subc chains): the conditional +-eps fix-ups come straight
-// from the carry flag instead of 64-bit compares + selects, which halves the ALU-pipe work.
-// x = x3*2^96 + x2*2^64 + x1*2^32 + x0  ->  some u64 representative of x mod p
+// ---- carry-flag versions (PTX mad.cc / add.cc chains).  ptxas fuses each mad.lo.cc + madc.hi.cc pair into one
+// IMAD.WIDE.U32 with a carry-out predicate, and the fix-ups come straight from the carry flag.
+//
+// eps as an opaque run-time constant: with the literal 0xffffffff ptxas splits x*eps + t into IMAD.HI (4 issue cycles on
+// the FMA-heavy pipe) + IMAD.IADD; from a constant-bank operand it stays ONE IMAD.WIDE.U32 with carry-out.
+static __constant__ u32 c_gl_eps = 0xFFFFFFFFu;
+
+// x = x3*2^96 + x2*2^64 + x1*2^32 + x0  ->  some u64 representative of x mod p.
+//   t = x2*eps + (x1:x0)  (carry C),  t -= x3  (borrow B);  x = t + (C - B)*2^64 = t + (C - B)*eps  (mod p)
+// and t + (C - B)*eps always lands in [0, 2^64).  1 IMAD.WIDE + 9 ALU instructions.
 GL_D u64 gl_reduce128_cc(u32 x0, u32 x1, u32 x2, u32 x3) {
     u32 r0, r1;
     asm("{\n\t"
-        ".reg .u32 t0, t1, m, c;\n\t"
-        "sub.cc.u32 t0, %2, %5;\n\t"              // t = (x1:x0) - x3
-        "subc.cc.u32 t1, %3, 0;\n\t"
-        "subc.u32 m, 0, 0;\n\t"                   // m = borrow ? 0xffffffff : 0   (== eps when set)
-        "sub.cc.u32 t0, t0, m;\n\t"               // borrow: t -= eps  (i.e. += p mod 2^64)
-        "subc.u32 t1, t1, 0;\n\t"
-        "mad.lo.cc.u32 t0, %4, 0xffffffff, t0;\n\t"   // t += x2 * eps
-        "madc.hi.cc.u32 t1, %4, 0xffffffff, t1;\n\t"
-        "addc.u32 c, 0, 0;\n\t"                   // c = carry (0/1)
-        "mad.lo.cc.u32 %0, c, 0xffffffff, t0;\n\t"    // carry: += eps (cannot carry again)
-        "addc.u32 %1, t1, 0;\n\t"
+        ".reg .u32 t0, t1, w2, s;\n\t"
+        "mad.lo.cc.u32 t0, %4, %6, %2;\n\t"
+        "madc.hi.cc.u32 t1, %4, %6, %3;\n\t"
+        "addc.u32 w2, 0, 0;\n\t"
+        "sub.cc.u32 t0, t0, %5;\n\t"
+        "subc.cc.u32 t1, t1, 0;\n\t"
+        "subc.u32 w2, w2, 0;\n\t"                 // w2 = C - B in {-1, 0, 1}
+        "shr.s32 s, w2, 31;\n\t"
+        "sub.cc.u32 %0, t0, w2;\n\t"              // t += w2*eps = (w2 << 32) - sext(w2)
+        "subc.u32 t1, t1, s;\n\t"
+        "add.u32 %1, t1, w2;\n\t"
         "}"
         : "=r"(r0), "=r"(r1)
-        : "r"(x0), "r"(x1), "r"(x2), "r"(x3));
+        : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(c_gl_eps));
     return pack64(r0, r1);
 }
 
-// a * b + c (all u64, any representatives) reduced: one 128-bit product, the addend folded into the
-// carry chain, one reduction.  (2^64-1)^2 + 2^64-1 < 2^128, so no overflow.
-GL_D u64 gl_mul_add_cc(u64 a, u64 b, u64 c) {
-    u32 a0 = lo32(a), a1 = hi32(a), b0 = lo32(b), b1 = hi32(b), c0 = lo32(c), c1 = hi32(c);
-    u32 r0, r1, r2, r3;
-    asm("{\n\t"
-        "mad.lo.cc.u32 %0, %4, %6, %8;\n\t"       // (r1:r0) = a0*b0 + c0   [+ carry into r1]
-        "madc.hi.cc.u32 %1, %4, %6, %9;\n\t"      //          + c1 << 32
-        "addc.u32 %2, 0, 0;\n\t"
-        "mad.lo.cc.u32 %1, %4, %7, %1;\n\t"       // += a0*b1 << 32
-        "madc.hi.cc.u32 %2, %4, %7, %2;\n\t"
-        "addc.u32 %3, 0, 0;\n\t"
-        "mad.lo.cc.u32 %1, %5, %6, %1;\n\t"       // += a1*b0 << 32
-        "madc.hi.cc.u32 %2, %5, %6, %2;\n\t"
-        "addc.u32 %3, %3, 0;\n\t"
-        "mad.lo.cc.u32 %2, %5, %7, %2;\n\t"       // += a1*b1 << 64
-        "madc.hi.u32 %3, %5, %7, %3;\n\t"
-        "}"
-        : "=&r"(r0), "=&r"(r1), "=&r"(r2), "=&r"(r3)
-        : "r"(a0), "r"(a1), "r"(b0), "r"(b1), "r"(c0), "r"(c1));
-    return gl_reduce128_cc(r0, r1, r2, r3);
-}
-
+// 64 x 64 -> 128: four IMAD.WIDE (one carrying out) and one three-word carry chain
 GL_D void gl_mul128_cc(u64 a, u64 b, u32& r0, u32& r1, u32& r2, u32& r3) {
     u32 a0 = lo32(a), a1 = hi32(a), b0 = lo32(b), b1 = hi32(b);
     asm("{\n\t"
-        "mul.lo.u32 %0, %4, %6;\n\t"
-        "mul.hi.u32 %1, %4, %6;\n\t"
-        "mad.lo.cc.u32 %1, %4, %7, %1;\n\t"
-        "madc.hi.u32 %2, %4, %7, 0;\n\t"
-        "mad.lo.cc.u32 %1, %5, %6, %1;\n\t"
-        "madc.hi.cc.u32 %2, %5, %6, %2;\n\t"
-        "addc.u32 %3, 0, 0;\n\t"
-        "mad.lo.cc.u32 %2, %5, %7, %2;\n\t"
-        "madc.hi.u32 %3, %5, %7, %3;\n\t"
+        ".reg .u64 p0, p1, p3;\n\t"
+        ".reg .u32 h0, l1, h1, m0, m1, m2, l3, h3;\n\t"
+        "mul.wide.u32 p0, %4, %6;\n\t"
+        "mul.wide.u32 p1, %4, %7;\n\t"
+        "mul.wide.u32 p3, %5, %7;\n\t"
+        "mov.b64 {%0, h0}, p0;\n\t"
+        "mov.b64 {l1, h1}, p1;\n\t"
+        "mov.b64 {l3, h3}, p3;\n\t"
+        "mad.lo.cc.u32 m0, %5, %6, l1;\n\t"       // (m2:m1:m0) = a1*b0 + a0*b1
+        "madc.hi.cc.u32 m1, %5, %6, h1;\n\t"
+        "addc.u32 m2, 0, 0;\n\t"
+        "add.cc.u32 %1, h0, m0;\n\t"
+        "addc.cc.u32 %2, l3, m1;\n\t"
+        "addc.u32 %3, h3, m2;\n\t"
         "}"
-        : "=&r"(r0), "=&r"(r1), "=&r"(r2), "=&r"(r3)
+        : "=r"(r0), "=&r"(r1), "=&r"(r2), "=&r"(r3)
         : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
 }
 
@@ -146,25 +136,48 @@ GL_D u64 gl_mul_cc(u64 a, u64 b) {
     return gl_reduce128_cc(r0, r1, r2, r3);
 }
 
+// a * b + c (all u64, any representatives) reduced.  The addend rides in the accumulators of the two IMAD.WIDE
+// whose products leave room for a 32-bit addend: (2^32-1)^2 + 2^32-1 < 2^64.
+GL_D u64 gl_mul_add_cc(u64 a, u64 b, u64 c) {
+    u32 a0 = lo32(a), a1 = hi32(a), b0 = lo32(b), b1 = hi32(b);
+    u64 p0 = mad_wide(a0, b0, (u64)lo32(c));
+    u64 p1 = mad_wide(a0, b1, (u64)hi32(c));
+    u64 p3 = mul_wide(a1, b1);
+    u32 r1, r2, r3;
+    asm("{\n\t"
+        ".reg .u32 m0, m1, m2;\n\t"
+        "mad.lo.cc.u32 m0, %3, %4, %5;\n\t"
+        "madc.hi.cc.u32 m1, %3, %4, %6;\n\t"
+        "addc.u32 m2, 0, 0;\n\t"
+        "add.cc.u32 %0, %7, m0;\n\t"
+        "addc.cc.u32 %1, %8, m1;\n\t"
+        "addc.u32 %2, %9, m2;\n\t"
+        "}"
+        : "=&r"(r1), "=&r"(r2), "=&r"(r3)
+        : "r"(a1), "r"(b0), "r"(lo32(p1)), "r"(hi32(p1)), "r"(hi32(p0)), "r"(lo32(p3)), "r"(hi32(p3)));
+    return gl_reduce128_cc(lo32(p0), r1, r2, r3);
+}
+
 GL_D u64 gl_sqr_cc(u64 a) {
     u32 a0 = lo32(a), a1 = hi32(a);
     u32 r0, r1, r2, r3;
     asm("{\n\t"
-        ".reg .u32 m0, m1, m2;\n\t"
-        "mul.lo.u32 m0, %4, %5;\n\t"              // cross = a0*a1
-        "mul.hi.u32 m1, %4, %5;\n\t"
-        "add.cc.u32 m0, m0, m0;\n\t"              // 2*cross as (m2:m1:m0)
-        "addc.cc.u32 m1, m1, m1;\n\t"
+        ".reg .u64 p0, p1, p3;\n\t"
+        ".reg .u32 h0, l1, h1, m0, m1, m2, l3, h3;\n\t"
+        "mul.wide.u32 p0, %4, %4;\n\t"
+        "mul.wide.u32 p1, %4, %5;\n\t"
+        "mul.wide.u32 p3, %5, %5;\n\t"
+        "mov.b64 {%0, h0}, p0;\n\t"
+        "mov.b64 {l1, h1}, p1;\n\t"
+        "mov.b64 {l3, h3}, p3;\n\t"
+        "add.cc.u32 m0, l1, l1;\n\t"              // (m2:m1:m0) = 2 * a0*a1
+        "addc.cc.u32 m1, h1, h1;\n\t"
         "addc.u32 m2, 0, 0;\n\t"
-        "mul.lo.u32 %0, %4, %4;\n\t"              // a0^2
-        "mul.hi.u32 %1, %4, %4;\n\t"
-        "mul.lo.u32 %2, %5, %5;\n\t"              // a1^2
-        "mul.hi.u32 %3, %5, %5;\n\t"
-        "add.cc.u32 %1, %1, m0;\n\t"
-        "addc.cc.u32 %2, %2, m1;\n\t"
-        "addc.u32 %3, %3, m2;\n\t"
+        "add.cc.u32 %1, h0, m0;\n\t"
+        "addc.cc.u32 %2, l3, m1;\n\t"
+        "addc.u32 %3, h3, m2;\n\t"
         "}"
-        : "=&r"(r0), "=&r"(r1), "=&r"(r2), "=&r"(r3)
+        : "=r"(r0), "=&r"(r1), "=&r"(r2), "=&r"(r3)
         : "r"(a0), "r"(a1));
     return gl_reduce128_cc(r0, r1, r2, r3);
 }
@@ -220,19 +233,19 @@ GL_D u64 gl_acc_reduce(const GlAcc& t) {
         "add.cc.u32 w2, w2, %8;\n\t"            // w2 += l2
         "addc.cc.u32 w3, w3, 0;\n\t"
         "addc.u32 w4, w4, 0;\n\t"
-        "sub.cc.u32 t0, %2, w3;\n\t"            // t = (w1:w0) - (w4:w3)
-        "subc.cc.u32 t1, w1, w4;\n\t"
-        "subc.u32 m, 0, 0;\n\t"
-        "sub.cc.u32 t0, t0, m;\n\t"             // borrow: -= eps
-        "subc.u32 t1, t1, 0;\n\t"
-        "mad.lo.cc.u32 t0, w2, 0xffffffff, t0;\n\t"   // += w2 * eps
-        "madc.hi.cc.u32 t1, w2, 0xffffffff, t1;\n\t"
+        "mad.lo.cc.u32 t0, w2, %11, %2;\n\t"     // t = w2*eps + (w1:w0), carry C
+        "madc.hi.cc.u32 t1, w2, %11, w1;\n\t"
         "addc.u32 c, 0, 0;\n\t"
-        "mad.lo.cc.u32 %0, c, 0xffffffff, t0;\n\t"    // carry: += eps
-        "addc.u32 %1, t1, 0;\n\t"
+        "sub.cc.u32 t0, t0, w3;\n\t"            // t -= (w4:w3), borrow B;  c = C - B
+        "subc.cc.u32 t1, t1, w4;\n\t"
+        "subc.u32 c, c, 0;\n\t"
+        "shr.s32 m, c, 31;\n\t"
+        "sub.cc.u32 %0, t0, c;\n\t"             // t += c*eps
+        "subc.u32 t1, t1, m;\n\t"
+        "add.u32 %1, t1, c;\n\t"
         "}"
         : "=r"(r0), "=r"(r1)
-        : "r"(t.l0), "r"(t.h0), "r"(t.c0), "r"(t.l1), "r"(t.h1), "r"(t.c1), "r"(t.l2), "r"(t.h2), "r"(t.c2));
+        : "r"(t.l0), "r"(t.h0), "r"(t.c0), "r"(t.l1), "r"(t.h1), "r"(t.c1), "r"(t.l2), "r"(t.h2), "r"(t.c2), "r"(c_gl_eps));
     return pack64(r0, r1);
 }
 
