@@ -86,9 +86,14 @@ static __constant__ u32 c_gl_eps = 0xFFFFFFFFu;
 
 // x = x3*2^96 + x2*2^64 + x1*2^32 + x0  ->  some u64 representative of x mod p.
 //   t = x2*eps + (x1:x0)  (carry C),  t -= x3  (borrow B);  x = t + (C - B)*2^64 = t + (C - B)*eps  (mod p)
-// and t + (C - B)*eps always lands in [0, 2^64).  1 IMAD.WIDE + 9 ALU instructions.
+// and t + (C - B)*eps always lands in [0, 2^64): C = 1 needs t <= 2^64 - 2^33 + 1, B = 1 (x3 < 2^32) needs
+// t >= 2^64 - 2^32 + 1, so the single signed fix-up can neither overflow nor underflow.
+// Default: x2*eps + (x1:x0) as ONE accumulating IMAD.WIDE.U32 with carry-out (1 FMA-heavy + 9 ALU instructions).
+// -DGL_REDUCE_ALU: x2*eps = (x2 << 32) - x2 on the ALU pipe (12 ALU instructions, no multiply) -- measured slower:
+// tools/sboxbench.cu gives 31.2 (default) vs 36.5 (ALU form) SMSP cycles per multiplication, leaf hashing 8.64 vs 9.56 ms.
 GL_D u64 gl_reduce128_cc(u32 x0, u32 x1, u32 x2, u32 x3) {
     u32 r0, r1;
+#ifndef GL_REDUCE_ALU
     asm("{\n\t"
         ".reg .u32 t0, t1, w2, s;\n\t"
         "mad.lo.cc.u32 t0, %4, %6, %2;\n\t"
@@ -104,6 +109,25 @@ GL_D u64 gl_reduce128_cc(u32 x0, u32 x1, u32 x2, u32 x3) {
         "}"
         : "=r"(r0), "=r"(r1)
         : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(c_gl_eps));
+#else
+    asm("{\n\t"
+        ".reg .u32 e0, e1, t0, t1, w2, s;\n\t"
+        "sub.cc.u32 e0, 0, %4;\n\t"               // e = x2*eps = (x2 << 32) - x2
+        "subc.u32 e1, %4, 0;\n\t"
+        "add.cc.u32 t0, %2, e0;\n\t"              // t = (x1:x0) + e, carry C
+        "addc.cc.u32 t1, %3, e1;\n\t"
+        "addc.u32 w2, 0, 0;\n\t"
+        "sub.cc.u32 t0, t0, %5;\n\t"              // t -= x3, borrow B
+        "subc.cc.u32 t1, t1, 0;\n\t"
+        "subc.u32 w2, w2, 0;\n\t"                 // w2 = C - B in {-1, 0, 1}
+        "shr.s32 s, w2, 31;\n\t"
+        "sub.cc.u32 %0, t0, w2;\n\t"              // t += w2*eps = (w2 << 32) - sext(w2)
+        "subc.u32 t1, t1, s;\n\t"
+        "add.u32 %1, t1, w2;\n\t"
+        "}"
+        : "=r"(r0), "=r"(r1)
+        : "r"(x0), "r"(x1), "r"(x2), "r"(x3));
+#endif
     return pack64(r0, r1);
 }
 

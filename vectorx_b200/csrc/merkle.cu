@@ -176,6 +176,8 @@ int32_t merkle_build_device(vx_ctx* ctx, const u64* leaves, bool col_major, uint
             case 2: LEAF(true, 2, 8); break;      // round-1a kernel: IMAD.WIDE MDS layer
             case 3: LEAF(true, 0, 4); break;      // up to 128 registers
             case 4: LEAF(true, 0, 6); break;      // up to 80 registers
+            case 5: LEAF(true, 0, 10); break;     // 48 registers, 10 blocks per SM
+            case 6: LEAF(true, 0, 9); break;      // 56 registers, 9 blocks per SM
             default: LEAF(true, 0, 8); break;     // state in registers, 64 registers / 8 blocks per SM
         }
     } else {
