@@ -51,6 +51,7 @@ enum { VX_EV_START = 0, VX_EV_STAGED, VX_EV_INTT, VX_EV_LDE, VX_EV_LEAF, VX_EV_T
 struct vx_ctx {
     int device = 0;
     int sm_count = 0;
+    int ntt_legacy = 0;                 // VX_NTT_LEGACY=1: radix-2 shared-memory passes only (A/B switch)
     int poseidon_variant = 0;           // VX_POSEIDON_VARIANT (A/B switch for profiling): 0 = default, 1 = shared-memory state, 2 = 128-register form
     cudaStream_t stream = nullptr;
     std::mutex mu;                      // serialises calls on this context's stream
@@ -58,6 +59,7 @@ struct vx_ctx {
     u64 *w_lo = nullptr, *w_hi = nullptr, *wi_lo = nullptr, *wi_hi = nullptr;
     u64 *g_lo = nullptr, *g_hi = nullptr, *gi_lo = nullptr, *gi_hi = nullptr;
     u64 *roots12 = nullptr, *iroots12 = nullptr;
+    u64 *roots12f = nullptr, *iroots12f = nullptr;      // w_4096^e, e < 4096 (radix-16 group twiddles)
     // phase events of the most recent commit on this context (see vx_ctx_phase_ms)
     cudaEvent_t ev[VX_NUM_PHASE_EVENTS] = {};
 };
@@ -65,7 +67,8 @@ struct vx_ctx {
 struct TwiddleView {     // passed by value to kernels
     const u64* lo;       // W^(E & 0xffff)
     const u64* hi;       // W^((E >> 16) << 16)
-    const u64* roots12;  // w_4096^e
+    const u64* roots12;  // w_4096^e, e < 2048
+    const u64* full12;   // w_4096^e, e < 4096
 };
 
 // W^E for a 32-bit exponent (W of order 2^32): w_M^e = W^(e << (32 - log M))

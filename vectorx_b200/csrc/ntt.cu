@@ -53,12 +53,19 @@ int32_t ntt_module_init(vx_ctx* ctx) {
     u64 w12i = gl_inv_host(w12); acc = 1;
     for (int i = 0; i < 2048; i++) { r[i] = acc; acc = gl_mul_slow(acc, w12i); }
     VX_CHECK(upload(ctx, r, &ctx->iroots12));
+    r.resize(4096);
+    acc = 1;
+    for (int i = 0; i < 4096; i++) { r[i] = acc; acc = gl_mul_slow(acc, w12); }
+    VX_CHECK(upload(ctx, r, &ctx->roots12f));
+    acc = 1;
+    for (int i = 0; i < 4096; i++) { r[i] = acc; acc = gl_mul_slow(acc, w12i); }
+    VX_CHECK(upload(ctx, r, &ctx->iroots12f));
     return VX_OK;
 }
 
 void ntt_module_destroy(vx_ctx* ctx) {
     u64* ptrs[] = {ctx->w_lo, ctx->w_hi, ctx->wi_lo, ctx->wi_hi, ctx->g_lo, ctx->g_hi,
-                   ctx->gi_lo, ctx->gi_hi, ctx->roots12, ctx->iroots12};
+                   ctx->gi_lo, ctx->gi_hi, ctx->roots12, ctx->iroots12, ctx->roots12f, ctx->iroots12f};
     for (u64* p : ptrs) if (p) cudaFree(p);
 }
 
@@ -67,6 +74,7 @@ static TwiddleView tw_view(vx_ctx* ctx, bool inverse) {
     t.lo = inverse ? ctx->wi_lo : ctx->w_lo;
     t.hi = inverse ? ctx->wi_hi : ctx->w_hi;
     t.roots12 = inverse ? ctx->iroots12 : ctx->roots12;
+    t.full12 = inverse ? ctx->iroots12f : ctx->roots12f;
     return t;
 }
 
@@ -150,15 +158,201 @@ __global__ void __launch_bounds__(256) ntt_final_pass(u64* __restrict__ data, ui
     for (uint32_t e = threadIdx.x; e < chunk; e += blockDim.x) base[e] = gl_canon(sm[e]);
 }
 
+// ------------------------------------------------------------------------------------------------ radix-16 register passes
+// In Goldilocks w_64 = 8, so every root of unity of order <= 64 is a power of two: a 2^R-point DFT (R <= 4) needs no
+// real multiplication, only products by the compile-time constants 2^(96 j / half) below (ptxas folds the zero halves).
+// A "group" is R DIF stages at once on 2^R elements held in registers:
+//   y_j = sum_k x_k w_{2^R}^{jk}   (multiplication-free),   then   y_j *= w_M^{b j}   (M = 2^R S, b = index below S),
+// with y_j left at position bitrev_R(j) -- exactly what R radix-2 DIF stages over blocks of size M would produce.
+// The inverse transform is the same network on x_{(-k) mod 2^R} with the inverse twiddle tables.
+template <int S_BITS>
+GL_D u64 gl_mul_2exp(u64 x) {      // x * 2^S_BITS mod p, S_BITS < 96
+    constexpr u64 C = S_BITS < 64 ? (1ULL << (S_BITS & 63))
+                                  : (((1ULL << ((S_BITS - 64) & 31)) << 32) - (1ULL << ((S_BITS - 64) & 31)));   // 2^k * (2^32 - 1)
+    return gl_mul_cc(x, C);
+}
+
+template <int R, int STAGE, int J>
+GL_D u64 dft_twiddle(u64 d) {      // d * w_{2 half}^J with half = 2^(R - 1 - STAGE): w_{2 half} = 2^(96 / half)
+    constexpr int half = 1 << (R - 1 - STAGE);
+    constexpr int sh = (96 / half) * J;
+    if constexpr (J == 0) return d;
+    else return gl_mul_2exp<sh>(d);
+}
+
+template <int R, int STAGE, int B, int J>
+GL_D void dft_stage_pair(u64* x) {
+    constexpr int half = 1 << (R - 1 - STAGE);
+    u64 u = x[B + J], v = x[B + J + half];
+    x[B + J] = gl_add(u, v);
+    x[B + J + half] = dft_twiddle<R, STAGE, J>(gl_sub(u, v));
+}
+template <int R, int STAGE, int B, int J>
+GL_D void dft_stage_js(u64* x) {
+    constexpr int half = 1 << (R - 1 - STAGE);
+    if constexpr (J < half) {
+        dft_stage_pair<R, STAGE, B, J>(x);
+        dft_stage_js<R, STAGE, B, J + 1>(x);
+    }
+}
+template <int R, int STAGE, int B>
+GL_D void dft_stage_blocks(u64* x) {
+    constexpr int half = 1 << (R - 1 - STAGE);
+    if constexpr (B < (1 << R)) {
+        dft_stage_js<R, STAGE, B, 0>(x);
+        dft_stage_blocks<R, STAGE, B + 2 * half>(x);
+    }
+}
+template <int R, int STAGE>
+GL_D void dft_stages(u64* x) {
+    if constexpr (STAGE < R) {
+        dft_stage_blocks<R, STAGE, 0>(x);
+        dft_stages<R, STAGE + 1>(x);
+    }
+}
+// in place: x[q] <- y_{bitrev_R(q)}
+template <int R>
+GL_D void dft_dif(u64* x, bool inverse) {
+    if (inverse) {
+#pragma unroll
+        for (int k = 1; k < (1 << R) / 2; k++) { u64 t = x[k]; x[k] = x[(1 << R) - k]; x[(1 << R) - k] = t; }
+    }
+    dft_stages<R, 0>(x);
+}
+__host__ __device__ constexpr int brev_small(int q, int bits) {
+    int r = 0;
+    for (int i = 0; i < bits; i++) r |= ((q >> i) & 1) << (bits - 1 - i);
+    return r;
+}
+
+struct LdeScale {               // coset scaling fused into the first pass of the LDE: x_m *= (g w_N^rho)^m
+    const u64 *g_lo, *g_hi;     // g^m = g_hi[m >> 12] * g_lo[m & 4095]
+    TwiddleView fwd;            // forward W tables for w_N^(rho m)
+    uint32_t log_N, rate_bits, blk_first, blk_count;
+    u64 step[8][16];            // step[b][k] = (g w_N^rho_b)^(k * 16 * 2^low), b < blk_count <= 8
+};
+
+// Strided pass: the top 8 bits of every 2^log_M block, as two radix-16 groups.  A CTA owns a tile of 256 rows (row
+// stride 2^low elements, low = log_M - 8) x 16 contiguous elements (one 128-byte line per row); thread (r, t) holds
+// rows r + 16 k of column t for the first group and rows 16 r + k for the second (exchange through shared memory).
+// grid.x = tiles per transform, grid.y = transforms.  SCALE: in = coefficients (one transform per column), out = LDE
+// (blk_count transforms per column), log_M = log_n.
+template <bool SCALE>
+__global__ void __launch_bounds__(256) ntt_strided256_kernel(const u64* in, u64* out, uint32_t log_n, uint32_t log_M,
+                                                             TwiddleView tw, bool inverse,
+                                                             const __grid_constant__ LdeScale sc) {
+    __shared__ u64 sm[256 * NTT_PITCH];
+    const uint32_t low = log_M - 8;
+    const uint32_t tiles_per_blk = 1u << (low - 4);
+    const uint64_t blk = blockIdx.x / tiles_per_blk;
+    const uint32_t i0 = (blockIdx.x % tiles_per_blk) * NTT_TW + (threadIdx.x & 15);
+    const uint32_t t = threadIdx.x & 15, r = threadIdx.x >> 4;
+    uint64_t src_tr = blockIdx.y, dst_tr = blockIdx.y;
+    uint32_t cb = 0;
+    if (SCALE) { cb = blockIdx.y % sc.blk_count; src_tr = blockIdx.y / sc.blk_count; }
+    const u64* src = in + (src_tr << log_n) + (blk << log_M) + i0;
+    u64* dst = out + (dst_tr << log_n) + (blk << log_M) + i0;
+    u64 x[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) x[k] = src[(uint64_t)(r + 16 * k) << low];
+    const uint32_t b1 = (r << low) + i0;                      // index below S1 = 16 * 2^low
+    if (SCALE) {
+        const uint32_t rho = sc.rate_bits ? (__brev(sc.blk_first + cb) >> (32 - sc.rate_bits)) : 0;
+        u64 f = gl_mul_cc(__ldg(sc.g_hi + (b1 >> 12)), __ldg(sc.g_lo + (b1 & 4095)));
+        const u32 E = (b1 * rho) << (32 - sc.log_N);
+        if (E) f = gl_mul_cc(f, tw_pow_view(sc.fwd, E));
+#pragma unroll
+        for (int k = 0; k < 16; k++) x[k] = gl_mul_cc(x[k], k ? gl_mul_cc(f, sc.step[cb][k]) : f);
+    }
+    dft_dif<4>(x, inverse);
+#pragma unroll
+    for (int q = 1; q < 16; q++) {
+        const u32 E = (b1 * (u32)brev_small(q, 4)) << (32 - log_M);
+        if (E) x[q] = gl_mul_cc(x[q], tw_pow_view(tw, E));
+    }
+#pragma unroll
+    for (int q = 0; q < 16; q++) sm[(r + 16 * q) * NTT_PITCH + t] = x[q];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; k++) x[k] = sm[(16 * r + k) * NTT_PITCH + t];
+    dft_dif<4>(x, inverse);
+#pragma unroll
+    for (int q = 1; q < 16; q++) {
+        const u32 E = (i0 * (u32)brev_small(q, 4)) << (32 - (log_M - 4));      // w_{M/16}^(i0 j)
+        if (E) x[q] = gl_mul_cc(x[q], tw_pow_view(tw, E));
+    }
+#pragma unroll
+    for (int q = 0; q < 16; q++) dst[(uint64_t)(16 * r + q) << low] = gl_canon(x[q]);
+}
+
+// one radix-2^R group over a 4096-element chunk held in (padded) shared memory; S = elements below the group
+#define NTT_PAD(i) ((i) + ((i) >> 4))
+template <int R>
+GL_D void ntt_smem_group(u64* sm, uint32_t s_bits, const u64* __restrict__ full12, bool inverse) {
+    const uint32_t S = 1u << s_bits;
+    for (uint32_t u = threadIdx.x; u < (4096u >> R); u += 256) {
+        const uint32_t b = u & (S - 1);
+        const uint32_t base = ((u >> s_bits) << (s_bits + R)) + b;
+        u64 x[1 << R];
+#pragma unroll
+        for (int k = 0; k < (1 << R); k++) x[k] = sm[NTT_PAD(base + ((uint32_t)k << s_bits))];
+        dft_dif<R>(x, inverse);
+        if (s_bits) {
+#pragma unroll
+            for (int q = 1; q < (1 << R); q++) {
+                const uint32_t e = (b * (uint32_t)brev_small(q, R)) << (12 - s_bits - R);
+                if (e) x[q] = gl_mul_cc(x[q], __ldg(full12 + e));
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < (1 << R); q++) sm[NTT_PAD(base + ((uint32_t)q << s_bits))] = x[q];
+    }
+}
+
+// Final pass: F DIF stages on contiguous 2^F blocks (F <= 12); a CTA owns 4096 contiguous elements.
+__global__ void __launch_bounds__(256) ntt_final4096_kernel(u64* __restrict__ data, uint32_t F, TwiddleView tw, bool inverse) {
+    __shared__ u64 sm[4096 + 256];
+    u64* base = data + ((uint64_t)blockIdx.x << 12);
+    for (uint32_t e = threadIdx.x; e < 4096; e += 256) sm[NTT_PAD(e)] = base[e];
+    __syncthreads();
+    uint32_t rem = F;
+    const uint32_t r1 = ((F - 1) & 3) + 1;                  // first group takes F mod 4 bits (or 4)
+    rem -= r1;
+    switch (r1) {
+        case 1: ntt_smem_group<1>(sm, rem, tw.full12, inverse); break;
+        case 2: ntt_smem_group<2>(sm, rem, tw.full12, inverse); break;
+        case 3: ntt_smem_group<3>(sm, rem, tw.full12, inverse); break;
+        default: ntt_smem_group<4>(sm, rem, tw.full12, inverse); break;
+    }
+    __syncthreads();
+    while (rem) {
+        rem -= 4;
+        ntt_smem_group<4>(sm, rem, tw.full12, inverse);
+        __syncthreads();
+    }
+    for (uint32_t e = threadIdx.x; e < 4096; e += 256) base[e] = gl_canon(sm[NTT_PAD(e)]);
+}
+
 int32_t ntt_dif_inplace(vx_ctx* ctx, u64* data, uint64_t count, uint32_t log_n, bool inverse) {
     if (log_n == 0 || count == 0) return VX_OK;
     VX_REQUIRE(log_n <= 32, "ntt: log_n %u exceeds the field's two-adicity", log_n);
-    VX_REQUIRE(count < 65536, "ntt: too many transforms in one call (%llu)", (unsigned long long)count);
     TwiddleView tw = tw_view(ctx, inverse);
     uint32_t rem = log_n;
+    const bool fast = !ctx->ntt_legacy;
     while (rem > 12) {
+        uint64_t tiles;
+        VX_REQUIRE(count < 65536, "ntt: too many transforms in one call (%llu)", (unsigned long long)count);
+        if (fast && rem >= 16) {                       // radix-16 register pass over the top 8 bits
+            tiles = (1ULL << log_n) >> 12;
+            VX_REQUIRE(tiles < (1ULL << 31), "ntt: transform too large");
+            dim3 grid((unsigned)tiles, (unsigned)count);
+            ntt_strided256_kernel<false><<<grid, 256, 0, ctx->stream>>>(data, data, log_n, rem, tw, inverse, LdeScale{});
+            VX_LAUNCH_COUNT(ctx, 1);
+            rem -= 8;
+            continue;
+        }
         uint32_t A = rem - 8 < 8 ? rem - 8 : 8;
-        uint64_t tiles = (1ULL << log_n) / ((1ULL << A) * NTT_TW);
+        tiles = (1ULL << log_n) / ((1ULL << A) * NTT_TW);
         VX_REQUIRE(tiles < (1ULL << 31), "ntt: transform too large");
         dim3 grid((unsigned)tiles, (unsigned)count);
         size_t smem = (size_t)(1u << A) * NTT_PITCH * sizeof(u64);
@@ -166,9 +360,16 @@ int32_t ntt_dif_inplace(vx_ctx* ctx, u64* data, uint64_t count, uint32_t log_n, 
         VX_LAUNCH_COUNT(ctx, 1);
         rem -= A;
     }
+    uint64_t total = count << log_n;
+    if (fast && rem >= 1 && (total & 4095) == 0) {
+        VX_REQUIRE((total >> 12) < (1ULL << 31), "ntt: too many blocks");
+        ntt_final4096_kernel<<<(unsigned)(total >> 12), 256, 0, ctx->stream>>>(data, rem, tw, inverse);
+        VX_LAUNCH_COUNT(ctx, 1);
+        VX_CUDA(cudaGetLastError());
+        return VX_OK;
+    }
     // a CTA owns 2^chunk_bits contiguous elements = one or more whole 2^rem blocks
     uint32_t chunk_bits = rem < 10 ? 10 : rem;
-    uint64_t total = count << log_n;
     uint32_t max_bits = log_n + (uint32_t)__builtin_ctzll(count);     // largest power of two dividing total
     if (chunk_bits > max_bits) chunk_bits = max_bits;
     uint64_t blocks = total >> chunk_bits;
@@ -229,6 +430,26 @@ int32_t lde_batch(vx_ctx* ctx, const u64* coeffs, u64* lde_out, uint32_t c, uint
     VX_REQUIRE(log_n + rate_bits <= 26, "lde: 2^%u points exceeds the coset table (2^26)", log_n + rate_bits);
     VX_REQUIRE(blk_count >= 1 && blk_first + blk_count <= (1u << rate_bits), "lde: coset block range out of bounds");
     uint64_t n = 1ULL << log_n;
+    if (!ctx->ntt_legacy && log_n >= 16 && blk_count <= 8) {
+        // first pass fused with the coset scaling: reads the coefficients once per coset (L2-resident), writes the LDE
+        LdeScale sc;
+        memset(&sc, 0, sizeof sc);
+        sc.g_lo = ctx->g_lo; sc.g_hi = ctx->g_hi; sc.fwd = tw_view(ctx, false);
+        sc.log_N = log_n + rate_bits; sc.rate_bits = rate_bits; sc.blk_first = blk_first; sc.blk_count = blk_count;
+        const u64 wN = gl_root_of_unity_host(log_n + rate_bits);
+        for (uint32_t b = 0; b < blk_count; b++) {
+            uint32_t rho = (uint32_t)bitrev_u64(blk_first + b, rate_bits);
+            u64 base = gl_mul_slow(GL_GENERATOR, gl_pow_host(wN, rho));          // g w_N^rho
+            u64 st = gl_pow_host(base, n >> 4), acc = 1;                         // ^(16 * 2^low), low = log_n - 8
+            for (int k = 0; k < 16; k++) { sc.step[b][k] = acc; acc = gl_mul_slow(acc, st); }
+        }
+        dim3 grid((unsigned)(n >> 12), (unsigned)(c * blk_count));
+        ntt_strided256_kernel<true><<<grid, 256, 0, ctx->stream>>>(coeffs, lde_out, log_n, log_n, sc.fwd, false, sc);
+        VX_LAUNCH_COUNT(ctx, 1);
+        VX_CUDA(cudaGetLastError());
+        // remaining stages: every 2^(log_n - 8) block is an independent transform
+        return ntt_dif_inplace(ctx, lde_out, ((uint64_t)c * blk_count) << 8, log_n - 8, false);
+    }
     dim3 grid((unsigned)((n + 255) / 256), c);
     lde_scale_kernel<<<grid, 256, 0, ctx->stream>>>(coeffs, lde_out, log_n, rate_bits, blk_first, blk_count,
                                                     ctx->g_lo, ctx->g_hi, tw_view(ctx, false));

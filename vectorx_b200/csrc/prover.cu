@@ -202,7 +202,7 @@ extern "C" int32_t vx_quotient(vx_ctx* ctx, const vx_circuit_desc* d, vx_batch* 
     }
     p.n_inv = gl_inv_host(n % GL_P);
     p.out = d_q.p;
-    p.tw.lo = ctx->w_lo; p.tw.hi = ctx->w_hi; p.tw.roots12 = ctx->roots12;
+    p.tw.lo = ctx->w_lo; p.tw.hi = ctx->w_hi; p.tw.roots12 = ctx->roots12; p.tw.full12 = ctx->roots12f;
     size_t smem = (size_t)VX_PROGRAM_REGS * QBLOCK * sizeof(u64);
     VX_CUDA(cudaFuncSetAttribute(quotient_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     quotient_kernel<<<(unsigned)((N + QBLOCK - 1) / QBLOCK), QBLOCK, smem, ctx->stream>>>(p);
@@ -293,7 +293,7 @@ extern "C" int32_t vx_zs_partial_products(vx_ctx* ctx, const vx_circuit_desc* d,
     VX_CHECK(dbk.alloc((size_t)R * 8, ctx->stream));
     VX_CUDA(cudaMemcpyAsync(dw.p, wires, (size_t)R * n * 8, cudaMemcpyDefault, ctx->stream));
     VX_CUDA(cudaMemcpyAsync(ds.p, sigmas, (size_t)R * n * 8, cudaMemcpyDefault, ctx->stream));
-    TwiddleView tw; tw.lo = ctx->w_lo; tw.hi = ctx->w_hi; tw.roots12 = ctx->roots12;
+    TwiddleView tw; tw.lo = ctx->w_lo; tw.hi = ctx->w_hi; tw.roots12 = ctx->roots12; tw.full12 = ctx->roots12f;
     std::vector<u64> bk(R);
     for (uint32_t k = 0; k < nch; k++) {
         for (uint32_t w = 0; w < R; w++) bk[w] = gl_mul_slow(betas[k] % GL_P, d->k_is[w] % GL_P);
