@@ -74,6 +74,9 @@ extern "C" int32_t vx_ctx_create(int32_t device, vx_ctx** out) {
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh);
     }
     for (int i = 0; i < VX_NUM_PHASE_EVENTS; i++) cudaEventCreate(&ctx->ev[i]);
+    cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    for (auto& e : ctx->copy_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->copy_free, cudaEventDisableTiming);
     int32_t r = poseidon_module_init(ctx);
     if (r == VX_OK) r = ntt_module_init(ctx);
     if (r == VX_OK) r = fri_module_init(ctx);
@@ -88,6 +91,9 @@ extern "C" void vx_ctx_destroy(vx_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     ntt_module_destroy(ctx);
     for (int i = 0; i < VX_NUM_PHASE_EVENTS; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (auto& e : ctx->copy_ev) if (e) cudaEventDestroy(e);
+    if (ctx->copy_free) cudaEventDestroy(ctx->copy_free);
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -122,20 +128,39 @@ static int32_t commit_run(vx_ctx* ctx, vx_batch* b, const u64* src, bool is_valu
     VX_CHECK(b->digests.alloc((size_t)2 * (N_loc - caps_loc) * 4 * sizeof(u64), ctx->stream));
     VX_CHECK(b->cap.alloc((size_t)caps_loc * 4 * sizeof(u64), ctx->stream));
     EV(ctx, VX_EV_START);
+    const bool from_host = !vx_is_device_ptr(src);
+    // column chunks: with a host source the H2D copy of chunk k+1 (copy stream) overlaps the transforms of chunk k
+    const uint32_t nchunks = (from_host && c >= 16) ? 8 : 1;
+    DevBuf stage;
+    u64* work = nullptr;
     if (is_values) {
-        // stage the values in the (not yet used) LDE buffer when it is big enough, transform, emit coefficients
-        DevBuf stage;
-        u64* work = b->lde.p;
-        if (b->lde.bytes < coeff_bytes) { VX_CHECK(stage.alloc(coeff_bytes, ctx->stream)); work = stage.p; }
-        VX_CUDA(cudaMemcpyAsync(work, src, coeff_bytes, cudaMemcpyDefault, ctx->stream));
-        EV(ctx, VX_EV_STAGED);
-        VX_CHECK(intt_batch(ctx, work, b->coeffs.p, c, b->log_n));
-    } else {
-        VX_CUDA(cudaMemcpyAsync(b->coeffs.p, src, coeff_bytes, cudaMemcpyDefault, ctx->stream));
-        EV(ctx, VX_EV_STAGED);
+        // stage the values in the (not yet used) LDE buffer when it is big enough and chunks cannot collide with it
+        work = b->lde.p;
+        if (nchunks > 1 || b->lde.bytes < coeff_bytes) { VX_CHECK(stage.alloc(coeff_bytes, ctx->stream)); work = stage.p; }
     }
-    EV(ctx, VX_EV_INTT);
-    VX_CHECK(lde_batch(ctx, b->coeffs.p, b->lde.p, c, b->log_n, b->rate_bits, b->blk_first, b->blk_count));
+    if (nchunks > 1) {
+        VX_CUDA(cudaEventRecord(ctx->copy_free, ctx->stream));             // allocations above are stream-ordered
+        VX_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_free, 0));
+    }
+    for (uint32_t k = 0; k < nchunks; k++) {
+        const uint32_t c0 = (uint32_t)((uint64_t)c * k / nchunks), c1 = (uint32_t)((uint64_t)c * (k + 1) / nchunks);
+        if (c1 == c0) continue;
+        const size_t off = (size_t)c0 * n, bytes = (size_t)(c1 - c0) * n * sizeof(u64);
+        u64* dst = is_values ? work + off : b->coeffs.p + off;
+        if (nchunks > 1) {
+            VX_CUDA(cudaMemcpyAsync(dst, src + off, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+            VX_CUDA(cudaEventRecord(ctx->copy_ev[k], ctx->copy_stream));
+            VX_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[k], 0));
+        } else {
+            VX_CUDA(cudaMemcpyAsync(dst, src + off, bytes, cudaMemcpyDefault, ctx->stream));
+            EV(ctx, VX_EV_STAGED);
+        }
+        if (is_values) VX_CHECK(intt_batch(ctx, work + off, b->coeffs.p + off, c1 - c0, b->log_n));
+        if (nchunks == 1) EV(ctx, VX_EV_INTT);
+        VX_CHECK(lde_batch(ctx, b->coeffs.p + off, b->lde.p + (size_t)c0 * N_loc, c1 - c0, b->log_n, b->rate_bits,
+                           b->blk_first, b->blk_count));
+    }
+    if (nchunks > 1) { EV(ctx, VX_EV_STAGED); EV(ctx, VX_EV_INTT); }      // phases interleave: all reported under "lde"
     EV(ctx, VX_EV_LDE);
     VX_CHECK(merkle_build_device(ctx, b->lde.p, true, N_loc, N_loc, c, b->cap_height_loc(), b->digests.p, b->cap.p,
                                  ctx->ev[VX_EV_LEAF]));

@@ -54,6 +54,9 @@ struct vx_ctx {
     int ntt_legacy = 0;                 // VX_NTT_LEGACY=1: radix-2 shared-memory passes only (A/B switch)
     int poseidon_variant = 0;           // VX_POSEIDON_VARIANT (A/B switch for profiling): 0 = default, 1 = shared-memory state, 2 = 128-register form
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr; // host->device staging of commit inputs, overlapped with the transforms
+    cudaEvent_t copy_ev[16] = {};       // one per column chunk in flight
+    cudaEvent_t copy_free = nullptr;    // staging buffer no longer read by the compute stream
     std::mutex mu;                      // serialises calls on this context's stream
     std::atomic<uint64_t> launches{0};
     u64 *w_lo = nullptr, *w_hi = nullptr, *wi_lo = nullptr, *wi_hi = nullptr;
