@@ -231,6 +231,11 @@ def main():
     cap_all = torch.empty((1 << cap, 4), dtype=torch.int64, device=f"cuda:{local_rank}")
     cap_host = torch.empty((1 << cap, 4), dtype=torch.int64).pin_memory()
     phase_acc = {}
+    if G > 1:
+        from vectorx_b200.sharded import DeviceEngine, ShardPlan, TorchComm, sharded_commit
+        plan = ShardPlan(G, rank, c, log_n, rate, cap)
+        engine, comm = DeviceEngine(ctx), TorchComm(dist)
+        bufs = {"coeff_mine": coeff_mine, "coeff_all": coeff_all, "cap_loc": cap_loc, "cap_all": cap_all}
 
     def one_step(src, from_host):
         """One commit. src: this rank's (cpr, n) values (host-pinned or device). Returns nothing; cap -> cap_host."""
@@ -244,21 +249,13 @@ def main():
                 check(lib.vx_batch_cap(h, cap_host.data_ptr()), "vx_batch_cap")
             lib.vx_batch_free(h)
             return
-        # column-sharded iNTT (device in/out through the same ABI), then NCCL all-gather of coefficients
-        check(lib.vx_ntt(ctx.handle, src.data_ptr(), coeff_mine.data_ptr(), cpr, log_n, 1, 0), "vx_ntt")
-        dist.all_gather_into_tensor(coeff_all, coeff_mine)
-        torch.cuda.current_stream().synchronize()
-        h = vp()
-        check(lib.vx_commit_from_coeffs_shard(ctx.handle, coeff_all.data_ptr(), c, log_n, rate, cap, rank, G,
-                                              ctypes.byref(h)), "vx_commit_from_coeffs_shard")
+        # column-sharded iNTT -> NCCL all-gather of coefficients -> own cosets / cap subtrees -> caps gathered
+        h, _ = sharded_commit(src, plan, engine, comm, bufs)
         for k, v in ctx.phase_ms().items():
             phase_acc[k] = phase_acc.get(k, 0.0) + v
-        check(lib.vx_batch_cap(h, cap_loc.data_ptr()), "vx_batch_cap")
-        dist.all_gather_into_tensor(cap_all, cap_loc)              # "merge the subtree caps"
         if from_host and rank == 0:
             cap_host.copy_(cap_all, non_blocking=False)
-        torch.cuda.current_stream().synchronize()
-        lib.vx_batch_free(h)
+        engine.free(h)
 
     def barrier():
         if dist is not None:
@@ -270,17 +267,17 @@ def main():
         sets = host_sets if from_host else dev_sets
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # G == 1: events on the library's stream.  G > 1: the NCCL legs run on torch's current stream and every library
+        # call is blocking, so events on torch's stream bracket all device work of the region.
+        ev_stream = stream if G == 1 else torch.cuda.current_stream()
         t0 = time.perf_counter()
-        e0.record(stream)
+        e0.record(ev_stream)
         for i in range(steps):
             one_step(sets[i % N_INPUT_SETS], from_host)
-        e1.record(stream)
+        e1.record(ev_stream)
         barrier()
         wall = (time.perf_counter() - t0) * 1e3
-        dev = e0.elapsed_time(e1)
-        ms = max(dev, 0.0)
-        if G > 1:                       # NCCL legs run on torch's stream: use the wall clock of the bracketed region
-            ms = wall
+        ms = max(e0.elapsed_time(e1), 0.0)
         t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local_rank}")
         if dist is not None:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -291,6 +288,18 @@ def main():
         one_step(dev_sets[i % N_INPUT_SETS], False)
     for i in range(2):
         one_step(host_sets[i % N_INPUT_SETS], True)
+    if G > 1:
+        # sanity (untimed): the gathered cap of the sharded commit must equal a whole commit of the same values
+        full0 = gen_values(c, n, seed=0x5EED0001)
+        one_step(dev_sets[0], False)
+        torch.cuda.synchronize()
+        if rank == 0:
+            whole = vx.PolynomialBatch.from_values(full0, rate, False, cap, ctx=ctx)
+            same = np.array_equal(whole.cap.hashes, cap_all.cpu().numpy().view(np.uint64))
+            whole.close()
+            if not same:
+                raise SystemExit("bench.py: sharded commit cap differs from the single-GPU cap")
+        del full0
     launches0 = ctx.launch_count
     phase_acc.clear()
     sampler = ClockSampler(local_rank)

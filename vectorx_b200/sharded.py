@@ -1,0 +1,146 @@
+"""One commit sharded over G GPUs (coset partition) -- host-side plan and driver.
+
+Rank g of G (G a power of two, G <= 2^rate_bits, G <= 2^cap_height) ends up owning leaf block
+[g N/G, (g+1) N/G): whole LDE cosets and whole cap subtrees, so no interior hashing crosses GPUs.
+
+    1. iNTT of this rank's column slice                       (no communication)
+    2. all-gather of the coefficients, 8 n c bytes in total    (the ONE exchange step; NCCL over NVLink)
+    3. coset NTTs + leaf hashing + subtrees of the own block   (no communication)
+    4. all-gather of the 2^cap_height / G local cap entries    (512 B)
+
+The compute steps go through an engine object: `DeviceEngine` binds the C ABI (libvectorx_b200.so) and is the only
+engine in the product; tests inject a CPU engine to exercise the plan and the collective plumbing over gloo.
+The path this replaces is plonky2's single-process PolynomialBatch::from_values (reached from
+contracts/lib/succinctx/plonky2x/core/src/backend/circuit/build.rs:69-75); upstream has no multi-device form.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+
+
+@dataclass(frozen=True)
+class ShardPlan:
+    world: int
+    rank: int
+    c: int
+    log_n: int
+    rate_bits: int
+    cap_height: int
+
+    def __post_init__(self):
+        g = self.world
+        if g < 1 or g & (g - 1):
+            raise ValueError(f"world size {g} is not a power of two")
+        if not 0 <= self.rank < g:
+            raise ValueError(f"rank {self.rank} out of range for world size {g}")
+        if g > (1 << self.rate_bits) or g > (1 << self.cap_height):
+            raise ValueError(f"{g} shards need rate_bits >= {g.bit_length() - 1} and cap_height >= {g.bit_length() - 1} "
+                             "(whole cosets and whole cap subtrees per shard)")
+        if self.c < 1:
+            raise ValueError("empty batch")
+
+    # ---- column slice for the iNTT stage (last ranks zero-padded so every rank gathers equal blocks)
+    @property
+    def cols_per_rank(self) -> int:
+        return (self.c + self.world - 1) // self.world
+
+    @property
+    def col_lo(self) -> int:
+        return min(self.c, self.rank * self.cols_per_rank)
+
+    @property
+    def col_hi(self) -> int:
+        return min(self.c, self.col_lo + self.cols_per_rank)
+
+    # ---- leaf block / cap slice owned after the exchange
+    @property
+    def n(self) -> int:
+        return 1 << self.log_n
+
+    @property
+    def lde_size(self) -> int:
+        return self.n << self.rate_bits
+
+    @property
+    def leaves(self) -> int:
+        return self.lde_size // self.world
+
+    @property
+    def leaf_first(self) -> int:
+        return self.rank * self.leaves
+
+    @property
+    def caps(self) -> int:
+        return (1 << self.cap_height) // self.world
+
+    @property
+    def cap_first(self) -> int:
+        return self.rank * self.caps
+
+    @property
+    def cosets(self):
+        """natural coset indices rho (LDE point i = 2^rate_bits k + rho) of the leaf blocks this rank owns, in leaf order"""
+        per = (1 << self.rate_bits) // self.world
+        out = []
+        for b in range(self.rank * per, (self.rank + 1) * per):
+            rho = int(format(b, f"0{self.rate_bits}b")[::-1], 2) if self.rate_bits else 0
+            out.append(rho)
+        return out
+
+    @property
+    def exchange_bytes_per_rank(self) -> int:
+        """bytes this rank receives in the coefficient all-gather"""
+        return 8 * self.n * self.cols_per_rank * (self.world - 1)
+
+
+class DeviceEngine:
+    """Compute steps through the C ABI on this rank's GPU. Arrays are torch CUDA tensors (int64 views of u64)."""
+
+    def __init__(self, ctx):
+        from ._lib import check, load
+        self.ctx, self.lib, self.check = ctx, load(), check
+
+    def fence(self):
+        """collectives run on torch's current stream, the library on its own: order them"""
+        import torch
+        torch.cuda.current_stream().synchronize()
+
+    def intt(self, values, coeffs_out, ncols: int, log_n: int):
+        self.check(self.lib.vx_ntt(self.ctx.handle, values.data_ptr(), coeffs_out.data_ptr(), ncols, log_n, 1, 0), "vx_ntt")
+
+    def commit_shard(self, coeffs_all, plan: ShardPlan, cap_out):
+        from ._lib import vp
+        h = vp()
+        self.check(self.lib.vx_commit_from_coeffs_shard(self.ctx.handle, coeffs_all.data_ptr(), plan.c, plan.log_n,
+                                                        plan.rate_bits, plan.cap_height, plan.rank, plan.world,
+                                                        ctypes.byref(h)), "vx_commit_from_coeffs_shard")
+        self.check(self.lib.vx_batch_cap(h, cap_out.data_ptr()), "vx_batch_cap")
+        return h
+
+    def free(self, handle):
+        self.lib.vx_batch_free(handle)
+
+
+class TorchComm:
+    """torch.distributed all-gather (NCCL on GPUs, gloo in the CPU tests)."""
+
+    def __init__(self, dist):
+        self.dist = dist
+
+    def all_gather(self, out, inp):
+        self.dist.all_gather_into_tensor(out, inp)
+
+
+def sharded_commit(values_local, plan: ShardPlan, engine, comm, bufs):
+    """values_local: this rank's (cols_per_rank, n) slice of the values (zero rows beyond col_hi).
+    bufs: dict of preallocated tensors on the engine's device:
+        coeff_mine (cols_per_rank, n), coeff_all (world * cols_per_rank, n), cap_loc (caps, 4), cap_all (2^cap_height, 4).
+    Returns (shard handle, cap_all) -- cap_all is plonky2's merkle_tree.cap of the WHOLE commitment on every rank."""
+    engine.intt(values_local, bufs["coeff_mine"], plan.cols_per_rank, plan.log_n)
+    comm.all_gather(bufs["coeff_all"], bufs["coeff_mine"])
+    engine.fence()
+    handle = engine.commit_shard(bufs["coeff_all"], plan, bufs["cap_loc"])
+    comm.all_gather(bufs["cap_all"], bufs["cap_loc"])
+    engine.fence()
+    return handle, bufs["cap_all"]
