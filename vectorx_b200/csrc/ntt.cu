@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(256) ntt_strided_pass(u64* __restrict__ data, 
     const uint32_t tiles_per_blk = 1u << (low - 4);
     const uint64_t blk = blockIdx.x / tiles_per_blk;
     const uint32_t i0_base = (blockIdx.x % tiles_per_blk) * NTT_TW;
-    u64* base = data + ((uint64_t)blockIdx.y << log_n) + (blk << log_M) + i0_base;
+    u64* base = data + (((uint64_t)blockIdx.z * gridDim.y + blockIdx.y) << log_n) + (blk << log_M) + i0_base;
     const uint32_t R = 1u << A;
     const uint32_t elems = R * NTT_TW;
 
@@ -247,9 +247,10 @@ __global__ void __launch_bounds__(256) ntt_strided256_kernel(const u64* in, u64*
     const uint64_t blk = blockIdx.x / tiles_per_blk;
     const uint32_t i0 = (blockIdx.x % tiles_per_blk) * NTT_TW + (threadIdx.x & 15);
     const uint32_t t = threadIdx.x & 15, r = threadIdx.x >> 4;
-    uint64_t src_tr = blockIdx.y, dst_tr = blockIdx.y;
+    const uint64_t tr = (uint64_t)blockIdx.z * gridDim.y + blockIdx.y;       // transform index (grid.y x grid.z)
+    uint64_t src_tr = tr, dst_tr = tr;
     uint32_t cb = 0;
-    if (SCALE) { cb = blockIdx.y % sc.blk_count; src_tr = blockIdx.y / sc.blk_count; }
+    if (SCALE) { cb = (uint32_t)(tr % sc.blk_count); src_tr = tr / sc.blk_count; }
     const u64* src = in + (src_tr << log_n) + (blk << log_M) + i0;
     u64* dst = out + (dst_tr << log_n) + (blk << log_M) + i0;
     u64 x[16];
@@ -341,11 +342,14 @@ int32_t ntt_dif_inplace(vx_ctx* ctx, u64* data, uint64_t count, uint32_t log_n, 
     const bool fast = !ctx->ntt_legacy;
     while (rem > 12) {
         uint64_t tiles;
-        VX_REQUIRE(count < 65536, "ntt: too many transforms in one call (%llu)", (unsigned long long)count);
+        // transforms are spread over grid.y x grid.z (count must factor as gy * gz with gy a power of two <= 32768)
+        uint64_t gy = count, gz = 1;
+        while (gy > 32768 && (gy & 1) == 0) { gy >>= 1; gz <<= 1; }
+        VX_REQUIRE(gy <= 65535 && gz <= 65535, "ntt: cannot tile %llu transforms over the grid", (unsigned long long)count);
         if (fast && rem >= 16) {                       // radix-16 register pass over the top 8 bits
             tiles = (1ULL << log_n) >> 12;
             VX_REQUIRE(tiles < (1ULL << 31), "ntt: transform too large");
-            dim3 grid((unsigned)tiles, (unsigned)count);
+            dim3 grid((unsigned)tiles, (unsigned)gy, (unsigned)gz);
             ntt_strided256_kernel<false><<<grid, 256, 0, ctx->stream>>>(data, data, log_n, rem, tw, inverse, LdeScale{});
             VX_LAUNCH_COUNT(ctx, 1);
             rem -= 8;
@@ -354,7 +358,7 @@ int32_t ntt_dif_inplace(vx_ctx* ctx, u64* data, uint64_t count, uint32_t log_n, 
         uint32_t A = rem - 8 < 8 ? rem - 8 : 8;
         tiles = (1ULL << log_n) / ((1ULL << A) * NTT_TW);
         VX_REQUIRE(tiles < (1ULL << 31), "ntt: transform too large");
-        dim3 grid((unsigned)tiles, (unsigned)count);
+        dim3 grid((unsigned)tiles, (unsigned)gy, (unsigned)gz);
         size_t smem = (size_t)(1u << A) * NTT_PITCH * sizeof(u64);
         ntt_strided_pass<<<grid, 256, smem, ctx->stream>>>(data, log_n, rem, A, tw);
         VX_LAUNCH_COUNT(ctx, 1);
@@ -443,7 +447,10 @@ int32_t lde_batch(vx_ctx* ctx, const u64* coeffs, u64* lde_out, uint32_t c, uint
             u64 st = gl_pow_host(base, n >> 4), acc = 1;                         // ^(16 * 2^low), low = log_n - 8
             for (int k = 0; k < 16; k++) { sc.step[b][k] = acc; acc = gl_mul_slow(acc, st); }
         }
-        dim3 grid((unsigned)(n >> 12), (unsigned)(c * blk_count));
+        uint64_t gy = (uint64_t)c * blk_count, gz = 1;
+        while (gy > 32768 && (gy & 1) == 0) { gy >>= 1; gz <<= 1; }
+        VX_REQUIRE(gy <= 65535, "lde: cannot tile %u x %u transforms over the grid", c, blk_count);
+        dim3 grid((unsigned)(n >> 12), (unsigned)gy, (unsigned)gz);
         ntt_strided256_kernel<true><<<grid, 256, 0, ctx->stream>>>(coeffs, lde_out, log_n, log_n, sc.fwd, false, sc);
         VX_LAUNCH_COUNT(ctx, 1);
         VX_CUDA(cudaGetLastError());
