@@ -340,12 +340,29 @@ def main():
                 traffic = json.load(f).get("dram_bytes_per_launch")
         except Exception:
             pass
+        pipes = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_leaf_hash_pipes.json")) as f:
+                pipes = json.load(f)
+        except Exception:
+            pass
+        wide_peak = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "int_peaks_r01.json")) as f:
+                wide_peak = float(json.load(f)["imad_wide_acc"]["thread_instr_per_s"]) / 1e9
+        except Exception:
+            pass
         roofline = {
             "kernel": "leaf_hash_kernel<col_major> (Poseidon sponge, one thread per LDE row)",
             "bound": "int_alu",
             "achieved": leaf_gops, "peak": int_peak, "unit": "G 32x32 mul-add/s",
             "frac": (leaf_gops / int_peak) if leaf_gops else None,
             "peak_source": int_src,
+            # the counted unit (32x32+64 multiply-add) is one IMAD.WIDE.U32, whose own measured issue rate is lower than
+            # the 32-bit IMAD rate used as `peak`; both fractions are reported, plus what ncu saw on the pipes
+            "peak_imad_wide": wide_peak,
+            "frac_vs_imad_wide": (leaf_gops / wide_peak) if (leaf_gops and wide_peak) else None,
+            "ncu_pipes": pipes,
             "algorithmic_ops_per_launch": perms * IMADS_PER_PERMUTATION,
             "ms_per_launch": leaf_ms,
             "traffic": traffic,
