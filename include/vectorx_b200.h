@@ -52,6 +52,14 @@ uint64_t vx_ctx_launch_count(vx_ctx* ctx);
  * Plays the role of plonky2's TimingTree scopes ("IFFT", "FFT + blinding", "build Merkle tree"). */
 int32_t vx_ctx_phase_ms(vx_ctx* ctx, float out[5]);
 
+/* ---- device buffers for callers that keep prover intermediates on the GPU between calls (witness values, Z / partial
+ * products, quotient coefficients: in plonky2 these are host Vecs handed from one phase of
+ * prove_with_partition_witness to the next).  Every `host or device` pointer of this header may be one of these. */
+int32_t vx_dev_alloc(vx_ctx* ctx, size_t bytes, uint64_t** out);
+void vx_dev_free(vx_ctx* ctx, uint64_t* p);
+/* dst/src: host or device, any combination; blocking */
+int32_t vx_dev_copy(vx_ctx* ctx, void* dst, const void* src, size_t bytes);
+
 /* ---- PolynomialBatch (plonky2 fri/oracle.rs) ------------------------------------------------
  * vx_commit_from_values replaces PolynomialBatch::from_values(values, rate_bits, blinding=false,
  *   cap_height, timing, fft_root_table): reached from prove_with_partition_witness
@@ -110,7 +118,18 @@ const uint64_t* vx_batch_digests_device(const vx_batch* b);
 enum {
     VX_OP_END = 0, VX_OP_LOADW = 1, VX_OP_LOADC = 2, VX_OP_LOADPI = 3, VX_OP_LOADK = 4,
     VX_OP_ADD = 5, VX_OP_SUB = 6, VX_OP_MUL = 7, VX_OP_ADDK = 8, VX_OP_MULK = 9, VX_OP_RSUBK = 10,
-    VX_OP_SUBK = 11, VX_OP_EMIT = 12, VX_OP_BEGINGATE = 13, VX_OP_ENDGATE = 14
+    VX_OP_SUBK = 11, VX_OP_EMIT = 12, VX_OP_BEGINGATE = 13, VX_OP_ENDGATE = 14, VX_OP_NOP = 15,
+    /* Poseidon super-instructions (PoseidonGate dominates every plonky2 circuit; these run the library's native
+     * Poseidon layers on interpreter registers).  SBOX7: dst = a^7.  The 12-register forms are followed by four operand
+     * words: bytes 0-7 of word 1 and 0-3 of word 2 are the source registers, words 3-4 likewise the destinations
+     * (all sources are read before any destination is written).
+     *   MDS12K   dst = MDS * src + RC[imm]       (imm = round whose constants are added, 30 = none)
+     *   DENSE12  dst = D * src + e               (MDS of full round 3 merged with the partial rounds' first matrix)
+     *   PARTIAL12 src = (y, s1..s11), x0 = y + k[imm]:  dst = (25 x0 + sum v[imm][i] s_i,  s_i + w[imm][i] x0)
+     * with D, e, k, v, w the tables of vx_poseidon_fast_tables. */
+    VX_OP_SBOX7 = 16, VX_OP_MDS12K = 17, VX_OP_DENSE12 = 18, VX_OP_PARTIAL12 = 19,
+    /* RANGE4: dst = a (a-1)(a-2)(a-3)  (2-bit limb checks of the U32 gates);  MADK: dst = a * imm64 + b (Horner steps) */
+    VX_OP_RANGE4 = 20, VX_OP_MADK = 21
 };
 #define VX_PROGRAM_REGS 64
 typedef struct vx_circuit_desc {
@@ -187,6 +206,9 @@ void vx_tree_free(vx_tree* t);
 int32_t vx_poseidon_permute(vx_ctx* ctx, const uint64_t* states_in, uint64_t count, uint64_t* states_out);
 /* hash_n_to_hash_no_pad of `count` inputs of `len` elements each (row-major) -> count x 4 */
 int32_t vx_hash_no_pad(vx_ctx* ctx, const uint64_t* inputs, uint64_t count, uint32_t len, uint64_t* out);
+/* ONE permutation on the HOST (scalar C, spec round structure): the duplex step of plonky2's Challenger
+ * (iop/challenger.rs), which north_star keeps on the host.  Not a fallback for the device kernels: no batch form. */
+int32_t vx_challenger_permute(uint64_t state[12]);
 /* the 360 round constants the device uses (for audit against the reference table) */
 int32_t vx_poseidon_constants(uint64_t out[360]);
 /* the derived "fast partial round" tables (same refactoring as plonky2's FAST_PARTIAL_*): dense 12x12

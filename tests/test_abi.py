@@ -50,3 +50,29 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src, f
+
+
+def test_host_challenger_matches_oracle():
+    """The host-side duplex sponge (vx_challenger_permute: plain C, no GPU) against the oracle and the reference KAT
+    (contracts/lib/succinctx/plonky2x/core/src/frontend/hash/poseidon/poseidon256.rs:163-202)."""
+    import numpy as np
+    import oracle
+    from oracle import pyref
+    from vectorx_b200.challenger import Challenger, hash_no_pad_host, poseidon_host
+    assert [hex(x) for x in poseidon_host([0] * 12)[:4]] == ["0x3c18a9786cb0b359", "0xc4055e3364a246c3",
+                                                             "0x7953db0ab48808f4", "0xc71603f33a1144ca"]
+    for seed in range(4):
+        st = oracle.random_field((12,), seed=seed)
+        assert np.array_equal(np.array(poseidon_host(st.tolist()), dtype=np.uint64), oracle.poseidon(st))
+    assert poseidon_host([2**64 - 1] * 12) == poseidon_host([(2**64 - 1) % 0xFFFFFFFF00000001] * 12)   # any representative
+    inputs, out, got, exp = pyref.kat_poseidon256()
+    assert hash_no_pad_host(inputs) == out
+    for ln in (0, 1, 7, 8, 9, 135):
+        xs = oracle.random_field((ln,), seed=100 + ln).tolist() if ln else []
+        want = [int(x) for x in oracle.hash_no_pad(xs)] if ln else [0, 0, 0, 0]
+        assert hash_no_pad_host(xs) == want
+    a, b = Challenger(), pyref.Challenger() if hasattr(pyref, "Challenger") else None
+    if b is not None:
+        for x in range(1, 20):
+            a.observe_element(x); b.observe_element(x)
+        assert a.get_n_challenges(5) == b.get_n_challenges(5)

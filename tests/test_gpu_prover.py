@@ -52,8 +52,15 @@ def test_zs_partial_products(case, ctx):
     assert (out[:2, 0] == 1).all()
 
 
-def test_quotient_polys(case, ctx):
+@pytest.mark.parametrize("superops", [True, False])
+def test_quotient_polys(case, ctx, superops):
+    """compute_quotient_polys bit-for-bit, with the gate program in both forms: native Poseidon / RANGE4 / MADK
+    super-instructions (default) and scalar field operations only."""
     circ, wires, pis, proof, tr, pc = case
+    if not superops:
+        pc = vx.CircuitData(circ.d, [g.id() for g in circ.gates], circ.selector_index, circ.groups, circ.constants,
+                            circ.sigmas, ctx=ctx, superops=False)
+        assert len(pc.program) > 2 * len(case[5].program)
     rate, cap = pc.rate_bits, pc.cap_height
     wb = vx.PolynomialBatch.from_values(wires, rate, False, cap, ctx=ctx)
     zb = vx.PolynomialBatch.from_values(tr["zpp"], rate, False, cap, ctx=ctx)

@@ -27,6 +27,9 @@ SIGNATURES = {
     "vx_ctx_stream": (vp, [vp]),
     "vx_ctx_launch_count": (c_u64, [vp]),
     "vx_ctx_phase_ms": (c_i32, [vp, ctypes.POINTER(ctypes.c_float)]),
+    "vx_dev_alloc": (c_i32, [vp, ctypes.c_size_t, ctypes.POINTER(vp)]),
+    "vx_dev_free": (None, [vp, vp]),
+    "vx_dev_copy": (c_i32, [vp, vp, vp, ctypes.c_size_t]),
     "vx_commit_from_coeffs_shard": (c_i32, [vp, vp, c_u32, c_u32, c_u32, c_u32, c_u32, c_u32, ctypes.POINTER(vp)]),
     "vx_batch_shard": (c_i32, [vp, u64p]),
     "vx_commit_from_values": (c_i32, [vp, vp, c_u32, c_u32, c_u32, c_u32, ctypes.POINTER(vp)]),
@@ -48,6 +51,7 @@ SIGNATURES = {
     "vx_tree_free": (None, [vp]),
     "vx_poseidon_permute": (c_i32, [vp, vp, c_u64, vp]),
     "vx_hash_no_pad": (c_i32, [vp, vp, c_u64, c_u32, vp]),
+    "vx_challenger_permute": (c_i32, [vp]),
     "vx_poseidon_constants": (c_i32, [vp]),
     "vx_poseidon_fast_tables": (c_i32, [vp, vp, vp, vp, vp]),
     "vx_zs_partial_products": (c_i32, [vp, vp, vp, vp, vp, vp, vp]),
@@ -155,3 +159,68 @@ def default_context(device: int = 0) -> Context:
     if device not in _default_ctx:
         _default_ctx[device] = Context(device)
     return _default_ctx[device]
+
+
+class DeviceArray:
+    """A (rows, cols) u64 matrix in device memory owned by the library (vx_dev_alloc): what the prover keeps on the GPU
+    between phases.  Accepted wherever the binding takes an array (it exposes .shape and data_ptr())."""
+
+    def __init__(self, ctx: Context, shape, _ptr=None, _owner=None):
+        self.ctx, self.shape = ctx, tuple(int(x) for x in shape)
+        self._owner = _owner
+        if _ptr is None:
+            h = vp()
+            check(load().vx_dev_alloc(ctx.handle, self.nbytes, ctypes.byref(h)), "vx_dev_alloc")
+            self._p = h.value
+        else:
+            self._p = _ptr
+
+    @property
+    def nbytes(self) -> int:
+        n = 8
+        for d in self.shape:
+            n *= d
+        return n
+
+    @classmethod
+    def from_host(cls, ctx: Context, a: np.ndarray) -> "DeviceArray":
+        a = np.ascontiguousarray(a, dtype=np.uint64)
+        d = cls(ctx, a.shape)
+        check(load().vx_dev_copy(ctx.handle, d._p, a.ctypes.data, a.nbytes), "vx_dev_copy")
+        return d
+
+    def to_host(self) -> np.ndarray:
+        out = np.zeros(self.shape, dtype=np.uint64)
+        check(load().vx_dev_copy(self.ctx.handle, out.ctypes.data, self._p, out.nbytes), "vx_dev_copy")
+        return out
+
+    def rows(self, first: int, count: int) -> "DeviceArray":
+        """borrowed view of rows [first, first + count)"""
+        stride = self.nbytes // self.shape[0]
+        return DeviceArray(self.ctx, (count,) + self.shape[1:], _ptr=self._p + first * stride, _owner=self)
+
+    def reshape(self, *shape) -> "DeviceArray":
+        v = DeviceArray(self.ctx, shape, _ptr=self._p, _owner=self)
+        assert v.nbytes == self.nbytes
+        return v
+
+    # duck-typing for ptr()
+    def data_ptr(self) -> int:
+        return self._p
+
+    def is_contiguous(self) -> bool:
+        return True
+
+    def element_size(self) -> int:
+        return 8
+
+    def close(self):
+        if self._p and self._owner is None:
+            load().vx_dev_free(self.ctx.handle, self._p)
+        self._p = 0
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

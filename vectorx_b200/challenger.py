@@ -1,30 +1,21 @@
 """Host-side Fiat-Shamir challenger (plonky2 iop/challenger.rs `Challenger<F, PoseidonHash>`).
 
 north_star keeps the challenger on the host: it absorbs a few hundred elements per proof.  The duplex
-sponge needs a scalar Poseidon permutation, implemented here with Python integers from the library's
-own round constants (vx_poseidon_constants)."""
+sponge needs a scalar Poseidon permutation: the library's host-side vx_challenger_permute."""
 from __future__ import annotations
 
-from .plonky2 import poseidon_round_constants
+import ctypes
+
+from ._lib import check, load
 
 P = 0xFFFFFFFF00000001
-_CIRC = [17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20]
-_RC = None
 
 
 def poseidon_host(state):
-    global _RC
-    if _RC is None:
-        _RC = [int(x) for x in poseidon_round_constants()]
-    s = [int(x) % P for x in state]
-    for r in range(30):
-        s = [(s[i] + _RC[12 * r + i]) % P for i in range(12)]
-        if r < 4 or r >= 26:
-            s = [pow(x, 7, P) for x in s]
-        else:
-            s[0] = pow(s[0], 7, P)
-        s = [(sum(s[(i + j) % 12] * _CIRC[i] for i in range(12)) + (8 * s[0] if j == 0 else 0)) % P for j in range(12)]
-    return s
+    """One scalar permutation on the host (vx_challenger_permute: plain C inside the library, no GPU involved)."""
+    buf = (ctypes.c_uint64 * 12)(*[int(x) % P for x in state])
+    check(load().vx_challenger_permute(buf), "vx_challenger_permute")
+    return [int(x) for x in buf]
 
 
 def hash_no_pad_host(inputs):

@@ -80,6 +80,7 @@ extern "C" int32_t vx_ctx_create(int32_t device, vx_ctx** out) {
     int32_t r = poseidon_module_init(ctx);
     if (r == VX_OK) r = ntt_module_init(ctx);
     if (r == VX_OK) r = fri_module_init(ctx);
+    if (r == VX_OK) r = prover_module_init(ctx);
     if (r != VX_OK) { vx_ctx_destroy(ctx); return r; }
     *out = ctx;
     return VX_OK;
@@ -115,6 +116,35 @@ extern "C" int32_t vx_ctx_phase_ms(vx_ctx* ctx, float out[VX_NUM_PHASE_EVENTS - 
 }
 extern "C" void* vx_ctx_stream(vx_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 extern "C" uint64_t vx_ctx_launch_count(vx_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
+
+extern "C" int32_t vx_dev_alloc(vx_ctx* ctx, size_t bytes, uint64_t** out) {
+    VX_REQUIRE(ctx && out, "vx_dev_alloc: NULL argument");
+    *out = nullptr;
+    CtxGuard g(ctx);
+    void* p = nullptr;
+    cudaError_t e = cudaMallocAsync(&p, bytes ? bytes : 8, ctx->stream);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        vx_set_error("vx_dev_alloc: %zu bytes: %s", bytes, cudaGetErrorString(e));
+        return VX_ENOMEM;
+    }
+    VX_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out = (uint64_t*)p;
+    return VX_OK;
+}
+extern "C" void vx_dev_free(vx_ctx* ctx, uint64_t* p) {
+    if (!ctx || !p) return;
+    CtxGuard g(ctx);
+    cudaFreeAsync(p, ctx->stream);
+}
+extern "C" int32_t vx_dev_copy(vx_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    VX_REQUIRE(ctx && (bytes == 0 || (dst && src)), "vx_dev_copy: NULL argument");
+    if (bytes == 0) return VX_OK;
+    CtxGuard g(ctx);
+    VX_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, ctx->stream));
+    VX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VX_OK;
+}
 
 #define EV(ctx, i) VX_CUDA(cudaEventRecord((ctx)->ev[i], (ctx)->stream))
 
@@ -414,6 +444,38 @@ extern "C" int32_t vx_hash_no_pad(vx_ctx* ctx, const uint64_t* in, uint64_t coun
     VX_CHECK(hash_no_pad_device(ctx, a.p, count, len, b.p));
     VX_CHECK(copy_out(ctx, (u64*)out, b.p, b.bytes));
     VX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VX_OK;
+}
+
+// host-side scalar permutation for the Fiat-Shamir challenger (spec form: add constants, x^7, MDS)
+extern "C" int32_t vx_challenger_permute(uint64_t state[12]) {
+    if (!state) { vx_set_error("vx_challenger_permute: NULL"); return VX_EINVAL; }
+    static u64 rc[360];
+    static std::once_flag once;
+    std::call_once(once, [] { poseidon_round_constants_host(rc); });
+    static const u64 CIRC[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+    u64 s[12];
+    for (int i = 0; i < 12; i++) s[i] = state[i] % GL_P;
+    for (int r = 0; r < 30; r++) {
+        const bool full = r < 4 || r >= 26;
+        for (int i = 0; i < 12; i++) {
+            u64 x = s[i] + rc[12 * r + i];
+            if (x < s[i] || x >= GL_P) x -= GL_P;
+            if (full || i == 0) {
+                u64 x2 = gl_mul_slow(x, x), x4 = gl_mul_slow(x2, x2), x3 = gl_mul_slow(x2, x);
+                x = gl_mul_slow(x3, x4);
+            }
+            s[i] = x;
+        }
+        u64 t[12];
+        for (int j = 0; j < 12; j++) {
+            unsigned __int128 acc = (j == 0) ? (unsigned __int128)8 * s[0] : 0;
+            for (int i = 0; i < 12; i++) acc += (unsigned __int128)s[(i + j) % 12] * CIRC[i];
+            t[j] = (u64)(acc % GL_P);
+        }
+        memcpy(s, t, sizeof s);
+    }
+    memcpy(state, s, sizeof s);
     return VX_OK;
 }
 

@@ -170,6 +170,7 @@ int32_t hash_no_pad_device(vx_ctx* ctx, const u64* in, uint64_t count, uint32_t 
 
 // ntt.cu ------------------------------------------------------------------------------------------
 int32_t ntt_module_init(vx_ctx* ctx);
+int32_t prover_module_init(vx_ctx* ctx);                   // prover.cu: its own copy of the Poseidon tables
 int32_t fri_module_init(vx_ctx* ctx);                      // fri.cu: its own copy of the Poseidon tables
 void ntt_module_destroy(vx_ctx* ctx);
 // In-place forward DIF NTT of `count` contiguous transforms of size 2^log_n starting at data

@@ -12,8 +12,19 @@
 // [VX_PROGRAM_REGS][blockDim] shared-memory array; instruction words are warp-uniform loads.
 // Constraint terms are alpha-reduced with lazy 128-bit dot products (one reduction per challenge).
 #include "common.cuh"
+#include "poseidon.cuh"      // this TU's copy of the Poseidon tables: the interpreter's super-instructions run native layers
 
-#define QBLOCK 128
+#define QBLOCK 128           // == POSEIDON_BLOCK (the dense layer's scratch is sized for it)
+#define QCHUNK 1024          // program words staged in shared memory at a time; no instruction straddles a chunk
+
+int32_t prover_module_init(vx_ctx* ctx) {
+    u64 rc[360];
+    poseidon_round_constants_host(rc);
+    PoseidonTables t;
+    if (!poseidon_derive_tables(rc, &t)) { vx_set_error("poseidon: table derivation failed"); return VX_ECUDA; }
+    VX_CUDA(poseidon_upload_constants(t, ctx->stream));
+    return VX_OK;
+}
 
 struct QuotParams {
     const u64 *cs, *wires, *zpp;       // LDE column-major, leaf order, stride N
@@ -21,6 +32,8 @@ struct QuotParams {
     uint32_t bits, rate_bits, degree_bits;
     uint32_t num_wires, num_routed, num_constants, num_selectors, num_challenges, num_pp, max_degree;
     const u64* program;
+    uint32_t program_len;              // padded to a multiple of QCHUNK
+    uint32_t num_regs;                 // registers the program uses (shared-memory register file rows)
     const u64* beta_k;                 // [challenge][routed]  beta_k * k_j
     const u64* apow;                   // [challenge][num_terms] alpha_k^j
     uint32_t num_terms, num_perm_terms;
@@ -33,12 +46,18 @@ struct QuotParams {
     TwiddleView tw;
 };
 
+// 12 register numbers from two operand words
+#define QREGS12(w0, w1, k) (((k) < 8 ? (uint32_t)((w0) >> (8 * (k))) : (uint32_t)((w1) >> (8 * ((k) - 8)))) & 0xffu)
+
 __global__ void __launch_bounds__(QBLOCK) quotient_kernel(const QuotParams p) {
-    extern __shared__ u64 regfile[];
-    u64* R = regfile + threadIdx.x;
+    extern __shared__ u64 qsmem[];
+    u64* prog_s = qsmem;                                   // [QCHUNK]
+    u64* scratch = qsmem + QCHUNK + threadIdx.x;           // [12][QBLOCK] column of this thread (dense layer)
+    u64* R = qsmem + QCHUNK + 12 * QBLOCK + threadIdx.x;   // [num_regs][QBLOCK] register file column
 #define REG(i) R[(i) * QBLOCK]
-    const uint64_t j = (uint64_t)blockIdx.x * QBLOCK + threadIdx.x;
-    if (j >= p.N) return;
+    const uint64_t j_raw = (uint64_t)blockIdx.x * QBLOCK + threadIdx.x;
+    const bool live = j_raw < p.N;
+    const uint64_t j = live ? j_raw : p.N - 1;             // idle threads shadow the last point (they take part in barriers)
     const uint64_t N = p.N;
     const uint32_t i = (uint32_t)bitrev_u64(j, p.bits);                 // natural LDE index
     const u64 x = gl_mul_cc(GL_GENERATOR, tw_pow_view(p.tw, i << (32 - p.bits)));
@@ -85,50 +104,95 @@ __global__ void __launch_bounds__(QBLOCK) quotient_kernel(const QuotParams p) {
         }
     }
 
-    // ---- gate constraints: bytecode interpreter
-    const u64* pc = p.program;
+    // ---- gate constraints: bytecode interpreter.  The program is the same for every thread: the block stages it through
+    // shared memory QCHUNK words at a time, so an instruction fetch is a broadcast LDS instead of a dependent global load.
     GlAcc h[2];
     uint32_t cidx = 0;
-    for (;;) {
-        const u64 ins = __ldg(pc++);
-        const uint32_t op = (uint32_t)ins & 0xff, dst = (uint32_t)(ins >> 8) & 0xff;
-        const uint32_t ra = (uint32_t)(ins >> 16) & 0xff, rb = (uint32_t)(ins >> 24) & 0xff;
-        const uint32_t imm = (uint32_t)(ins >> 32);
-        if (op == VX_OP_END) break;
-        switch (op) {
-            case VX_OP_LOADW: REG(dst) = p.wires[(uint64_t)imm * N + j]; break;
-            case VX_OP_LOADC: REG(dst) = p.cs[(uint64_t)imm * N + j]; break;
-            case VX_OP_LOADPI: REG(dst) = p.pi_hash[imm & 3]; break;
-            case VX_OP_LOADK: REG(dst) = __ldg(pc++); break;
-            case VX_OP_ADD: REG(dst) = gl_add(REG(ra), REG(rb)); break;
-            case VX_OP_SUB: REG(dst) = gl_sub(REG(ra), REG(rb)); break;
-            case VX_OP_MUL: REG(dst) = gl_mul_cc(REG(ra), REG(rb)); break;
-            case VX_OP_ADDK: REG(dst) = gl_add(REG(ra), __ldg(pc++)); break;
-            case VX_OP_MULK: REG(dst) = gl_mul_cc(REG(ra), __ldg(pc++)); break;
-            case VX_OP_RSUBK: REG(dst) = gl_sub(__ldg(pc++), REG(ra)); break;
-            case VX_OP_SUBK: REG(dst) = gl_sub(REG(ra), __ldg(pc++)); break;
-            case VX_OP_BEGINGATE:
-                gl_acc_init(h[0], 0); gl_acc_init(h[1], 0);
-                cidx = p.num_perm_terms;
-                break;
-            case VX_OP_EMIT: {
-                u64 v = REG(ra);
-                gl_acc_mad(h[0], v, __ldg(apow0 + cidx));
-                if (nch > 1) gl_acc_mad(h[1], v, __ldg(apow1 + cidx));
-                cidx++;
-                break;
+    bool done = false;
+    for (uint32_t base = 0; base < p.program_len && !done; base += QCHUNK) {
+        __syncthreads();
+        for (uint32_t t = threadIdx.x; t < QCHUNK; t += QBLOCK) prog_s[t] = __ldg(p.program + base + t);
+        __syncthreads();
+        uint32_t pc = 0;
+        while (pc < QCHUNK) {
+            const u64 ins = prog_s[pc++];
+            const uint32_t op = (uint32_t)ins & 0xff, dst = (uint32_t)(ins >> 8) & 0xff;
+            const uint32_t ra = (uint32_t)(ins >> 16) & 0xff, rb = (uint32_t)(ins >> 24) & 0xff;
+            const uint32_t imm = (uint32_t)(ins >> 32);
+            if (op == VX_OP_END) { done = true; break; }
+            switch (op) {
+                case VX_OP_LOADW: REG(dst) = p.wires[(uint64_t)imm * N + j]; break;
+                case VX_OP_LOADC: REG(dst) = p.cs[(uint64_t)imm * N + j]; break;
+                case VX_OP_LOADPI: REG(dst) = p.pi_hash[imm & 3]; break;
+                case VX_OP_LOADK: REG(dst) = prog_s[pc++]; break;
+                case VX_OP_ADD: REG(dst) = gl_add(REG(ra), REG(rb)); break;
+                case VX_OP_SUB: REG(dst) = gl_sub(REG(ra), REG(rb)); break;
+                case VX_OP_MUL: REG(dst) = gl_mul_cc(REG(ra), REG(rb)); break;
+                case VX_OP_ADDK: REG(dst) = gl_add(REG(ra), prog_s[pc++]); break;
+                case VX_OP_MULK: REG(dst) = gl_mul_cc(REG(ra), prog_s[pc++]); break;
+                case VX_OP_RSUBK: REG(dst) = gl_sub(prog_s[pc++], REG(ra)); break;
+                case VX_OP_SUBK: REG(dst) = gl_sub(REG(ra), prog_s[pc++]); break;
+                case VX_OP_MADK: REG(dst) = gl_mul_add_cc(REG(ra), prog_s[pc++], REG(rb)); break;
+                case VX_OP_SBOX7: REG(dst) = gl_pow7_cc(REG(ra)); break;
+                case VX_OP_RANGE4: {
+                    const u64 a = gl_canon(REG(ra));
+                    const u64 t01 = gl_mul_cc(a, gl_sub(a, 1));
+                    REG(dst) = gl_mul_cc(t01, gl_mul_cc(gl_sub(a, 2), gl_sub(a, 3)));
+                    break;
+                }
+                case VX_OP_MDS12K:
+                case VX_OP_DENSE12:
+                case VX_OP_PARTIAL12: {
+                    const u64 s0 = prog_s[pc], s1 = prog_s[pc + 1], d0 = prog_s[pc + 2], d1 = prog_s[pc + 3];
+                    pc += 4;
+                    u64 st[12];
+#pragma unroll
+                    for (int k = 0; k < 12; k++) st[k] = REG(QREGS12(s0, s1, k));
+                    if (op == VX_OP_MDS12K) {
+                        poseidon_mds_add_freq(st, c_pos.rc22 + 36 * imm);
+                    } else if (op == VX_OP_DENSE12) {
+                        poseidon_dense_layer(st, scratch);
+                    } else {
+                        const u64* v = c_pos.pv + 11 * imm;
+                        const u64* w = c_pos.pw + 11 * imm;
+                        const u64 x0 = gl_add_canon(st[0], c_pos.pk[imm]);
+                        GlAcc d;
+                        gl_acc_init(d, 0);
+                        gl_acc_mad_small(d, x0, 25u);
+#pragma unroll
+                        for (int k = 1; k < 12; k++) gl_acc_mad(d, v[k - 1], st[k]);
+#pragma unroll
+                        for (int k = 1; k < 12; k++) st[k] = gl_mul_add_cc(w[k - 1], x0, st[k]);
+                        st[0] = gl_acc_reduce(d);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 12; k++) REG(QREGS12(d0, d1, k)) = st[k];
+                    break;
+                }
+                case VX_OP_BEGINGATE:
+                    gl_acc_init(h[0], 0); gl_acc_init(h[1], 0);
+                    cidx = p.num_perm_terms;
+                    break;
+                case VX_OP_EMIT: {
+                    u64 v = REG(ra);
+                    gl_acc_mad(h[0], v, __ldg(apow0 + cidx));
+                    if (nch > 1) gl_acc_mad(h[1], v, __ldg(apow1 + cidx));
+                    cidx++;
+                    break;
+                }
+                case VX_OP_ENDGATE: {
+                    u64 f = (ra == 255) ? 1 : REG(ra);
+                    gl_acc_mad(tot[0], f, gl_acc_reduce(h[0]));
+                    if (nch > 1) gl_acc_mad(tot[1], f, gl_acc_reduce(h[1]));
+                    break;
+                }
+                default: break;                     // VX_OP_NOP
             }
-            case VX_OP_ENDGATE: {
-                u64 f = (ra == 255) ? 1 : REG(ra);
-                gl_acc_mad(tot[0], f, gl_acc_reduce(h[0]));
-                if (nch > 1) gl_acc_mad(tot[1], f, gl_acc_reduce(h[1]));
-                break;
-            }
-            default: break;
         }
     }
     const u64 zi = p.zh_inv[coset];
-    for (uint32_t k = 0; k < nch; k++) p.out[(uint64_t)k * N + j] = gl_canon(gl_mul_cc(gl_acc_reduce(tot[k]), zi));
+    if (live)
+        for (uint32_t k = 0; k < nch; k++) p.out[(uint64_t)k * N + j] = gl_canon(gl_mul_cc(gl_acc_reduce(tot[k]), zi));
 #undef REG
 #undef ADD_TERM
 }
@@ -170,13 +234,44 @@ extern "C" int32_t vx_quotient(vx_ctx* ctx, const vx_circuit_desc* d, vx_batch* 
     DevBuf d_apow, d_betak, d_prog, d_q, d_qnat;
     VX_CHECK(d_apow.alloc(h_apow.size() * 8, ctx->stream));
     VX_CHECK(d_betak.alloc(h_betak.size() * 8, ctx->stream));
-    VX_CHECK(d_prog.alloc((d->program_len + 1) * 8, ctx->stream));
     VX_CHECK(d_q.alloc((size_t)nch * N * 8, ctx->stream));
     VX_CHECK(d_qnat.alloc((size_t)nch * N * 8, ctx->stream));
     VX_CUDA(cudaMemcpyAsync(d_apow.p, h_apow.data(), h_apow.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
     VX_CUDA(cudaMemcpyAsync(d_betak.p, h_betak.data(), h_betak.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-    std::vector<u64> prog(d->program, d->program + d->program_len);
+    // re-lay the program so that no instruction straddles a QCHUNK boundary (pad with NOPs), find the register count
+    std::vector<u64> prog;
+    prog.reserve(d->program_len + 2 * QCHUNK);
+    uint32_t max_reg = 0;
+    auto oplen = [](uint32_t op) -> uint32_t {
+        switch (op) {
+            case VX_OP_LOADK: case VX_OP_ADDK: case VX_OP_MULK: case VX_OP_RSUBK: case VX_OP_SUBK: case VX_OP_MADK: return 2;
+            case VX_OP_MDS12K: case VX_OP_DENSE12: case VX_OP_PARTIAL12: return 5;
+            default: return 1;
+        }
+    };
+    for (uint64_t pc = 0; pc < d->program_len;) {
+        const u64 ins = d->program[pc];
+        const uint32_t op = (uint32_t)ins & 0xff, len = oplen(op);
+        VX_REQUIRE(op <= VX_OP_MADK && pc + len <= d->program_len, "vx_quotient: malformed program at word %llu",
+                   (unsigned long long)pc);
+        while (prog.size() % QCHUNK + len > QCHUNK) prog.push_back(VX_OP_NOP);
+        for (uint32_t k = 0; k < len; k++) prog.push_back(d->program[pc + k]);
+        if (len == 5) {
+            for (uint32_t w = 1; w < 5; w++)
+                for (int k = 0; k < ((w & 1) ? 8 : 4); k++)
+                    max_reg = std::max(max_reg, (uint32_t)((d->program[pc + w] >> (8 * k)) & 0xff));
+        } else if (op != VX_OP_BEGINGATE && op != VX_OP_NOP && op != VX_OP_END) {
+            const uint32_t dst = (uint32_t)(ins >> 8) & 0xff, ra = (uint32_t)(ins >> 16) & 0xff, rb = (uint32_t)(ins >> 24) & 0xff;
+            max_reg = std::max(max_reg, dst);
+            if (!(op == VX_OP_ENDGATE && ra == 255)) max_reg = std::max(max_reg, ra);
+            max_reg = std::max(max_reg, rb);
+        }
+        pc += len;
+    }
+    VX_REQUIRE(max_reg < VX_PROGRAM_REGS, "vx_quotient: program uses register %u (limit %d)", max_reg, VX_PROGRAM_REGS);
     prog.push_back(VX_OP_END);
+    while (prog.size() % QCHUNK) prog.push_back(VX_OP_END);
+    VX_CHECK(d_prog.alloc(prog.size() * 8, ctx->stream));
     VX_CUDA(cudaMemcpyAsync(d_prog.p, prog.data(), prog.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
 
     QuotParams p;
@@ -186,7 +281,8 @@ extern "C" int32_t vx_quotient(vx_ctx* ctx, const vx_circuit_desc* d, vx_batch* 
     p.num_wires = d->num_wires; p.num_routed = d->num_routed_wires; p.num_constants = d->num_constants;
     p.num_selectors = d->num_selectors; p.num_challenges = nch; p.num_pp = d->num_partial_products;
     p.max_degree = d->max_degree;
-    p.program = d_prog.p; p.beta_k = d_betak.p; p.apow = d_apow.p;
+    p.program = d_prog.p; p.program_len = (uint32_t)prog.size(); p.num_regs = max_reg + 1;
+    p.beta_k = d_betak.p; p.apow = d_apow.p;
     p.num_terms = num_terms; p.num_perm_terms = perm_terms;
     for (uint32_t k = 0; k < nch; k++) { p.betas[k] = betas[k] % GL_P; p.gammas[k] = gammas[k] % GL_P; }
     for (int t = 0; t < 4; t++) p.pi_hash[t] = pi_hash[t] % GL_P;
@@ -203,7 +299,7 @@ extern "C" int32_t vx_quotient(vx_ctx* ctx, const vx_circuit_desc* d, vx_batch* 
     p.n_inv = gl_inv_host(n % GL_P);
     p.out = d_q.p;
     p.tw.lo = ctx->w_lo; p.tw.hi = ctx->w_hi; p.tw.roots12 = ctx->roots12; p.tw.full12 = ctx->roots12f;
-    size_t smem = (size_t)VX_PROGRAM_REGS * QBLOCK * sizeof(u64);
+    size_t smem = ((size_t)QCHUNK + (size_t)(12 + p.num_regs) * QBLOCK) * sizeof(u64);
     VX_CUDA(cudaFuncSetAttribute(quotient_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     quotient_kernel<<<(unsigned)((N + QBLOCK - 1) / QBLOCK), QBLOCK, smem, ctx->stream>>>(p);
     VX_LAUNCH_COUNT(ctx, 1);

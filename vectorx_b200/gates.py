@@ -19,7 +19,8 @@ from ._lib import check, load, ptr
 
 P = 0xFFFFFFFF00000001
 OP = dict(END=0, LOADW=1, LOADC=2, LOADPI=3, LOADK=4, ADD=5, SUB=6, MUL=7, ADDK=8, MULK=9, RSUBK=10, SUBK=11,
-          EMIT=12, BEGINGATE=13, ENDGATE=14)
+          EMIT=12, BEGINGATE=13, ENDGATE=14, NOP=15, SBOX7=16, MDS12K=17, DENSE12=18, PARTIAL12=19, RANGE4=20, MADK=21)
+MULTI = ("MDS12K", "DENSE12", "PARTIAL12")        # 12 registers in, 12 registers out
 NUM_REGS = 64
 MDS_CIRC = [17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20]
 MDS_DIAG0 = 8
@@ -47,6 +48,20 @@ class Trace:
 
     def konst(self, k):
         return self.new("LOADK", imm=k % P)
+
+    def multi(self, op, srcs, imm=0):
+        """12-in / 12-out super-instruction: returns the 12 result values."""
+        srcs = [_val(x) for x in srcs]
+        assert op in MULTI and len(srcs) == 12 and all(isinstance(x, Sym) for x in srcs)
+        self.ops.append((op, tuple(x.id for x in srcs), 12, imm))
+        base = len(self.ops)
+        for k in range(12):
+            self.ops.append(("RES", base - 1, k, None))
+        return [Sym(self, base + k) for k in range(12)]
+
+    def sbox7(self, x):
+        x = _val(x)
+        return self.new("SBOX7", x.id)
 
     def emit(self, s):
         s = _val(s)
@@ -111,15 +126,28 @@ def _val(o):
 
 
 # ------------------------------------------------------------------------------------------------ gate formulas
+SUPEROPS = True          # set by build_program: RANGE4 / MADK / Poseidon super-instructions vs scalar operations only
+
+
+def _madk(acc, k, l):
+    """acc * k + l"""
+    acc, l = _val(acc), _val(l)
+    if SUPEROPS and isinstance(acc, Sym) and isinstance(l, Sym):
+        return acc.t.new("MADK", acc.id, l.id, int(k) % P)
+    return acc * k + l
+
+
 def _horner(limbs, base):
     acc = limbs[-1]
     for l in reversed(limbs[:-1]):
-        acc = acc * base + l
+        acc = _madk(acc, base, l)
     return acc
 
 
 def _range4(x):
     x = _val(x)
+    if SUPEROPS:
+        return x.t.new("RANGE4", x.id)
     return x * (x - 1) * (x - 2) * (x - 3)
 
 
@@ -166,9 +194,9 @@ def gate_u32_arithmetic(t, w, c, pi, params):
             limb = w(6 * n + 32 * i + j)
             t.emit(_range4(limb))
             if j < 16:
-                low = limb if low is None else low * 4 + limb
+                low = limb if low is None else _madk(low, 4, limb)
             else:
-                high = limb if high is None else high * 4 + limb
+                high = limb if high is None else _madk(high, 4, limb)
         t.emit(low - lo)
         t.emit(high - hi)
 
@@ -182,7 +210,7 @@ def gate_u32_subtraction(t, w, c, pi, params):
         for j in reversed(range(16)):
             limb = w(5 * n + 16 * i + j)
             t.emit(_range4(limb))
-            comb = limb if comb is None else comb * 4 + limb
+            comb = limb if comb is None else _madk(comb, 4, limb)
         t.emit(comb - res)
         b_out = _val(b_out)
         t.emit(b_out * (1 - b_out))
@@ -214,8 +242,11 @@ def poseidon_fast_tables():
 
 
 def gate_poseidon(t, w, c, pi, params):
+    """PoseidonGate constraints; with params["superops"] the layers run as the interpreter's native Poseidon
+    super-instructions, otherwise as scalar field operations (the same values either way)."""
     T = poseidon_fast_tables()
     rc = T["rc"]
+    sup = params.get("superops", True)
     swap = _val(w(24))
     t.emit(swap * (swap - 1))
     delta = [w(25 + i) for i in range(4)]
@@ -224,22 +255,27 @@ def gate_poseidon(t, w, c, pi, params):
     st = [w(i) + delta[i] for i in range(4)] + [w(i + 4) - delta[i] for i in range(4)] + [w(i) for i in range(8, 12)]
 
     def sbox(x):
+        if sup:
+            return t.sbox7(x)
         x2 = x * x
         x3 = x2 * x
         x4 = x2 * x2
         return x3 * x4
 
-    def mds(s):
+    def mds(s, next_round):
+        """MDS * s + RC[next_round] (next_round = 30: nothing added)"""
+        if sup:
+            return t.multi("MDS12K", s, next_round)
         out = []
         for r in range(12):
             acc = s[r] * (MDS_CIRC[0] + (MDS_DIAG0 if r == 0 else 0))
             for i in range(1, 12):
                 acc = acc + s[(i + r) % 12] * MDS_CIRC[i]
-            out.append(acc)
+            out.append(acc + rc[12 * next_round + r] if next_round < 30 else acc)
         return out
 
-    for r in range(4):                               # first full rounds
-        st = [st[i] + rc[12 * r + i] for i in range(12)]
+    st = [_val(st[i]) + rc[i] for i in range(12)]
+    for r in range(4):                               # first full rounds (constants of round r already added)
         if r != 0:
             for i in range(12):
                 sin = w(29 + 12 * (r - 1) + i)
@@ -247,8 +283,10 @@ def gate_poseidon(t, w, c, pi, params):
                 st[i] = sin
         st = [sbox(x) for x in st]
         if r < 3:
-            st = mds(st)
-        else:                                        # MDS layer merged with the partial rounds' initial matrix
+            st = mds(st, r + 1)
+        elif sup:                                    # MDS layer merged with the partial rounds' initial matrix
+            st = t.multi("DENSE12", st)
+        else:
             new = []
             for j in range(12):
                 acc = st[0] * T["d"][12 * j]
@@ -259,18 +297,21 @@ def gate_poseidon(t, w, c, pi, params):
     for r in range(22):                              # partial rounds, sparse form
         sin = w(65 + r)
         t.emit(st[0] - sin)
+        if sup:
+            st = t.multi("PARTIAL12", [sbox(sin)] + st[1:], r)
+            continue
         x0 = sbox(sin) + T["k"][r]
         d = x0 * 25
         for i in range(1, 12):
             d = d + st[i] * T["v"][11 * r + i - 1]
         st = [d] + [st[i] + x0 * T["w"][11 * r + i - 1] for i in range(1, 12)]
+    st = [_val(st[i]) + rc[12 * 26 + i] for i in range(12)]
     for r in range(4):                               # second full rounds
-        st = [st[i] + rc[12 * (26 + r) + i] for i in range(12)]
         for i in range(12):
             sin = w(87 + 12 * r + i)
             t.emit(st[i] - sin)
             st[i] = sin
-        st = mds([sbox(x) for x in st])
+        st = mds([sbox(x) for x in st], 27 + r if r < 3 else 30)
     for i in range(12):
         t.emit(st[i] - w(12 + i))
 
@@ -307,12 +348,22 @@ def lookup(gate_id: str):
 
 
 # ------------------------------------------------------------------------------------------------ assembler
+def _pack_regs(regs):
+    """12 register numbers -> two operand words (8 + 4 bytes)"""
+    w0 = sum(r << (8 * i) for i, r in enumerate(regs[:8]))
+    w1 = sum(r << (8 * i) for i, r in enumerate(regs[8:]))
+    return [w0, w1]
+
+
 def assemble(trace: Trace, filter_id):
     """Linear-scan register allocation of one gate's SSA trace -> (bytecode words, filter register)."""
     ops = trace.ops
     last = {}
     for idx, (op, a, b, imm) in enumerate(ops):
-        for v in (a, b):
+        if op == "RES":
+            continue
+        operands = a if isinstance(a, tuple) else (a, b)
+        for v in operands:
             if v is not None:
                 last[v] = idx
     if filter_id is not None:
@@ -325,6 +376,25 @@ def assemble(trace: Trace, filter_id):
         return OP[op] | (dst << 8) | (a << 16) | (b << 24) | ((imm & 0xFFFFFFFF) << 32)
 
     for idx, (op, a, b, imm) in enumerate(ops):
+        if op == "RES":
+            continue
+        if op in MULTI:
+            srcs = [reg[v] for v in a]
+            for v in set(a):
+                if last[v] == idx:
+                    free.append(reg[v])
+            if len(free) < 12:
+                raise RuntimeError("gate program needs more than %d registers" % NUM_REGS)
+            dsts = []
+            for k in range(12):
+                rd = free.pop()
+                reg[idx + 1 + k] = rd
+                dsts.append(rd)
+            words += [enc(op, imm=imm)] + _pack_regs(srcs) + _pack_regs(dsts)
+            for k in range(12):
+                if (idx + 1 + k) not in last:
+                    free.append(reg[idx + 1 + k])
+            continue
         ra = reg[a] if a is not None else 0
         rb = reg[b] if b is not None else 0
         for v in {a, b}:                           # operands dying here free their register first:
@@ -343,6 +413,10 @@ def assemble(trace: Trace, filter_id):
             words += [enc(op, rd), imm]
         elif op in ("ADD", "SUB", "MUL"):
             words.append(enc(op, rd, ra, rb))
+        elif op in ("SBOX7", "RANGE4"):
+            words.append(enc(op, rd, ra))
+        elif op == "MADK":
+            words += [enc(op, rd, ra, rb), imm]
         else:                                      # ADDK / MULK / RSUBK / SUBK: immediate in the next word
             words += [enc(op, rd, ra), imm]
         if idx not in last:                        # dead value
@@ -350,9 +424,13 @@ def assemble(trace: Trace, filter_id):
     return words, (reg[filter_id] if filter_id is not None else 255)
 
 
-def build_program(gate_ids: list[str], selector_index: list[int], groups: list[tuple], num_selectors: int) -> np.ndarray:
+def build_program(gate_ids: list[str], selector_index: list[int], groups: list[tuple], num_selectors: int,
+                  superops: bool = True) -> np.ndarray:
     """One program for all gates (already in plonky2's sorted order).  The gate-local constant i is column
-    num_selectors + i of the constants_sigmas batch; the filter follows compute_filter()."""
+    num_selectors + i of the constants_sigmas batch; the filter follows compute_filter().
+    superops=False emits scalar field operations only (the same constraint values; kept for A/B and parity tests)."""
+    global SUPEROPS
+    SUPEROPS = superops
     words = []
     many = num_selectors > 1
     for gi, gid in enumerate(gate_ids):
@@ -369,6 +447,7 @@ def build_program(gate_ids: list[str], selector_index: list[int], groups: list[t
 
         def pi(i, t=t):
             return Ref(lambda: t.pi(i))
+        params = dict(params, superops=superops)
         fn(t, w, c, pi, params)
         # filter = prod_{j in group, j != gi} (j - s) [* (UNUSED - s)]
         lo, hi = groups[selector_index[gi]]

@@ -12,11 +12,12 @@ The challenger and the proof assembly stay on the host.
 from __future__ import annotations
 
 import ctypes
+import time
 
 import numpy as np
 
 from . import gates as gate_lib
-from ._lib import Context, check, default_context, load, ptr, vp
+from ._lib import Context, DeviceArray, check, default_context, load, ptr, vp
 from .challenger import Challenger, hash_no_pad_host
 from .plonky2 import PolynomialBatch
 
@@ -47,7 +48,7 @@ class CircuitData:
     def __init__(self, degree_bits, gate_ids, selector_index, groups, constants, sigmas, *, num_wires=135,
                  num_routed_wires=80, rate_bits=3, cap_height=4, num_challenges=2, max_degree=8,
                  quotient_degree_factor=8, num_query_rounds=28, proof_of_work_bits=16, arity_bits=4,
-                 final_poly_bits=5, ctx: Context | None = None):
+                 final_poly_bits=5, ctx: Context | None = None, superops: bool = True):
         self.ctx = ctx or default_context()
         self.degree_bits, self.n = degree_bits, 1 << degree_bits
         self.gate_ids, self.selector_index, self.groups = list(gate_ids), list(selector_index), [tuple(g) for g in groups]
@@ -59,12 +60,14 @@ class CircuitData:
         self.arity_bits, self.final_poly_bits = arity_bits, final_poly_bits
         self.constants = np.ascontiguousarray(constants, dtype=np.uint64)
         self.sigmas = np.ascontiguousarray(sigmas, dtype=np.uint64)
+        self.sigmas_dev = DeviceArray.from_host(self.ctx, self.sigmas)      # prover-only data: resident for every proof
         self.num_constants = self.constants.shape[0]
         self.num_partial_products = (num_routed_wires + max_degree - 1) // max_degree - 1
         self.k_is = np.array([pow(GENERATOR, j, P) for j in range(num_routed_wires)], dtype=np.uint64)
         meta = [gate_lib.lookup(g) for g in self.gate_ids]
         self.num_gate_constraints = max(m[4] for m in meta)
-        self.program = gate_lib.build_program(self.gate_ids, self.selector_index, self.groups, self.num_selectors)
+        self.program = gate_lib.build_program(self.gate_ids, self.selector_index, self.groups, self.num_selectors,
+                                              superops=superops)
         # CircuitBuilder::build: constants_sigmas commitment and the circuit digest
         cs = np.concatenate([self.constants, self.sigmas])
         self.constants_sigmas_commitment = PolynomialBatch.from_values(cs, rate_bits, False, cap_height, ctx=self.ctx)
@@ -91,36 +94,56 @@ def prove(circ: CircuitData, wires: np.ndarray, public_inputs, trace: dict | Non
     """prove_with_partition_witness: wires is the (num_wires, n) witness matrix. Returns the proof as a dict."""
     lib, ctx = load(), circ.ctx
     T = trace if trace is not None else {}
+    phases = T.setdefault("phase_ms", {})       # plonky2's TimingTree scopes: every C call is blocking, so wall time is device time + launch
+    _t = [time.perf_counter()]
+
+    def lap(name):
+        now = time.perf_counter()
+        phases[name] = phases.get(name, 0.0) + (now - _t[0]) * 1e3
+        _t[0] = now
     n, d, rate, cap_h = circ.n, circ.degree_bits, circ.rate_bits, circ.cap_height
     N, bits, nch = n << rate, d + rate, circ.num_challenges
+    want_trace = trace is not None and trace.get("intermediates", True)
     wires = np.ascontiguousarray(wires, dtype=np.uint64)
     pi_hash = hash_no_pad_host(list(public_inputs))
     ch = Challenger()
     ch.observe_hash(circ.circuit_digest)
     ch.observe_hash(pi_hash)
-    wires_c = PolynomialBatch.from_values(wires, rate, False, cap_h, ctx=ctx)
+    lap("host")
+    wires_d = DeviceArray.from_host(ctx, wires)          # the witness goes to the GPU once; every later phase reads it there
+    lap("upload witness")
+    wires_c = PolynomialBatch.from_values(wires_d, rate, False, cap_h, ctx=ctx)
+    lap("commit wires")
     ch.observe_cap(wires_c.cap.hashes.tolist())
     betas = ch.get_n_challenges(nch)
     gammas = ch.get_n_challenges(nch)
-    zpp = np.zeros((nch * (1 + circ.num_partial_products), n), dtype=np.uint64)
+    zpp = DeviceArray(ctx, (nch * (1 + circ.num_partial_products), n))
     a_betas, a_gammas = _u64(betas), _u64(gammas)        # keep the arrays alive across the FFI calls
-    check(lib.vx_zs_partial_products(ctx.handle, ctypes.byref(circ.desc), ptr(wires), ptr(circ.sigmas),
+    check(lib.vx_zs_partial_products(ctx.handle, ctypes.byref(circ.desc), ptr(wires_d), ptr(circ.sigmas_dev),
                                      ptr(a_betas), ptr(a_gammas), ptr(zpp)), "vx_zs_partial_products")
+    lap("Z / partial products")
     zpp_c = PolynomialBatch.from_values(zpp, rate, False, cap_h, ctx=ctx)
+    lap("commit Z / partial products")
     ch.observe_cap(zpp_c.cap.hashes.tolist())
     alphas = ch.get_n_challenges(nch)
-    qcoeffs = np.zeros((nch, N), dtype=np.uint64)
+    qcoeffs = DeviceArray(ctx, (nch, N))
     cs_c = circ.constants_sigmas_commitment
     a_pi, a_alphas = _u64(pi_hash), _u64(alphas)
     check(lib.vx_quotient(ctx.handle, ctypes.byref(circ.desc), cs_c.handle, wires_c.handle, zpp_c.handle,
                           ptr(a_pi), ptr(a_betas), ptr(a_gammas), ptr(a_alphas), ptr(qcoeffs)), "vx_quotient")
+    lap("compute quotient polys")
     qchunks = qcoeffs.reshape(nch * circ.quotient_degree_factor, n)
     q_c = PolynomialBatch.from_coeffs(qchunks, rate, False, cap_h, ctx=ctx)
+    lap("commit quotient")
     ch.observe_cap(q_c.cap.hashes.tolist())
     zeta = ch.get_extension_challenge()
     g_n = pow(7277203076849721926, 1 << (32 - d), P)
     zeta_next = [zeta[0] * g_n % P, zeta[1] * g_n % P]
-    T.update(betas=betas, gammas=gammas, alphas=alphas, zpp=zpp, quotient_coeffs=qchunks, zeta=zeta, pi_hash=pi_hash)
+    T.update(betas=betas, gammas=gammas, alphas=alphas, zeta=zeta, pi_hash=pi_hash)
+    if want_trace:                                       # tests compare the intermediates; a proof never needs them on the host
+        T.update(zpp=zpp.to_host(), quotient_coeffs=qchunks.to_host())
+    for buf in (wires_d, zpp, qcoeffs):
+        buf.close()
 
     def ev(batch, point):
         out = np.zeros((batch.num_polys, 2), dtype=np.uint64)
@@ -133,6 +156,7 @@ def prove(circ: CircuitData, wires: np.ndarray, public_inputs, trace: dict | Non
         "wires": ev(wires_c, zeta), "plonk_zs": z_open[:nch], "partial_products": z_open[nch:],
         "quotient_polys": ev(q_c, zeta), "plonk_zs_next": ev(zpp_c, zeta_next)[:nch],
     }
+    lap("openings")
     for key in ("constants", "plonk_sigmas", "wires", "plonk_zs", "partial_products", "quotient_polys", "plonk_zs_next"):
         for e in openings[key]:
             ch.observe_extension_element(e)
@@ -150,7 +174,9 @@ def prove(circ: CircuitData, wires: np.ndarray, public_inputs, trace: dict | Non
     batches[1].ranges, batches[1].num_ranges = r1, 1
     fri = vp()
     a_alpha = _u64(alpha)
+    lap("host")
     check(lib.vx_fri_begin(ctx.handle, handles, 4, batches, 2, ptr(a_alpha), ctypes.byref(fri)), "vx_fri_begin")
+    lap("FRI batch + LDE")
     try:
         arities = circ.fri_reduction_arity_bits()
         fri_caps = []
@@ -167,10 +193,12 @@ def prove(circ: CircuitData, wires: np.ndarray, public_inputs, trace: dict | Non
         final_poly = [[int(a), int(b)] for a, b in fbuf[:flen.value]]
         for c in final_poly:
             ch.observe_extension_element(c)
+        lap("FRI fold-and-commit")
         st, pos = ch.pow_state()
         wit = ctypes.c_uint64(0)
         a_st = _u64(st)
         check(lib.vx_pow_grind(ctx.handle, ptr(a_st), pos, circ.proof_of_work_bits, ctypes.byref(wit)), "vx_pow_grind")
+        lap("FRI proof of work")
         pow_witness = int(wit.value)
         ch.observe_element(pow_witness)
         ch.get_challenge()
@@ -191,6 +219,7 @@ def prove(circ: CircuitData, wires: np.ndarray, public_inputs, trace: dict | Non
             check(lib.vx_fri_query(fri, li, ptr(a_idx), k, ptr(rows), ptr(paths)), "vx_fri_query")
             layer_rows.append(rows)
             layer_paths.append(paths[:, :depth])
+        lap("FRI queries")
     finally:
         lib.vx_fri_free(fri)
     queries = []
@@ -203,4 +232,5 @@ def prove(circ: CircuitData, wires: np.ndarray, public_inputs, trace: dict | Non
              "queries": queries, "public_inputs": list(public_inputs)}
     for b in (wires_c, zpp_c, q_c):
         b.close()
+    lap("host")
     return proof
