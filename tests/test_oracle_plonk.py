@@ -119,6 +119,27 @@ def run_program(words, wires, consts_cols, pi_hash, apow, num_perm_terms):
         elif op == OP["BEGINGATE"]: h, cidx = 0, num_perm_terms
         elif op == OP["EMIT"]: h = (h + R[ra] * apow[cidx]) % P; cidx += 1
         elif op == OP["ENDGATE"]: total = (total + (1 if ra == 255 else R[ra]) * h) % P
+        elif op == OP["NOP"]: pass
+        elif op == OP["MADK"]: R[dst] = (R[ra] * words[pc] + R[rb]) % P; pc += 1
+        elif op == OP["SBOX7"]: R[dst] = pow(R[ra], 7, P)
+        elif op == OP["RANGE4"]: R[dst] = R[ra] * (R[ra] - 1) * (R[ra] - 2) * (R[ra] - 3) % P
+        elif op in (OP["MDS12K"], OP["DENSE12"], OP["PARTIAL12"]):
+            unpack = lambda w0, w1: [(w0 >> (8 * k)) & 0xFF for k in range(8)] + [(w1 >> (8 * k)) & 0xFF for k in range(4)]
+            srcs, dsts = unpack(words[pc], words[pc + 1]), unpack(words[pc + 2], words[pc + 3])
+            pc += 4
+            st = [R[r] for r in srcs]
+            T = vgates.poseidon_fast_tables()
+            if op == OP["MDS12K"]:
+                out = [(sum(st[(i + r) % 12] * vgates.MDS_CIRC[i] for i in range(12)) + (vgates.MDS_DIAG0 * st[0] if r == 0 else 0)
+                        + (T["rc"][12 * imm + r] if imm < 30 else 0)) % P for r in range(12)]
+            elif op == OP["DENSE12"]:
+                out = [(sum(st[i] * T["d"][12 * j + i] for i in range(12)) + T["e"][j]) % P for j in range(12)]
+            else:
+                x0 = (st[0] + T["k"][imm]) % P
+                out = [(25 * x0 + sum(st[i] * T["v"][11 * imm + i - 1] for i in range(1, 12))) % P]
+                out += [(st[i] + x0 * T["w"][11 * imm + i - 1]) % P for i in range(1, 12)]
+            for r, v in zip(dsts, out):
+                R[r] = v
         else: raise AssertionError(op)
     return total
 
