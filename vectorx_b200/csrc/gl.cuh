@@ -213,6 +213,48 @@ GL_D u64 gl_pow7_cc(u64 x) {
     return gl_mul_cc(x3, x4);
 }
 
+// a + b and a - b for ANY u64 representatives, as pure carry chains (8 ALU instructions, no compare / select):
+//   a + b = s + C 2^64 = s + C eps (mod p); the fix-up itself can carry once more (only when s >= p), and then the
+//   second fix-up lands below 2 eps.  Same with borrows for the difference (-2^64 = -eps).
+GL_D u64 gl_add_cc(u64 a, u64 b) {
+    // ptxas keeps CC.CF as the HARDWARE carry (a borrow is CF = 0), so "subc m, 0, 0" after an add chain gives C - 1,
+    // not -C: one NOT turns it into the mask C eps.  (The IMAD.WIDE form c * eps + s measured slower: 1.56 vs 1.49 ms LDE.)
+    u32 r0, r1;
+    asm("{\n\t"
+        ".reg .u32 s0, s1, m;\n\t"
+        "add.cc.u32 s0, %2, %4;\n\t"
+        "addc.cc.u32 s1, %3, %5;\n\t"
+        "subc.u32 m, 0, 0;\n\t"                  // C - 1
+        "not.b32 m, m;\n\t"                      // -C = C eps (low word)
+        "add.cc.u32 s0, s0, m;\n\t"              // s += C eps, carry C2 (only when s >= p)
+        "addc.cc.u32 s1, s1, 0;\n\t"
+        "subc.u32 m, 0, 0;\n\t"
+        "not.b32 m, m;\n\t"
+        "add.cc.u32 %0, s0, m;\n\t"              // s += C2 eps: s < eps here, cannot carry
+        "addc.u32 %1, s1, 0;\n\t"
+        "}"
+        : "=r"(r0), "=r"(r1)
+        : "r"(lo32(a)), "r"(hi32(a)), "r"(lo32(b)), "r"(hi32(b)));
+    return pack64(r0, r1);
+}
+GL_D u64 gl_sub_cc(u64 a, u64 b) {
+    u32 r0, r1;
+    asm("{\n\t"
+        ".reg .u32 d0, d1, m;\n\t"
+        "sub.cc.u32 d0, %2, %4;\n\t"
+        "subc.cc.u32 d1, %3, %5;\n\t"
+        "subc.u32 m, 0, 0;\n\t"                  // m = -B
+        "sub.cc.u32 d0, d0, m;\n\t"              // d -= B eps
+        "subc.cc.u32 d1, d1, 0;\n\t"
+        "subc.u32 m, 0, 0;\n\t"
+        "sub.cc.u32 %0, d0, m;\n\t"
+        "subc.u32 %1, d1, 0;\n\t"
+        "}"
+        : "=r"(r0), "=r"(r1)
+        : "r"(lo32(a)), "r"(hi32(a)), "r"(lo32(b)), "r"(hi32(b)));
+    return pack64(r0, r1);
+}
+
 // ---- lazy dot products: sum_i a_i * b_i accumulated UNREDUCED in three column accumulators
 //   T0 += a0*b0,  T1 += a0*b1 + a1*b0,  T2 += a1*b1      (value = T0 + T1*2^32 + T2*2^64)
 // each a 64-bit IMAD.WIDE accumulator plus a carry counter, so a term costs 4 multiply-adds and 4

@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(POSEIDON_BLOCK) level_hash_kernel(u64* __restr
 // (< 12) owns state element i, the S-box layer runs in parallel and the MDS layer gathers the 12 elements with warp
 // shuffles (spec round structure: add constants, x^7, MDS; partial rounds apply x^7 on lane 0 only).  ~5x lower latency,
 // ~3x more thread-instructions: used only while a level has at most VX_COOP_MAX_PAIRS pairs.
-#define VX_COOP_MAX_PAIRS 16384
+#define VX_COOP_MAX_PAIRS 4096
 __global__ void __launch_bounds__(256) level_hash_coop_kernel(u64* __restrict__ digests, u64* __restrict__ cap, uint32_t lvl,
                                                               uint32_t sub_bits, uint64_t total_pairs) {
     constexpr u32 C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};

@@ -184,8 +184,8 @@ template <int R, int STAGE, int B, int J>
 GL_D void dft_stage_pair(u64* x) {
     constexpr int half = 1 << (R - 1 - STAGE);
     u64 u = x[B + J], v = x[B + J + half];
-    x[B + J] = gl_add(u, v);
-    x[B + J + half] = dft_twiddle<R, STAGE, J>(gl_sub(u, v));
+    x[B + J] = gl_add_cc(u, v);
+    x[B + J + half] = dft_twiddle<R, STAGE, J>(gl_sub_cc(u, v));
 }
 template <int R, int STAGE, int B, int J>
 GL_D void dft_stage_js(u64* x) {
