@@ -177,6 +177,8 @@ def main():
     ap.add_argument("--rate-bits", type=int, default=3)
     ap.add_argument("--cap-height", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: 'peer' = the library's own kernels over NVLink peer memory, 'nccl' = torch.distributed all-gather (A/B)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     w = workload_from_args(a)
@@ -231,11 +233,16 @@ def main():
     cap_all = torch.empty((1 << cap, 4), dtype=torch.int64, device=f"cuda:{local_rank}")
     cap_host = torch.empty((1 << cap, 4), dtype=torch.int64).pin_memory()
     phase_acc = {}
+    use_nccl = False
     if G > 1:
-        from vectorx_b200.sharded import DeviceEngine, ShardPlan, TorchComm, sharded_commit
+        from vectorx_b200.sharded import DeviceEngine, PeerGroup, ShardPlan, TorchComm, sharded_commit
         plan = ShardPlan(G, rank, c, log_n, rate, cap)
-        engine, comm = DeviceEngine(ctx), TorchComm(dist)
-        bufs = {"coeff_mine": coeff_mine, "coeff_all": coeff_all, "cap_loc": cap_loc, "cap_all": cap_all}
+        use_nccl = a.exchange == "nccl"
+        if use_nccl:
+            engine, comm = DeviceEngine(ctx), TorchComm(dist)
+            bufs = {"coeff_mine": coeff_mine, "coeff_all": coeff_all, "cap_loc": cap_loc, "cap_all": cap_all}
+        else:
+            group = PeerGroup(ctx, plan, dist)
 
     def one_step(src, from_host):
         """One commit. src: this rank's (cpr, n) values (host-pinned or device). Returns nothing; cap -> cap_host."""
@@ -248,6 +255,14 @@ def main():
             if from_host:
                 check(lib.vx_batch_cap(h, cap_host.data_ptr()), "vx_batch_cap")
             lib.vx_batch_free(h)
+            return
+        if not use_nccl:
+            # the library's own exchange: coefficient blocks stored into every rank's gather buffer over NVLink peer
+            # memory, flags instead of collectives (csrc/shard.cu); one blocking call per rank
+            h = group.commit_from_values(src, cap_host if from_host else cap_all)
+            for k, v in ctx.phase_ms().items():
+                phase_acc[k] = phase_acc.get(k, 0.0) + v
+            group.free_batch(h)
             return
         # column-sharded iNTT -> NCCL all-gather of coefficients -> own cosets / cap subtrees -> caps gathered
         h, _ = sharded_commit(src, plan, engine, comm, bufs)
@@ -269,7 +284,7 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         # G == 1: events on the library's stream.  G > 1: the NCCL legs run on torch's current stream and every library
         # call is blocking, so events on torch's stream bracket all device work of the region.
-        ev_stream = stream if G == 1 else torch.cuda.current_stream()
+        ev_stream = stream if (G == 1 or not use_nccl) else torch.cuda.current_stream()
         t0 = time.perf_counter()
         e0.record(ev_stream)
         for i in range(steps):
@@ -385,7 +400,7 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u64 (Goldilocks field, 32-bit IMAD limbs)", "data": "synthetic",
             "config": {"workload": workload_name(w),
-                       "parallelism": "single GPU" if G == 1 else f"coset-sharded x{G}: column-sharded iNTT + NCCL all-gather of coefficients + per-rank cosets/cap subtrees",
+                       "parallelism": "single GPU" if G == 1 else f"coset-sharded x{G}: column-sharded iNTT + " + ("NCCL all-gather of coefficients" if use_nccl else "coefficients stored into every rank's gather buffer by the library's own kernel over NVLink peer memory (flags, no NCCL on the data path)") + " + per-rank cosets/cap subtrees",
                        "l2": f"inputs rotate over {N_INPUT_SETS} sets ({N_INPUT_SETS * elems * 8 / 1e6:.0f} MB) and each step streams a {8 * N * c / 1e6:.0f} MB LDE, both > 126 MB L2",
                        "elements": "n*c input trace elements per commit"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": (1 << cap) * 32,

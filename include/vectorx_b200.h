@@ -82,6 +82,31 @@ int32_t vx_commit_from_coeffs(vx_ctx* ctx, const uint64_t* coeffs, uint32_t c, u
 int32_t vx_commit_from_coeffs_shard(vx_ctx* ctx, const uint64_t* coeffs, uint32_t c, uint32_t log_n,
                                     uint32_t rate_bits, uint32_t cap_height, uint32_t shard_index,
                                     uint32_t shard_count, vx_batch** out);
+/* The same partition with the exchange done by the library itself over NVLink peer memory (no NCCL on the data path):
+ * every rank iNTTs its slice of the value columns, stores the coefficients into every rank's gather buffer with its
+ * own kernel (release flag per rank, system scope), waits for all peers' flags, then extends and hashes its own
+ * cosets / cap subtrees and pushes its cap entries to every rank the same way.  A group owns this rank's buffers:
+ *   vx_shard_group_create     one per rank (rank r of `world`, same shape everywhere);
+ *   vx_shard_group_ipc_handle + vx_shard_group_connect_ipc    one process per GPU: exchange the 64-byte CUDA IPC
+ *                             handles out of band (world x 64 bytes, entry r = rank r's handle);
+ *   vx_shard_group_connect_local   all ranks in one process (one vx_ctx per device; what a Rust prover does);
+ *   vx_shard_commit_from_values    values_local = this rank's ceil(c/world) x n slice of the columns (columns
+ *                             rank*ceil(c/world).., zero rows beyond c), host or device; cap_all_out (2^cap_height x 4,
+ *                             host or device, may be NULL) receives the cap of the WHOLE commitment; *out is this
+ *                             rank's shard, as from vx_commit_from_coeffs_shard.  ALL ranks must be inside this call
+ *                             concurrently; a peer that does not show up within ~2 s makes it fail with VX_ECUDA. */
+typedef struct vx_shard_group vx_shard_group;
+int32_t vx_shard_group_create(vx_ctx* ctx, uint32_t rank, uint32_t world, uint32_t c, uint32_t log_n,
+                              uint32_t rate_bits, uint32_t cap_height, vx_shard_group** out);
+int32_t vx_shard_group_ipc_handle(vx_shard_group* g, uint8_t handle_out[64]);
+int32_t vx_shard_group_connect_ipc(vx_shard_group* g, const uint8_t* handles);
+int32_t vx_shard_group_connect_local(vx_shard_group* const* groups, uint32_t world);
+int32_t vx_shard_commit_from_values(vx_shard_group* g, const uint64_t* values_local, uint64_t* cap_all_out,
+                                    vx_batch** out);
+/* this rank's gather buffer: world*ceil(c/world) x n coefficients of the last commit (device, borrowed) */
+const uint64_t* vx_shard_group_coeffs_device(const vx_shard_group* g);
+uint32_t vx_shard_group_cols_per_rank(const vx_shard_group* g);
+void vx_shard_group_free(vx_shard_group* g);
 /* out[0] = first global leaf held, out[1] = leaves held, out[2] = cap entries held */
 int32_t vx_batch_shard(const vx_batch* b, uint64_t out[3]);
 void vx_batch_free(vx_batch* b);

@@ -32,6 +32,14 @@ SIGNATURES = {
     "vx_dev_copy": (c_i32, [vp, vp, vp, ctypes.c_size_t]),
     "vx_commit_from_coeffs_shard": (c_i32, [vp, vp, c_u32, c_u32, c_u32, c_u32, c_u32, c_u32, ctypes.POINTER(vp)]),
     "vx_batch_shard": (c_i32, [vp, u64p]),
+    "vx_shard_group_create": (c_i32, [vp, c_u32, c_u32, c_u32, c_u32, c_u32, c_u32, ctypes.POINTER(vp)]),
+    "vx_shard_group_ipc_handle": (c_i32, [vp, vp]),
+    "vx_shard_group_connect_ipc": (c_i32, [vp, vp]),
+    "vx_shard_group_connect_local": (c_i32, [ctypes.POINTER(vp), c_u32]),
+    "vx_shard_commit_from_values": (c_i32, [vp, vp, vp, ctypes.POINTER(vp)]),
+    "vx_shard_group_coeffs_device": (vp, [vp]),
+    "vx_shard_group_cols_per_rank": (c_u32, [vp]),
+    "vx_shard_group_free": (None, [vp]),
     "vx_commit_from_values": (c_i32, [vp, vp, c_u32, c_u32, c_u32, c_u32, ctypes.POINTER(vp)]),
     "vx_commit_from_coeffs": (c_i32, [vp, vp, c_u32, c_u32, c_u32, c_u32, ctypes.POINTER(vp)]),
     "vx_batch_free": (None, [vp]),

@@ -181,6 +181,9 @@ __global__ void __launch_bounds__(256) level_hash_coop_kernel(u64* __restrict__ 
     const uint32_t el = lane < 12 ? lane : 0;                        // lanes 12..15 shadow lane 0 (results unused)
     u64 s = lane < 8 ? src[lane] : 0;
     s = gl_add_canon(s, c_pos.rc[el]);
+    uint32_t from[12];                                               // source lanes of the MDS gather (loop invariant)
+#pragma unroll
+    for (int i = 0; i < 12; i++) from[i] = el + i >= 12 ? el + i - 12 : el + i;
 #pragma unroll 1
     for (int r = 0; r < POSEIDON_ROUNDS; r++) {
         const bool full = r < 4 || r >= 26;
@@ -190,10 +193,8 @@ __global__ void __launch_bounds__(256) level_hash_coop_kernel(u64* __restrict__ 
         const u32 slo = lo32(s), shi = hi32(s);
 #pragma unroll
         for (int i = 0; i < 12; i++) {
-            uint32_t from = el + i;
-            from = from >= 12 ? from - 12 : from;
-            u32 xl = __shfl_sync(0xffffffffu, slo, from, 16);
-            u32 xh = __shfl_sync(0xffffffffu, shi, from, 16);
+            u32 xl = __shfl_sync(0xffffffffu, slo, from[i], 16);
+            u32 xh = __shfl_sync(0xffffffffu, shi, from[i], 16);
             al = mad_wide(xl, C[i], al);
             ah = mad_wide(xh, C[i], ah);
         }
@@ -217,9 +218,13 @@ int32_t merkle_build_device(vx_ctx* ctx, const u64* leaves, bool col_major, uint
     VX_REQUIRE(cap_height <= log_N, "merkle: cap_height %u > log2(leaves) %u", cap_height, log_N);
     VX_REQUIRE(c >= 1, "merkle: empty leaves");
     uint32_t sub_bits = log_N - cap_height;
-    unsigned blocks = (unsigned)((N + 127) / 128);
+    // few leaves (a shard of a sharded commit, the small oracles): 64- or 32-thread blocks spread the warps evenly over
+    // the SMs (512 blocks of 128 on 148 SMs leave some SMs with 16 warps and others with 12)
+    unsigned threads = POSEIDON_BLOCK;
+    while (threads > 32 && (N + threads - 1) / threads < 8ULL * (uint64_t)ctx->sm_count) threads >>= 1;
+    unsigned blocks = (unsigned)((N + threads - 1) / threads);
     const int pv = ctx->poseidon_variant;
-#define LEAF(CM, V, MB) leaf_hash_kernel<CM, V, MB><<<blocks, POSEIDON_BLOCK, 0, ctx->stream>>>(leaves, stride, N, c, sub_bits, digests, cap)
+#define LEAF(CM, V, MB) leaf_hash_kernel<CM, V, MB><<<blocks, threads, 0, ctx->stream>>>(leaves, stride, N, c, sub_bits, digests, cap)
     if (col_major) {
         switch (pv) {
             case 1: LEAF(true, 1, 4); break;      // state in shared memory, rolled lane loops

@@ -8,6 +8,10 @@ Rank g of G (G a power of two, G <= 2^rate_bits, G <= 2^cap_height) ends up owni
     3. coset NTTs + leaf hashing + subtrees of the own block   (no communication)
     4. all-gather of the 2^cap_height / G local cap entries    (512 B)
 
+Two drivers share the plan: `sharded_commit` below keeps the exchange in a communicator object (torch.distributed:
+NCCL on GPUs, gloo in the CPU tests), and `PeerGroup` hands the whole commit to the library, whose own kernels do the
+exchange over NVLink peer memory (csrc/shard.cu) -- the path bench.py times at N > 1.
+
 The compute steps go through an engine object: `DeviceEngine` binds the C ABI (libvectorx_b200.so) and is the only
 engine in the product; tests inject a CPU engine to exercise the plan and the collective plumbing over gloo.
 The path this replaces is plonky2's single-process PolynomialBatch::from_values (reached from
@@ -144,3 +148,54 @@ def sharded_commit(values_local, plan: ShardPlan, engine, comm, bufs):
     comm.all_gather(bufs["cap_all"], bufs["cap_loc"])
     engine.fence()
     return handle, bufs["cap_all"]
+
+
+class PeerGroup:
+    """This rank's end of a library-level shard group (vx_shard_group_*): the exchange runs inside the library's own
+    kernels over peer memory.  `dist` (torch.distributed, initialised) is used once, to swap the 64-byte CUDA IPC
+    handles of the ranks' gather buffers; pass dist=None with `local_peers` for ranks living in one process."""
+
+    def __init__(self, ctx, plan: ShardPlan, dist=None):
+        import numpy as np
+        from ._lib import check, load, vp
+        self.ctx, self.plan, self.lib, self.check = ctx, plan, load(), check
+        self._h = vp()
+        check(self.lib.vx_shard_group_create(ctx.handle, plan.rank, plan.world, plan.c, plan.log_n, plan.rate_bits,
+                                             plan.cap_height, ctypes.byref(self._h)), "vx_shard_group_create")
+        if plan.world > 1 and dist is not None:
+            mine = np.zeros(64, dtype=np.uint8)
+            check(self.lib.vx_shard_group_ipc_handle(self._h, mine.ctypes.data), "vx_shard_group_ipc_handle")
+            gathered = [None] * plan.world
+            dist.all_gather_object(gathered, mine.tobytes())
+            table = np.frombuffer(b"".join(gathered), dtype=np.uint8).copy()
+            check(self.lib.vx_shard_group_connect_ipc(self._h, table.ctypes.data), "vx_shard_group_connect_ipc")
+
+    @staticmethod
+    def connect_local(groups):
+        """all ranks in this process: map each other's buffers directly (peer access)"""
+        from ._lib import check, load, vp
+        arr = (vp * len(groups))(*[g._h for g in groups])
+        check(load().vx_shard_group_connect_local(arr, len(groups)), "vx_shard_group_connect_local")
+
+    def commit_from_values(self, values_local, cap_all_out=None):
+        """values_local: (cols_per_rank, n) slice, host (numpy / pinned torch) or device (torch).  Returns the shard
+        handle (free with .free_batch); cap_all_out (2^cap_height, 4) receives the whole cap."""
+        from ._lib import ptr, vp
+        h = vp()
+        self.check(self.lib.vx_shard_commit_from_values(self._h, ptr(values_local), ptr(cap_all_out), ctypes.byref(h)),
+                   "vx_shard_commit_from_values")
+        return h
+
+    def free_batch(self, h):
+        self.lib.vx_batch_free(h)
+
+    def close(self):
+        if self._h:
+            self.lib.vx_shard_group_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
