@@ -65,6 +65,8 @@ extern "C" int32_t vx_ctx_create(int32_t device, vx_ctx** out) {
     ctx->sm_count = prop.multiProcessorCount;
     if (const char* v = getenv("VX_POSEIDON_VARIANT")) ctx->poseidon_variant = atoi(v);
     if (const char* v = getenv("VX_NTT_LEGACY")) ctx->ntt_legacy = atoi(v);
+    if (const char* v = getenv("VX_TREE_FUSE")) ctx->tree_fuse = atoi(v);
+    if (const char* v = getenv("VX_COOP_MAX_PAIRS")) ctx->coop_max_pairs = atoi(v);
     cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete ctx; vx_set_error("stream create: %s", cudaGetErrorString(e)); return VX_ECUDA; }
     // keep freed blocks in the stream-ordered pool: commits allocate GBs per call

@@ -52,6 +52,8 @@ struct vx_ctx {
     int device = 0;
     int sm_count = 0;
     int ntt_legacy = 0;                 // VX_NTT_LEGACY=1: radix-2 shared-memory passes only (A/B switch)
+    int coop_max_pairs = 4096;          // Merkle levels with at most this many pairs use 16 lanes per two_to_one (VX_COOP_MAX_PAIRS)
+    int tree_fuse = 1;                  // VX_TREE_FUSE=0: one launch per small Merkle level (A/B switch)
     int poseidon_variant = 0;           // VX_POSEIDON_VARIANT (A/B switch for profiling): 0 = default, 1 = shared-memory state, 2 = 128-register form
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr; // host->device staging of commit inputs, overlapped with the transforms

@@ -277,6 +277,26 @@ GL_D void gl_acc_mad(GlAcc& t, u64 a, u64 b) {
         : "+r"(t.l0), "+r"(t.h0), "+r"(t.c0), "+r"(t.l1), "+r"(t.h1), "+r"(t.c1), "+r"(t.l2), "+r"(t.h2), "+r"(t.c2)
         : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
 }
+// Same term with the four products issued as addend-free IMAD.WIDE and the accumulation done by 3-instruction carry
+// chains on the ALU pipe (tools/intpeak2.cu: 5.0 SMSP cycles per partial product against 6.8 for the accumulating
+// IMAD.WIDE with carry-out) -- A/B variant, selected per kernel.
+GL_D void gl_acc_mad_alu(GlAcc& t, u64 a, u64 b) {
+    u32 a0 = lo32(a), a1 = hi32(a), b0 = lo32(b), b1 = hi32(b);
+    u64 p00 = mul_wide(a0, b0), p01 = mul_wide(a0, b1), p10 = mul_wide(a1, b0), p11 = mul_wide(a1, b1);
+    asm("{\n\t"
+        "add.cc.u32 %0, %0, %9;\n\t"   "addc.cc.u32 %1, %1, %10;\n\t"  "addc.u32 %2, %2, 0;\n\t"
+        "add.cc.u32 %3, %3, %11;\n\t"  "addc.cc.u32 %4, %4, %12;\n\t"  "addc.u32 %5, %5, 0;\n\t"
+        "add.cc.u32 %3, %3, %13;\n\t"  "addc.cc.u32 %4, %4, %14;\n\t"  "addc.u32 %5, %5, 0;\n\t"
+        "add.cc.u32 %6, %6, %15;\n\t"  "addc.cc.u32 %7, %7, %16;\n\t"  "addc.u32 %8, %8, 0;\n\t"
+        "}"
+        : "+r"(t.l0), "+r"(t.h0), "+r"(t.c0), "+r"(t.l1), "+r"(t.h1), "+r"(t.c1), "+r"(t.l2), "+r"(t.h2), "+r"(t.c2)
+        : "r"(lo32(p00)), "r"(hi32(p00)), "r"(lo32(p01)), "r"(hi32(p01)), "r"(lo32(p10)), "r"(hi32(p10)),
+          "r"(lo32(p11)), "r"(hi32(p11)));
+}
+template <int ALU>
+GL_D void gl_acc_mad_v(GlAcc& t, u64 a, u64 b) {
+    if (ALU) gl_acc_mad_alu(t, a, b); else gl_acc_mad(t, a, b);
+}
 // small-constant term: a * k, k < 2^32
 GL_D void gl_acc_mad_small(GlAcc& t, u64 a, u32 k) {
     u32 a0 = lo32(a), a1 = hi32(a);

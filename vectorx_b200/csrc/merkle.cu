@@ -66,12 +66,16 @@ void poseidon_round_constants_host(u64 out[360]) {
     }
 }
 
+static __device__ u64 g_pos_rc[31 * 12];      // global-memory copy of c_pos.rc for kernels that index it per lane
+
 int32_t poseidon_module_init(vx_ctx* ctx) {
     u64 rc[360];
     poseidon_round_constants_host(rc);
     PoseidonTables t;
     if (!poseidon_derive_tables(rc, &t)) { vx_set_error("poseidon: table derivation failed"); return VX_ECUDA; }
     VX_CUDA(poseidon_upload_constants(t, ctx->stream));
+    VX_CUDA(cudaMemcpyToSymbolAsync(g_pos_rc, t.rc, sizeof t.rc, 0, cudaMemcpyHostToDevice, ctx->stream));
+    VX_CUDA(cudaStreamSynchronize(ctx->stream));
     return VX_OK;
 }
 
@@ -87,7 +91,7 @@ GL_D void store_digest(u64* dst, const u64 s[12]) {
 
 // one thread per leaf: hash_or_noop(leaf) -> interleaved slot (or cap when the subtree is 1 leaf)
 // V = 0: state in registers, frequency-domain MDS.  V = 1: state in shared memory, rolled lane loops.
-// V = 2: state in registers, IMAD.WIDE MDS (the round-1a kernel, kept for A/B runs).
+// V = 2: state in registers, IMAD.WIDE MDS (the round-1a kernel, kept for A/B runs).  V = 3: V 0 with ALU-side accumulation.
 template <bool COL_MAJOR, int V, int MINB>
 __global__ void __launch_bounds__(POSEIDON_BLOCK, MINB) leaf_hash_kernel(const u64* __restrict__ leaves, uint64_t stride,
                                                         uint64_t N, uint32_t c, uint32_t sub_bits,
@@ -115,7 +119,7 @@ __global__ void __launch_bounds__(POSEIDON_BLOCK, MINB) leaf_hash_kernel(const u
 #pragma unroll
                 for (int i = 0; i < POSEIDON_RATE; i++)
                     if (off + i < c) s[i] = src[(uint64_t)(off + i) * step];   // overwrite-mode absorb
-                poseidon_permute<V == 2 ? 1 : 0>(s, st);
+                poseidon_permute<V == 2 ? 1 : (V == 3 ? 2 : 0)>(s, st);
             } else {
 #pragma unroll
                 for (int i = 0; i < POSEIDON_RATE; i++)
@@ -166,9 +170,48 @@ __global__ void __launch_bounds__(POSEIDON_BLOCK) level_hash_kernel(u64* __restr
 // shuffles (spec round structure: add constants, x^7, MDS; partial rounds apply x^7 on lane 0 only).  ~5x lower latency,
 // ~3x more thread-instructions: used only while a level has at most VX_COOP_MAX_PAIRS pairs.
 #define VX_COOP_MAX_PAIRS 4096
+
+// The cooperative permutation: lane (of a 16-lane group) el < 12 holds state element el; returns the permuted element.
+// `s` enters WITHOUT the first round's constants.
+GL_D u64 poseidon_coop_permute(u64 s, const uint32_t lane, const uint32_t el, const u64* __restrict__ rc) {
+    constexpr u32 C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+    s = gl_add_canon(s, rc[el]);
+    uint32_t from[12];                                               // source lanes of the MDS gather (loop invariant)
+#pragma unroll
+    for (int i = 0; i < 12; i++) from[i] = el + i >= 12 ? el + i - 12 : el + i;
+    const u32 d = el == 0 ? 8u : 0u;
+#pragma unroll 1
+    for (int r = 0; r < POSEIDON_ROUNDS; r++) {
+        const bool full = r < 4 || r >= 26;
+        const u64 k = rc[12 * (r + 1) + el];                         // next round's constants (row 30 is zero)
+        if (full || lane == 0) s = gl_pow7_cc(s);
+        const u32 slo = lo32(s), shi = hi32(s);
+        // two independent accumulation chains per half (even / odd terms): the chain of dependent IMAD.WIDE is what
+        // bounds the latency of this layer
+        u64 al = (u64)lo32(k), ah = (u64)hi32(k);
+        u64 bl = mul_wide(slo, d), bh = mul_wide(shi, d);
+#pragma unroll
+        for (int i = 0; i < 12; i += 2) {
+            u32 xl = __shfl_sync(0xffffffffu, slo, from[i], 16);
+            u32 xh = __shfl_sync(0xffffffffu, shi, from[i], 16);
+            u32 yl = __shfl_sync(0xffffffffu, slo, from[i + 1], 16);
+            u32 yh = __shfl_sync(0xffffffffu, shi, from[i + 1], 16);
+            al = mad_wide(xl, C[i], al);
+            ah = mad_wide(xh, C[i], ah);
+            bl = mad_wide(yl, C[i + 1], bl);
+            bh = mad_wide(yh, C[i + 1], bh);
+        }
+        al += bl;                                                    // < 2^42: no carry
+        ah += bh;
+        u64 l = al + ((u64)lo32(ah) << 32);
+        u32 c = l < al;
+        s = gl_reduce96(l, hi32(ah) + c);
+    }
+    return s;
+}
+
 __global__ void __launch_bounds__(256) level_hash_coop_kernel(u64* __restrict__ digests, u64* __restrict__ cap, uint32_t lvl,
                                                               uint32_t sub_bits, uint64_t total_pairs) {
-    constexpr u32 C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
     const uint32_t lane = threadIdx.x & 15;
     const uint64_t t_raw = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
     const bool live = t_raw < total_pairs;
@@ -180,34 +223,52 @@ __global__ void __launch_bounds__(256) level_hash_coop_kernel(u64* __restrict__ 
     const u64* src = blk + 4 * pair_pos(q, lvl);
     const uint32_t el = lane < 12 ? lane : 0;                        // lanes 12..15 shadow lane 0 (results unused)
     u64 s = lane < 8 ? src[lane] : 0;
-    s = gl_add_canon(s, c_pos.rc[el]);
-    uint32_t from[12];                                               // source lanes of the MDS gather (loop invariant)
-#pragma unroll
-    for (int i = 0; i < 12; i++) from[i] = el + i >= 12 ? el + i - 12 : el + i;
-#pragma unroll 1
-    for (int r = 0; r < POSEIDON_ROUNDS; r++) {
-        const bool full = r < 4 || r >= 26;
-        if (full || lane == 0) s = gl_pow7_cc(s);
-        const u64 k = c_pos.rc[12 * (r + 1) + el];                   // next round's constants (row 30 is zero)
-        u64 al = (u64)lo32(k), ah = (u64)hi32(k);
-        const u32 slo = lo32(s), shi = hi32(s);
-#pragma unroll
-        for (int i = 0; i < 12; i++) {
-            u32 xl = __shfl_sync(0xffffffffu, slo, from[i], 16);
-            u32 xh = __shfl_sync(0xffffffffu, shi, from[i], 16);
-            al = mad_wide(xl, C[i], al);
-            ah = mad_wide(xh, C[i], ah);
-        }
-        const u32 d = el == 0 ? 8u : 0u;
-        al = mad_wide(slo, d, al);
-        ah = mad_wide(shi, d, ah);
-        u64 l = al + ((u64)lo32(ah) << 32);
-        u32 c = l < al;
-        s = gl_reduce96(l, hi32(ah) + c);
-    }
+    s = poseidon_coop_permute(s, lane, el, c_pos.rc);
     if (live && lane < 4) {
         u64* dst = (pair_bits == 0) ? cap + 4 * sidx : blk + 4 * (pair_pos(q >> 1, lvl + 1) + (q & 1));
         dst[lane] = gl_canon(s);
+    }
+}
+
+// Several small levels in ONE launch: a CTA owns 2^(nl-1) consecutive sibling pairs of layer lvl0 (all inside one cap
+// subtree) and reduces them through nl layers, 16 lanes per two_to_one, handing each layer's digests to the next through
+// shared memory (and writing every one to its slot of the interleaved layout).  A standalone launch of a small level
+// costs ~24 us, most of it cold instruction / constant caches and launch latency; here only the first layer pays that.
+#define VX_FUSE_MAX_LEVELS 7
+__global__ void __launch_bounds__(1024) level_hash_fused_kernel(u64* __restrict__ digests, u64* __restrict__ cap,
+                                                                uint32_t lvl0, uint32_t nl, uint32_t sub_bits) {
+    __shared__ u64 sh[2][4 << (VX_FUSE_MAX_LEVELS - 1)];              // digests of the layer just produced (ping-pong)
+    __shared__ u64 sh_rc[31 * 12];                                   // lanes read DIFFERENT constants: a constant-bank read
+    for (uint32_t i = threadIdx.x; i < 31 * 12; i += blockDim.x) sh_rc[i] = g_pos_rc[i];     // would serialise 12-fold
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 15, g = threadIdx.x >> 4;
+    const uint32_t el = lane < 12 ? lane : 0;
+    const uint32_t p0 = 1u << (nl - 1);                              // pairs of layer lvl0 owned by this CTA
+    const uint32_t pair_bits0 = sub_bits - lvl0 - 1;                 // pairs per subtree at lvl0 = 2^pair_bits0 >= p0
+    const uint64_t t0 = (uint64_t)blockIdx.x * p0;                   // first pair (global numbering over subtrees)
+    const uint64_t sidx = t0 >> pair_bits0;
+    const uint64_t q0 = t0 & ((1ULL << pair_bits0) - 1);
+    const uint64_t sub = 1ULL << sub_bits;
+    u64* blk = digests + 4 * sidx * (2 * sub - 2);
+    for (uint32_t i = 0; i < nl; i++) {
+        const uint32_t lvl = lvl0 + i;
+        const uint32_t pairs = p0 >> i;
+        if ((g & ~1u) < pairs) {                                     // warp-uniform: both groups of a warp shuffle together
+            const bool live = g < pairs;
+            const uint32_t gg = live ? g : pairs - 1;                // an idle second group redoes the last pair (no store)
+            const uint64_t q = (q0 >> i) + gg;
+            u64 s = 0;
+            if (lane < 8) s = i == 0 ? blk[4 * pair_pos(q, lvl) + lane] : sh[i & 1][8 * gg + lane];
+            s = poseidon_coop_permute(s, lane, el, sh_rc);
+            if (live && lane < 4) {
+                const u64 v = gl_canon(s);
+                const bool top = lvl + 1 == sub_bits;
+                u64* dst = top ? cap + 4 * sidx : blk + 4 * (pair_pos(q >> 1, lvl + 1) + (q & 1));
+                dst[lane] = v;
+                sh[(i + 1) & 1][4 * g + lane] = v;
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -233,6 +294,7 @@ int32_t merkle_build_device(vx_ctx* ctx, const u64* leaves, bool col_major, uint
             case 4: LEAF(true, 0, 6); break;      // up to 80 registers
             case 5: LEAF(true, 0, 10); break;     // 48 registers, 10 blocks per SM
             case 6: LEAF(true, 0, 9); break;      // 56 registers, 9 blocks per SM
+            case 7: LEAF(true, 3, 8); break;      // lazy dot products accumulated on the ALU pipe
             default: LEAF(true, 0, 8); break;     // state in registers, 64 registers / 8 blocks per SM
         }
     } else {
@@ -241,14 +303,25 @@ int32_t merkle_build_device(vx_ctx* ctx, const u64* leaves, bool col_major, uint
 #undef LEAF
     VX_LAUNCH_COUNT(ctx, 1);
     if (after_leaves) VX_CUDA(cudaEventRecord(after_leaves, ctx->stream));
-    for (uint32_t lvl = 0; lvl < sub_bits; lvl++) {
+    for (uint32_t lvl = 0; lvl < sub_bits;) {
         uint64_t total_pairs = N >> (lvl + 1);
-        if (total_pairs <= VX_COOP_MAX_PAIRS && !ctx->ntt_legacy) {
+        if (total_pairs <= (uint64_t)ctx->coop_max_pairs && !ctx->ntt_legacy && ctx->tree_fuse) {
+            // wide layers: short runs (many CTAs, spread over the SMs); the narrow top: one long run per subtree group
+            uint32_t nl = sub_bits - lvl;
+            const uint32_t cap_nl = total_pairs > 256 ? 5 : VX_FUSE_MAX_LEVELS;
+            if (nl > cap_nl) nl = cap_nl;
+            const uint32_t p0 = 1u << (nl - 1);
+            unsigned threads = p0 * 16 < 32 ? 32 : p0 * 16;
+            level_hash_fused_kernel<<<(unsigned)(total_pairs / p0), threads, 0, ctx->stream>>>(digests, cap, lvl, nl, sub_bits);
+            lvl += nl;
+        } else if (total_pairs <= (uint64_t)ctx->coop_max_pairs && !ctx->ntt_legacy) {
             unsigned b = (unsigned)((total_pairs * 16 + 255) / 256);
             level_hash_coop_kernel<<<b, 256, 0, ctx->stream>>>(digests, cap, lvl, sub_bits, total_pairs);
+            lvl++;
         } else {
             unsigned b = (unsigned)((total_pairs + 127) / 128);
             level_hash_kernel<<<b, 128, 0, ctx->stream>>>(digests, cap, lvl, sub_bits, total_pairs);
+            lvl++;
         }
         VX_LAUNCH_COUNT(ctx, 1);
     }

@@ -124,6 +124,7 @@ GL_D void poseidon_mds_add_freq(u64 s[12], const u32* __restrict__ kl) {
 // s <- D * s + e with D a dense matrix of full-width constants (the MDS layer of full round 3 merged
 // with the partial rounds' initial matrix).  Rows are produced in a rolled loop (small code) and
 // staged through this thread's shared-memory column: scratch[j * POSEIDON_BLOCK].
+template <int ALU = 0>
 GL_D void poseidon_dense_layer(u64 s[12], u64* __restrict__ scratch) {
 #pragma unroll 1
     for (int j = 0; j < 12; j++) {
@@ -131,7 +132,7 @@ GL_D void poseidon_dense_layer(u64 s[12], u64* __restrict__ scratch) {
         GlAcc acc;
         gl_acc_init(acc, c_pos.dense_e[j]);
 #pragma unroll
-        for (int i = 0; i < 12; i++) gl_acc_mad(acc, row[i], s[i]);
+        for (int i = 0; i < 12; i++) gl_acc_mad_v<ALU>(acc, row[i], s[i]);
         scratch[j * POSEIDON_BLOCK] = gl_acc_reduce(acc);
     }
 #pragma unroll
@@ -139,6 +140,7 @@ GL_D void poseidon_dense_layer(u64 s[12], u64* __restrict__ scratch) {
 }
 
 // 22 partial rounds in the sparse form (see poseidon_tables.h)
+template <int ALU = 0>
 GL_D void poseidon_partial_rounds(u64 s[12]) {
 #pragma unroll 1
     for (int r = 0; r < POSEIDON_PARTIAL_ROUNDS; r++) {
@@ -150,7 +152,7 @@ GL_D void poseidon_partial_rounds(u64 s[12]) {
         gl_acc_init(d, 0);
         gl_acc_mad_small(d, x0, 25u);
 #pragma unroll
-        for (int i = 1; i < 12; i++) gl_acc_mad(d, v[i - 1], s[i]);
+        for (int i = 1; i < 12; i++) gl_acc_mad_v<ALU>(d, v[i - 1], s[i]);
 #pragma unroll
         for (int i = 1; i < 12; i++) s[i] = gl_mul_add_cc(w[i - 1], x0, s[i]);
         s[0] = gl_acc_reduce(d);
@@ -158,7 +160,8 @@ GL_D void poseidon_partial_rounds(u64 s[12]) {
 }
 
 // scratch: this thread's column of a POSEIDON_BLOCK-wide shared array of 12 rows
-// MV = 0: frequency-domain MDS layer (shifts/adds on 22-bit limb planes); MV = 1: IMAD.WIDE MDS on 32-bit halves (A/B)
+// MV = 0: frequency-domain MDS layer (shifts/adds on 22-bit limb planes); MV = 1: IMAD.WIDE MDS on 32-bit halves (A/B);
+// MV = 2: MV 0 with the lazy dot products accumulated on the ALU pipe (gl_acc_mad_alu, A/B)
 template <int MV = 0>
 GL_D void poseidon_permute(u64 s[12], u64* __restrict__ scratch) {
     const u64* rc = c_pos.rc;
@@ -171,12 +174,12 @@ GL_D void poseidon_permute(u64 s[12], u64* __restrict__ scratch) {
         for (int r = 0; r < 4; r++) {
 #pragma unroll
             for (int i = 0; i < 12; i++) s[i] = gl_pow7_cc(s[i]);
-            if (half == 0 && r == 3) poseidon_dense_layer(s, scratch);
-            else if (MV == 0) poseidon_mds_add_freq(s, c_pos.rc22 + 36 * (first + r));
+            if (half == 0 && r == 3) poseidon_dense_layer<MV == 2>(s, scratch);
+            else if (MV != 1) poseidon_mds_add_freq(s, c_pos.rc22 + 36 * (first + r));
             else poseidon_mds_add(s, rc + 12 * (first + r));
         }
         if (half == 0) {
-            poseidon_partial_rounds(s);
+            poseidon_partial_rounds<MV == 2>(s);
 #pragma unroll
             for (int i = 0; i < 12; i++) s[i] = gl_add_canon(s[i], rc[26 * 12 + i]);
         }
