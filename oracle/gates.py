@@ -276,3 +276,379 @@ class PoseidonGate(Gate):
         for i in range(12):
             row[G.W_OUT + i] = st[i]
         return st
+
+
+# ------------------------------------------------------------------------------------------------ in-tree gates (exact)
+class U32AddManyGate(Gate):
+    """add_many_u32.rs:41-84 (layout), :149-190 (constraints): per op `num_addends` addends + carry -> 32-bit result +
+    output carry, decomposed into 16 + 3 two-bit limbs."""
+    NUM_RESULT_LIMBS, NUM_CARRY_LIMBS = 16, 3
+
+    def __init__(self, num_addends=3, num_ops=None):
+        a = num_addends
+        self.num_addends = a
+        self.num_ops = num_ops if num_ops is not None else min(NUM_WIRES // (a + 3 + 19), NUM_ROUTED // (a + 3))
+        self.name = f"U32AddManyGate {{ num_addends: {a}, num_ops: {self.num_ops} }}"
+        self.degree = 4
+        self.num_constraints = self.num_ops * (3 + 19)
+
+    def w_addend(self, i, j): return (self.num_addends + 3) * i + j
+    def w_carry(self, i): return (self.num_addends + 3) * i + self.num_addends
+    def w_result(self, i): return (self.num_addends + 3) * i + self.num_addends + 1
+    def w_out_carry(self, i): return (self.num_addends + 3) * i + self.num_addends + 2
+    def w_limb(self, i, j): return (self.num_addends + 3) * self.num_ops + 19 * i + j
+
+    def eval(self, w, c, pi):
+        out = []
+        for i in range(self.num_ops):
+            computed = w[self.w_carry(i)]
+            for j in range(self.num_addends):
+                computed = computed + w[self.w_addend(i, j)]
+            res, oc = w[self.w_result(i)], w[self.w_out_carry(i)]
+            out.append(oc * (1 << 32) + res - computed)
+            comb_res = comb_carry = None
+            for j in reversed(range(19)):
+                limb = w[self.w_limb(i, j)]
+                out.append(limb * (limb - 1) * (limb - 2) * (limb - 3))
+                if j < 16:
+                    comb_res = limb if comb_res is None else comb_res * 4 + limb
+                else:
+                    comb_carry = limb if comb_carry is None else comb_carry * 4 + limb
+            out.append(comb_res - res)
+            out.append(comb_carry - oc)
+        return out
+
+    def fill_witness(self, row, rnd):
+        for i in range(self.num_ops):
+            total = 0
+            for j in range(self.num_addends):
+                v = rnd.randrange(1 << 32)
+                row[self.w_addend(i, j)] = v
+                total += v
+            carry = rnd.randrange(1 << 32)
+            row[self.w_carry(i)] = carry
+            total += carry
+            res, oc = total & 0xFFFFFFFF, total >> 32
+            row[self.w_result(i)], row[self.w_out_carry(i)] = res, oc
+            for j in range(16):
+                row[self.w_limb(i, j)] = (res >> (2 * j)) & 3
+            for j in range(3):
+                row[self.w_limb(i, 16 + j)] = (oc >> (2 * j)) & 3
+
+
+class ComparisonGate(Gate):
+    """comparison.rs:44-92 (layout), :333-410 (constraints): result = (first <= second) on num_bits-bit inputs split
+    into num_chunks chunks (gadget use: multiple_comparison.rs:39, 32 bits in 16 chunks)."""
+
+    def __init__(self, num_bits=32, num_chunks=16):
+        self.num_bits, self.num_chunks = num_bits, num_chunks
+        self.chunk_bits = -(-num_bits // num_chunks)
+        self.name = f"ComparisonGate {{ num_bits: {num_bits}, num_chunks: {num_chunks} }}<D=2>"
+        self.degree = 1 << self.chunk_bits
+        self.num_constraints = 6 + 5 * num_chunks + self.chunk_bits
+
+    def eval(self, w, c, pi):
+        n, cb = self.num_chunks, self.chunk_bits
+        first = [w[4 + i] for i in range(n)]
+        second = [w[4 + n + i] for i in range(n)]
+
+        def horner(xs, base):
+            acc = xs[-1]
+            for x in reversed(xs[:-1]):
+                acc = acc * base + x
+            return acc
+
+        out = [horner(first, 1 << cb) - w[0], horner(second, 1 << cb) - w[1]]
+        msd = None
+        for i in range(n):
+            p1 = p2 = None
+            for x in range(1 << cb):
+                t1, t2 = first[i] - x, second[i] - x
+                p1 = t1 if p1 is None else p1 * t1
+                p2 = t2 if p2 is None else p2 * t2
+            out += [p1, p2]
+            diff = second[i] - first[i]
+            dummy, eq, inter = w[4 + 2 * n + i], w[4 + 3 * n + i], w[4 + 4 * n + i]
+            out.append(diff * dummy - (1 - eq))
+            out.append(eq * diff)
+            out.append(inter - eq * msd if msd is not None else inter - eq * 0)
+            msd = inter + (1 - eq) * diff
+        out.append(w[3] - msd)
+        bits = [w[4 + 5 * n + i] for i in range(cb + 1)]
+        for b in bits:
+            out.append(b * (1 - b))
+        out.append(w[3] + (1 << cb) - horner(bits, 2))
+        out.append(w[2] - bits[cb])
+        assert len(out) == self.num_constraints
+        return out
+
+    def fill_witness(self, row, rnd, a=None, b=None):
+        P = pyref.P
+        n, cb = self.num_chunks, self.chunk_bits
+        a = rnd.randrange(1 << self.num_bits) if a is None else a
+        b = rnd.randrange(1 << self.num_bits) if b is None else b
+        row[0], row[1] = a, b
+        msd = 0
+        for i in range(n):
+            x, y = (a >> (cb * i)) & ((1 << cb) - 1), (b >> (cb * i)) & ((1 << cb) - 1)
+            row[4 + i], row[4 + n + i] = x, y
+            diff = (y - x) % P
+            eq = 1 if x == y else 0
+            row[4 + 2 * n + i] = pow(diff, P - 2, P) if diff else 1        # equality dummy
+            row[4 + 3 * n + i] = eq
+            row[4 + 4 * n + i] = eq * msd % P                              # intermediate value
+            msd = (row[4 + 4 * n + i] + (1 - eq) * diff) % P
+        row[3] = msd
+        v = ((1 << cb) + (msd if msd < P // 2 else msd - P))               # 2^cb + signed msd in [1, 2^(cb+1))
+        for i in range(cb + 1):
+            row[4 + 5 * n + i] = (v >> i) & 1
+        row[2] = (v >> cb) & 1
+        assert row[2] == (1 if a <= b else 0)
+
+
+# ------------------------------------------------------------------------------------------------ upstream gates
+# plonky2 v0.2.0 gates restated from SURVEY.md Appendix B (source not vendored in /root/reference): PARITY UNPINNED;
+# each is validated by an honest-witness test (constraints vanish) and by GPU == oracle on random wires.
+D = 2
+W7 = 7          # F[x]/(x^2 - 7)
+
+
+def ext_mul(a, b):
+    return (a[0] * b[0] + a[1] * b[1] * W7, a[0] * b[1] + a[1] * b[0])
+
+
+def _ext_mul_int(a, b):
+    P = pyref.P
+    return ((a[0] * b[0] + W7 * a[1] * b[1]) % P, (a[0] * b[1] + a[1] * b[0]) % P)
+
+
+class ArithmeticExtensionGate(Gate):
+    """gates/arithmetic_extension.rs: per op out = m0 * m1 * c0 + addend * c1 over the quadratic extension."""
+
+    def __init__(self, num_ops=NUM_ROUTED // (4 * D)):
+        self.num_ops = num_ops
+        self.name = f"ArithmeticExtensionGate {{ num_ops: {num_ops} }}"
+        self.degree, self.num_constants, self.num_constraints = 3, 2, num_ops * D
+
+    def eval(self, w, c, pi):
+        out = []
+        for i in range(self.num_ops):
+            b = 4 * D * i
+            m0, m1, add, res = (w[b], w[b + 1]), (w[b + 2], w[b + 3]), (w[b + 4], w[b + 5]), (w[b + 6], w[b + 7])
+            pr = ext_mul(m0, m1)
+            for k in range(D):
+                out.append(res[k] - (pr[k] * c[0] + add[k] * c[1]))
+        return out
+
+    def fill_witness(self, row, rnd, c0, c1):
+        P = pyref.P
+        for i in range(self.num_ops):
+            b = 4 * D * i
+            v = [rnd.randrange(P) for _ in range(6)]
+            pr = _ext_mul_int((v[0], v[1]), (v[2], v[3]))
+            row[b:b + 6] = v
+            row[b + 6] = (pr[0] * c0 + v[4] * c1) % P
+            row[b + 7] = (pr[1] * c0 + v[5] * c1) % P
+
+
+class MulExtensionGate(Gate):
+    """gates/multiplication_extension.rs: per op out = m0 * m1 * c0."""
+
+    def __init__(self, num_ops=NUM_ROUTED // (3 * D)):
+        self.num_ops = num_ops
+        self.name = f"MulExtensionGate {{ num_ops: {num_ops} }}"
+        self.degree, self.num_constants, self.num_constraints = 3, 1, num_ops * D
+
+    def eval(self, w, c, pi):
+        out = []
+        for i in range(self.num_ops):
+            b = 3 * D * i
+            pr = ext_mul((w[b], w[b + 1]), (w[b + 2], w[b + 3]))
+            for k in range(D):
+                out.append(w[b + 4 + k] - pr[k] * c[0])
+        return out
+
+    def fill_witness(self, row, rnd, c0):
+        P = pyref.P
+        for i in range(self.num_ops):
+            b = 3 * D * i
+            v = [rnd.randrange(P) for _ in range(4)]
+            pr = _ext_mul_int((v[0], v[1]), (v[2], v[3]))
+            row[b:b + 4] = v
+            row[b + 4], row[b + 5] = pr[0] * c0 % P, pr[1] * c0 % P
+
+
+class ReducingGate(Gate):
+    """gates/reducing.rs: Horner accumulation acc_i = acc_{i-1} * alpha + coeff_i with base-field coefficients;
+    wires: output 0..D, alpha D..2D, old_acc 2D..3D, coeffs from 3D, intermediate accumulators after them (the last
+    accumulator is the output)."""
+    EXT_COEFFS = False
+
+    def __init__(self, num_coeffs=None):
+        if num_coeffs is None:
+            num_coeffs = (NUM_WIRES - 2 * D) // (D + (D if self.EXT_COEFFS else 1))
+            num_coeffs = min(num_coeffs, (NUM_ROUTED - 3 * D) // (D if self.EXT_COEFFS else 1))
+        self.num_coeffs = num_coeffs
+        self.name = f"{type(self).__name__} {{ num_coeffs: {num_coeffs} }}"
+        self.degree, self.num_constants, self.num_constraints = 2, 0, D * num_coeffs
+
+    def w_coeff(self, i):
+        return (3 * D + D * i, 3 * D + D * i + 1) if self.EXT_COEFFS else (3 * D + i, None)
+
+    def w_acc(self, i):
+        if i == self.num_coeffs - 1:
+            return 0
+        return 3 * D + self.num_coeffs * (D if self.EXT_COEFFS else 1) + D * i
+
+    def eval(self, w, c, pi):
+        alpha = (w[D], w[D + 1])
+        acc = (w[2 * D], w[2 * D + 1])
+        out = []
+        for i in range(self.num_coeffs):
+            c0, c1 = self.w_coeff(i)
+            a = self.w_acc(i)
+            pr = ext_mul(acc, alpha)
+            out.append(pr[0] + w[c0] - w[a])
+            out.append(pr[1] + w[c1] - w[a + 1] if c1 is not None else pr[1] - w[a + 1])
+            acc = (w[a], w[a + 1])
+        return out
+
+    def fill_witness(self, row, rnd):
+        P = pyref.P
+        alpha = (rnd.randrange(P), rnd.randrange(P))
+        acc = (rnd.randrange(P), rnd.randrange(P))
+        row[D], row[D + 1] = alpha
+        row[2 * D], row[2 * D + 1] = acc
+        for i in range(self.num_coeffs):
+            c0, c1 = self.w_coeff(i)
+            row[c0] = rnd.randrange(P)
+            if c1 is not None:
+                row[c1] = rnd.randrange(P)
+            pr = _ext_mul_int(acc, alpha)
+            acc = ((pr[0] + row[c0]) % P, (pr[1] + (row[c1] if c1 is not None else 0)) % P)
+            a = self.w_acc(i)
+            row[a], row[a + 1] = acc
+
+
+class ReducingExtensionGate(ReducingGate):
+    """gates/reducing_extension.rs: the same with extension-field coefficients."""
+    EXT_COEFFS = True
+
+
+class ExponentiationGate(Gate):
+    """gates/exponentiation.rs: output = base^(power bits), square-and-multiply from the top bit with every
+    intermediate value wired; wires: base 0, bits 1..1+n (little endian), output 1+n, intermediates from 2+n."""
+
+    def __init__(self, num_power_bits=(NUM_WIRES - 2) // 2):
+        n = num_power_bits
+        self.n = n
+        self.name = f"ExponentiationGate {{ num_power_bits: {n} }}<D=2>"
+        self.degree, self.num_constants, self.num_constraints = 4, 0, n + 1
+
+    def eval(self, w, c, pi):
+        n = self.n
+        out = []
+        for i in range(n):
+            bit = w[1 + (n - 1 - i)]
+            factor = bit * w[0] + (1 - bit)
+            if i == 0:
+                computed = factor
+            else:
+                prev = w[2 + n + i - 1]
+                computed = prev * prev * factor
+            out.append(computed - w[2 + n + i])
+        out.append(w[1 + n] - w[2 + n + n - 1])
+        return out
+
+    def fill_witness(self, row, rnd):
+        P = pyref.P
+        n = self.n
+        base, e = rnd.randrange(P), rnd.randrange(1 << n)
+        row[0] = base
+        cur = 1
+        for i in range(n):
+            row[1 + i] = (e >> i) & 1
+        for i in range(n):
+            bit = (e >> (n - 1 - i)) & 1
+            cur = cur * cur % P * (base if bit else 1) % P
+            row[2 + n + i] = cur
+        row[1 + n] = cur
+        assert cur == pow(base, e, P)
+
+
+class PoseidonMdsGate(Gate):
+    """gates/poseidon_mds.rs: 12 extension inputs (wires 0..24) -> 12 extension outputs (24..48), out = MDS * in."""
+    name = "PoseidonMdsGate"
+    degree, num_constants, num_constraints = 1, 0, 12 * D
+
+    def eval(self, w, c, pi):
+        out = []
+        for r in range(12):
+            for k in range(D):
+                acc = w[D * r + k] * (pyref.MDS_CIRC[0] + pyref.MDS_DIAG[r])
+                for i in range(1, 12):
+                    acc = acc + w[D * ((i + r) % 12) + k] * pyref.MDS_CIRC[i]
+                out.append(w[D * (12 + r) + k] - acc)
+        return out
+
+    def fill_witness(self, row, rnd):
+        P = pyref.P
+        for i in range(24):
+            row[i] = rnd.randrange(P)
+        for k in range(D):
+            res = pyref.mds([row[D * i + k] for i in range(12)])
+            for r in range(12):
+                row[D * (12 + r) + k] = res[r]
+
+
+class RandomAccessGate(Gate):
+    """gates/random_access.rs: per copy claimed = list[index] for a 2^bits list; index bits are unrouted wires after the
+    routed ones; `num_extra_constants` constant wires ride along."""
+
+    def __init__(self, bits=4, num_copies=None, num_extra_constants=None):
+        vs = 1 << bits
+        if num_copies is None:
+            num_copies = min(NUM_ROUTED // (2 + vs), NUM_WIRES // (2 + vs + bits))
+        if num_extra_constants is None:
+            num_extra_constants = min(2, NUM_ROUTED - (2 + vs) * num_copies)
+        self.bits, self.num_copies, self.num_extra = bits, num_copies, num_extra_constants
+        self.vs = vs
+        self.name = (f"RandomAccessGate {{ bits: {bits}, num_copies: {num_copies}, "
+                     f"num_extra_constants: {num_extra_constants} }}<D=2>")
+        self.degree, self.num_constants = bits + 1, num_extra_constants
+        self.num_constraints = num_copies * (bits + 2) + num_extra_constants
+
+    def num_routed(self): return (2 + self.vs) * self.num_copies + self.num_extra
+    def w_bit(self, i, copy): return self.num_routed() + copy * self.bits + i
+
+    def eval(self, w, c, pi):
+        out = []
+        for cp in range(self.num_copies):
+            b0 = (2 + self.vs) * cp
+            bits = [w[self.w_bit(i, cp)] for i in range(self.bits)]
+            for b in bits:
+                out.append(b * (b - 1))
+            rec = None
+            for b in reversed(bits):
+                rec = b if rec is None else rec * 2 + b
+            out.append(rec - w[b0])
+            items = [w[b0 + 2 + i] for i in range(self.vs)]
+            for b in bits:
+                items = [items[2 * k] + b * (items[2 * k + 1] - items[2 * k]) for k in range(len(items) // 2)]
+            out.append(items[0] - w[b0 + 1])
+        for i in range(self.num_extra):
+            out.append(c[i] - w[(2 + self.vs) * self.num_copies + i])
+        return out
+
+    def fill_witness(self, row, rnd, consts):
+        P = pyref.P
+        for cp in range(self.num_copies):
+            b0 = (2 + self.vs) * cp
+            idx = rnd.randrange(self.vs)
+            items = [rnd.randrange(P) for _ in range(self.vs)]
+            row[b0], row[b0 + 1] = idx, items[idx]
+            row[b0 + 2:b0 + 2 + self.vs] = items
+            for i in range(self.bits):
+                row[self.w_bit(i, cp)] = (idx >> i) & 1
+        for i in range(self.num_extra):
+            row[(2 + self.vs) * self.num_copies + i] = consts[i]

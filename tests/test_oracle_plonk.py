@@ -144,10 +144,11 @@ def run_program(words, wires, consts_cols, pi_hash, apow, num_perm_terms):
     return total
 
 
-def test_gate_programs_match_oracle_formulas():
+@pytest.mark.parametrize("mix", [None, synth.ALL_KINDS], ids=["default-mix", "all-18-gates"])
+def test_gate_programs_match_oracle_formulas(mix):
     """Random wires / constants (not a satisfying witness): the assembled bytecode and the oracle's direct
     formulas give the same filtered, alpha-reduced constraint sum -- for every gate type at once."""
-    circ, wires, pis = synth.build(5, seed=4)
+    circ, wires, pis = synth.build(5, seed=4) if mix is None else synth.build(6, seed=4, mix=mix)
     ids = [g.id() for g in circ.gates]
     prog = vgates.build_program(ids, circ.selector_index, circ.groups, circ.num_selectors)
     rnd = random.Random(8)
@@ -186,3 +187,48 @@ def test_poseidon_gate_program_is_satisfied_by_the_permutation():
     assert run_program(prog, row, [0], [0] * 4, apow, 22) == 0
     row[70] = (row[70] + 1) % P
     assert run_program(prog, row, [0], [0] * 4, apow, 22) != 0
+
+
+def test_every_gate_with_a_program_is_satisfied_by_its_honest_witness():
+    """The gates whose formulas are restated (in-tree sources for U32AddMany / Comparison, SURVEY Appendix B for the
+    upstream ones): an honest witness makes every constraint vanish over the base field, the vectorised field and the
+    extension field; random wires do not."""
+    from oracle import gates as og
+    from oracle.field import FA
+    rnd = random.Random(5)
+    cases = [(og.U32AddManyGate(3), (), ()), (og.U32AddManyGate(5), (), ()), (og.ComparisonGate(32, 16), (), ()),
+             (og.ComparisonGate(10, 5), (), ()), (og.ArithmeticExtensionGate(), (11, 13), (11, 13)),
+             (og.MulExtensionGate(), (17,), (17,)), (og.ReducingGate(), (), ()), (og.ReducingExtensionGate(), (), ()),
+             (og.ExponentiationGate(), (), ()), (og.PoseidonMdsGate(), (), ()), (og.RandomAccessGate(), ((5, 9),), (5, 9))]
+    for gate, fill_args, consts in cases:
+        for _ in range(4):
+            row = [0] * 135
+            gate.fill_witness(row, rnd, *fill_args)
+            out = gate.eval([FI(x) for x in row], [FI(x) for x in consts], [FI(0)] * 4)
+            assert len(out) == gate.num_constraints, gate.name
+            assert all(x.v == 0 for x in out), gate.name
+            oa = gate.eval([FA(np.array([x, x], dtype=np.uint64)) for x in row],
+                           [FA(np.array([x, x], dtype=np.uint64)) for x in consts], [FA(np.zeros(2, dtype=np.uint64))] * 4)
+            assert all((np.asarray(x.v) == 0).all() for x in oa), gate.name
+            oe = gate.eval([E2(x, 0) for x in row], [E2(x, 0) for x in consts], [E2(0, 0)] * 4)
+            assert all(x.a == 0 and x.b == 0 for x in oe), gate.name
+        w = [FI(rnd.randrange(P)) for _ in range(135)]
+        out = gate.eval(w, [FI(rnd.randrange(P)) for _ in range(4)], [FI(0)] * 4)
+        assert any(x.v != 0 for x in out), gate.name
+    g = og.ComparisonGate(32, 16)                      # equal inputs and both orders
+    for a, b in ((77, 77), (5, 9), (9, 5), (0, (1 << 32) - 1), ((1 << 32) - 1, 0)):
+        row = [0] * 135
+        g.fill_witness(row, rnd, a=a, b=b)
+        assert row[2] == (1 if a <= b else 0)
+        assert all(x.v == 0 for x in g.eval([FI(x) for x in row], [], [FI(0)] * 4))
+
+
+def test_oracle_proof_with_all_18_gate_types_verifies():
+    circ, wires, pis = synth.build(6, seed=11, mix=synth.ALL_KINDS)
+    assert len(circ.gates) == 18
+    proof = plonk.prove(circ, wires, pis)
+    assert plonk.verify(circ, proof)
+    rows = [r for r in range(circ.n) if circ.gates[circ.row_gate[r]].name.startswith("ComparisonGate")]
+    w2 = wires.copy()
+    w2[2, rows[0]] ^= np.uint64(1)                     # flip the comparison result
+    assert not plonk.verify(circ, plonk.prove(circ, w2, pis))

@@ -6,9 +6,11 @@ serialization/gates.rs:85-107) is built here by tracing Python statements of the
 symbolic values: arithmetic on `Sym` objects records SSA ops, which are register-allocated into the
 bytecode of include/vectorx_b200.h.
 
-Formulas: U32* gates follow the in-tree sources (frontend/uint/num/u32/gates/arithmetic_u32.rs:290-349,
-subtraction_u32.rs:235-271, range_check_u32.rs:93-115); the upstream plonky2 v0.2.0 gates follow
-SURVEY.md Appendix B.  PoseidonGate uses the fast partial-round tables exported by the library
+Formulas: U32* gates and ComparisonGate follow the in-tree sources (frontend/uint/num/u32/gates/
+arithmetic_u32.rs:290-349, subtraction_u32.rs:235-271, range_check_u32.rs:93-115, add_many_u32.rs:149-190,
+comparison.rs:333-410); the upstream plonky2 v0.2.0 gates follow SURVEY.md Appendix B.  18 of the 23 registered
+gate types have a program; CosetInterpolationGate, LookupGate, LookupTableGate (no lookups in VectorX),
+ArithmeticCubicGate and MulCubicGate (starkyx) need upstream source that is not in the reference tree.  PoseidonGate uses the fast partial-round tables exported by the library
 (vx_poseidon_fast_tables), like upstream's gate does.
 """
 from __future__ import annotations
@@ -316,6 +318,150 @@ def gate_poseidon(t, w, c, pi, params):
         t.emit(st[i] - w(12 + i))
 
 
+def gate_u32_add_many(t, w, c, pi, params):
+    """add_many_u32.rs:149-190"""
+    a, n = params["num_addends"], params["num_ops"]
+    for i in range(n):
+        b = (a + 3) * i
+        computed = _val(w(b + a))
+        for j in range(a):
+            computed = computed + w(b + j)
+        res, oc = w(b + a + 1), w(b + a + 2)
+        t.emit(oc * (1 << 32) + res - computed)
+        comb_res = comb_carry = None
+        for j in reversed(range(19)):
+            limb = w((a + 3) * n + 19 * i + j)
+            t.emit(_range4(limb))
+            if j < 16:
+                comb_res = limb if comb_res is None else _madk(comb_res, 4, limb)
+            else:
+                comb_carry = limb if comb_carry is None else _madk(comb_carry, 4, limb)
+        t.emit(comb_res - res)
+        t.emit(comb_carry - oc)
+
+
+def _range_product(x, size):
+    """prod_{k < size} (x - k)"""
+    if size == 4:
+        return _range4(x)
+    x = _val(x)
+    acc = x
+    for k in range(1, size):
+        acc = acc * (x - k)
+    return acc
+
+
+def gate_comparison(t, w, c, pi, params):
+    """comparison.rs:333-410"""
+    n, cb = params["num_chunks"], params["chunk_bits"]
+    t.emit(_horner([w(4 + i) for i in range(n)], 1 << cb) - w(0))
+    t.emit(_horner([w(4 + n + i) for i in range(n)], 1 << cb) - w(1))
+    msd = None
+    for i in range(n):
+        first, second = w(4 + i), w(4 + n + i)
+        t.emit(_range_product(first, 1 << cb))
+        t.emit(_range_product(second, 1 << cb))
+        diff = second - first
+        eq, inter = _val(w(4 + 3 * n + i)), _val(w(4 + 4 * n + i))
+        t.emit(diff * w(4 + 2 * n + i) - (1 - eq))
+        t.emit(eq * diff)
+        t.emit(inter - eq * msd if msd is not None else inter)
+        msd = inter + (1 - eq) * diff
+    t.emit(w(3) - msd)
+    bits = [w(4 + 5 * n + i) for i in range(cb + 1)]
+    for b in bits:
+        b = _val(b)
+        t.emit(b * (1 - b))
+    t.emit(w(3) + (1 << cb) - _horner(bits, 2))
+    t.emit(w(2) - bits[cb])
+
+
+def _ext_mul(a, b):
+    """(a0 + a1 x)(b0 + b1 x) mod x^2 - 7"""
+    a0, a1, b0, b1 = _val(a[0]), _val(a[1]), _val(b[0]), _val(b[1])
+    return a0 * b0 + a1 * b1 * 7, a0 * b1 + a1 * b0
+
+
+def gate_arithmetic_extension(t, w, c, pi, params):
+    c0, c1 = _val(c(0)), _val(c(1))
+    for i in range(params["num_ops"]):
+        b = 8 * i
+        pr = _ext_mul((w(b), w(b + 1)), (w(b + 2), w(b + 3)))
+        for k in range(2):
+            t.emit(w(b + 6 + k) - (pr[k] * c0 + w(b + 4 + k) * c1))
+
+
+def gate_mul_extension(t, w, c, pi, params):
+    c0 = _val(c(0))
+    for i in range(params["num_ops"]):
+        b = 6 * i
+        pr = _ext_mul((w(b), w(b + 1)), (w(b + 2), w(b + 3)))
+        for k in range(2):
+            t.emit(w(b + 4 + k) - pr[k] * c0)
+
+
+def gate_reducing(t, w, c, pi, params):
+    n, ext = params["num_coeffs"], params["ext"]
+    alpha = (_val(w(2)), _val(w(3)))
+    acc = (w(4), w(5))
+    for i in range(n):
+        a = 0 if i == n - 1 else 6 + n * (2 if ext else 1) + 2 * i
+        pr = _ext_mul(acc, alpha)
+        if ext:
+            t.emit(pr[0] + w(6 + 2 * i) - w(a))
+            t.emit(pr[1] + w(6 + 2 * i + 1) - w(a + 1))
+        else:
+            t.emit(pr[0] + w(6 + i) - w(a))
+            t.emit(pr[1] - w(a + 1))
+        acc = (w(a), w(a + 1))
+
+
+def gate_exponentiation(t, w, c, pi, params):
+    n = params["num_power_bits"]
+    base = _val(w(0))
+    for i in range(n):
+        bit = _val(w(1 + (n - 1 - i)))
+        factor = bit * base + (1 - bit)
+        if i == 0:
+            computed = factor
+        else:
+            prev = _val(w(2 + n + i - 1))
+            computed = prev * prev * factor
+        t.emit(computed - w(2 + n + i))
+    t.emit(w(1 + n) - w(2 + 2 * n - 1))
+
+
+def gate_poseidon_mds(t, w, c, pi, params):
+    for r in range(12):
+        for k in range(2):
+            acc = w(2 * r + k) * (MDS_CIRC[0] + (MDS_DIAG0 if r == 0 else 0))
+            for i in range(1, 12):
+                acc = acc + w(2 * ((i + r) % 12) + k) * MDS_CIRC[i]
+            t.emit(w(2 * (12 + r) + k) - acc)
+
+
+def gate_random_access(t, w, c, pi, params):
+    bits, copies, extra = params["bits"], params["num_copies"], params["num_extra_constants"]
+    vs = 1 << bits
+    routed = (2 + vs) * copies + extra
+    for cp in range(copies):
+        b0 = (2 + vs) * cp
+        bw = [_val(w(routed + cp * bits + i)) for i in range(bits)]
+        for b in bw:
+            t.emit(b * (b - 1))
+        t.emit(_horner(bw, 2) - w(b0))
+        items = [w(b0 + 2 + i) for i in range(vs)]
+        for b in bw:
+            nxt = []
+            for k in range(len(items) // 2):
+                x = _val(items[2 * k])
+                nxt.append(x + b * (items[2 * k + 1] - x))
+            items = nxt
+        t.emit(items[0] - w(b0 + 1))
+    for i in range(extra):
+        t.emit(c(i) - w((2 + vs) * copies + i))
+
+
 # id prefix -> (formula, parameter parser, degree, num_constants, num_constraints)
 def _p(name, key):
     import re
@@ -334,12 +480,30 @@ GATES = {
     "U32RangeCheckGate": (gate_u32_range_check, lambda s: {"num_input_limbs": _p(s, "num_input_limbs")},
                           lambda p: (4, 0, 17 * p["num_input_limbs"])),
     "PoseidonGate": (gate_poseidon, lambda s: {}, lambda p: (7, 0, 123)),
+    "U32AddManyGate": (gate_u32_add_many, lambda s: {"num_addends": _p(s, "num_addends"), "num_ops": _p(s, "num_ops")},
+                       lambda p: (4, 0, 22 * p["num_ops"])),
+    "ComparisonGate": (gate_comparison,
+                       lambda s: {"num_chunks": _p(s, "num_chunks"), "chunk_bits": -(-_p(s, "num_bits") // _p(s, "num_chunks"))},
+                       lambda p: (1 << p["chunk_bits"], 0, 6 + 5 * p["num_chunks"] + p["chunk_bits"])),
+    "ArithmeticExtensionGate": (gate_arithmetic_extension, lambda s: {"num_ops": _p(s, "num_ops")}, lambda p: (3, 2, 2 * p["num_ops"])),
+    "MulExtensionGate": (gate_mul_extension, lambda s: {"num_ops": _p(s, "num_ops")}, lambda p: (3, 1, 2 * p["num_ops"])),
+    "ReducingGate": (gate_reducing, lambda s: {"num_coeffs": _p(s, "num_coeffs"), "ext": False}, lambda p: (2, 0, 2 * p["num_coeffs"])),
+    "ReducingExtensionGate": (gate_reducing, lambda s: {"num_coeffs": _p(s, "num_coeffs"), "ext": True},
+                              lambda p: (2, 0, 2 * p["num_coeffs"])),
+    "ExponentiationGate": (gate_exponentiation, lambda s: {"num_power_bits": _p(s, "num_power_bits")},
+                           lambda p: (4, 0, p["num_power_bits"] + 1)),
+    "PoseidonMdsGate": (gate_poseidon_mds, lambda s: {}, lambda p: (1, 0, 24)),
+    "RandomAccessGate": (gate_random_access,
+                         lambda s: {"bits": _p(s, "bits"), "num_copies": _p(s, "num_copies"),
+                                    "num_extra_constants": _p(s, "num_extra_constants")},
+                         lambda p: (p["bits"] + 1, p["num_extra_constants"], p["num_copies"] * (p["bits"] + 2) + p["num_extra_constants"])),
 }
 
 
 def lookup(gate_id: str):
+    name = gate_id.split(" ")[0].split("<")[0]
     for prefix, entry in GATES.items():
-        if gate_id.startswith(prefix):
+        if name == prefix:
             fn, parse, meta = entry
             params = parse(gate_id)
             degree, num_constants, num_constraints = meta(params)
