@@ -40,6 +40,10 @@ typedef struct vx_tree vx_tree;     /* device-resident MerkleTree over row-major
 
 /* ---- context ------------------------------------------------------------------------------ */
 int32_t vx_ctx_create(int32_t device, vx_ctx** out);
+/* number of sm_100-class devices a context can be created on (0 when there is none; never fails).  The Rust side sizes
+ * its proof-level fan-out with it: LocalProver::batch_prove, P2X/backend/prover/local.rs:44-48, proves its independent
+ * inputs in a sequential loop; with one context per device they run side by side. */
+int32_t vx_device_count(void);
 void vx_ctx_destroy(vx_ctx* ctx);
 const char* vx_last_error(void);
 int32_t vx_device_sync(vx_ctx* ctx);

@@ -49,3 +49,37 @@ def test_prove_verifies_and_times(ctx):
         json.dump(rec, f, indent=1)
     print(json.dumps(rec))
     assert phases and total > 0
+
+
+def test_batch_prove_fan_out_throughput():
+    """LocalProver.batch_prove at the same size: proofs/s with one context, with two contexts on one GPU
+    (host-side gaps of one proof filled by the other) and with one context per visible GPU; record in
+    gpurun_out/prove_fanout.json.  Every proof of the widest run is compared with the single-context proof."""
+    from vectorx_b200.local_prover import CircuitSpec, LocalProver
+    bits = int(os.environ.get("VX_PROVE_BITS", "13"))
+    n_proofs = int(os.environ.get("VX_PROVE_BATCH", "16"))
+    circ, wires, pis = synth.build(bits, seed=11)
+    spec = CircuitSpec(circ.d, [g.id() for g in circ.gates], circ.selector_index, circ.groups, circ.constants, circ.sigmas)
+    n_dev = vx.device_count()
+    layouts = {"1 context": [0], "2 contexts on 1 GPU": [0, 0]}
+    if n_dev > 1:
+        layouts[f"{n_dev} GPUs x 1 context"] = list(range(n_dev))
+        layouts[f"{n_dev} GPUs x 2 contexts"] = list(range(n_dev)) * 2
+    rec = {"degree_bits": bits, "proofs_per_batch": n_proofs, "devices_visible": n_dev, "layouts": {}}
+    ref = None
+    for name, devices in layouts.items():
+        lp = LocalProver(devices=devices)
+        lp.batch_prove(spec, [(wires, pis)] * len(devices))      # warm-up: replicas, pools
+        t = time.perf_counter()
+        proofs = lp.batch_prove(spec, [(wires, pis)] * n_proofs)
+        dt = time.perf_counter() - t
+        rec["layouts"][name] = {"seconds": dt, "proofs_per_s": n_proofs / dt}
+        caps = [p["quotient_cap"].tolist() for p in proofs]
+        wits = [p["pow_witness"] for p in proofs]
+        if ref is None:
+            ref = (caps[0], wits[0])
+        assert all(c == ref[0] for c in caps) and all(w == ref[1] for w in wits)
+        lp.close()
+    with open(os.path.join(ROOT, "gpurun_out", "prove_fanout.json"), "w") as f:
+        json.dump(rec, f, indent=1)
+    print(json.dumps(rec))

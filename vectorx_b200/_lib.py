@@ -21,6 +21,7 @@ c_u64, c_u32, c_i32 = ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int32
 # name -> (restype, argtypes); must list every symbol declared in include/vectorx_b200.h
 SIGNATURES = {
     "vx_ctx_create": (c_i32, [c_i32, ctypes.POINTER(vp)]),
+    "vx_device_count": (c_i32, []),
     "vx_ctx_destroy": (None, [vp]),
     "vx_last_error": (ctypes.c_char_p, []),
     "vx_device_sync": (c_i32, [vp]),
@@ -158,6 +159,11 @@ class Context:
             self.close()
         except Exception:
             pass
+
+
+def device_count() -> int:
+    """sm_100-class devices visible to the library (0 without a GPU)."""
+    return int(load().vx_device_count())
 
 
 _default_ctx = {}

@@ -101,6 +101,17 @@ extern "C" void vx_ctx_destroy(vx_ctx* ctx) {
     delete ctx;
 }
 
+extern "C" int32_t vx_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int usable = 0;
+    for (int d = 0; d < n; d++) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, d) == cudaSuccess && prop.major == 10) usable++;
+        else cudaGetLastError();
+    }
+    return usable;
+}
 extern "C" int32_t vx_device_sync(vx_ctx* ctx) {
     VX_REQUIRE(ctx, "vx_device_sync: ctx is NULL");
     VX_CUDA(cudaStreamSynchronize(ctx->stream));

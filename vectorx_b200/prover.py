@@ -78,6 +78,11 @@ class CircuitData:
                                   self.num_gate_constraints, self.k_is.ctypes.data, self.program.ctypes.data,
                                   len(self.program))
 
+    def close(self):
+        """Release the device-resident prover data (before the context it lives on is destroyed)."""
+        self.constants_sigmas_commitment.close()
+        self.sigmas_dev.close()
+
     def fri_reduction_arity_bits(self):
         out, d = [], self.degree_bits
         while d > self.final_poly_bits and d + self.rate_bits - self.arity_bits >= self.cap_height:
