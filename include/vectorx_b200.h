@@ -229,6 +229,34 @@ int32_t vx_tree_leaves(vx_tree* t, const uint64_t* idx, uint32_t k, uint64_t* ro
 int32_t vx_tree_cap(vx_tree* t, uint64_t* cap_out);
 void vx_tree_free(vx_tree* t);
 
+/* ---- the wrapper-stage hasher: PoseidonBN128Hash over GoldilocksField --------------------------------------
+ * Replaces P2X/backend/wrapper/poseidon_bn128.rs:20-110 (`permution`: BN254 scalar field, t = 4, x^5, 8 + 56 rounds)
+ * and the Hasher impl P2X/backend/wrapper/plonky2_config.rs:128-197 (hash_no_pad: 3 canonical Goldilocks elements =
+ * 24 little-endian bytes per scalar, 3 scalars per permutation; hash_or_noop: up to 3 elements are the digest's own
+ * bytes; two_to_one: permute([0, 0, l, r])[0]) for MerkleTree::<F, PoseidonBN128Hash>::new (API use and tests at
+ * poseidon_bn128.rs:205-267).  A digest is one scalar = Fr::to_repr() = 32 little-endian bytes = 4 u64 words, canonical:
+ * the same size as a Goldilocks-Poseidon HashOut, so `digests`, caps and paths keep their layout.
+ * Known-answer test: poseidon_bn128.rs:134-181. */
+#define VX_HASHER_POSEIDON 0           /* PoseidonHash (PoseidonGoldilocksConfig) */
+#define VX_HASHER_POSEIDON_BN128 1     /* PoseidonBN128Hash (PoseidonBN128GoldilocksConfig) */
+/* MerkleTree::<F, H>::new with H chosen by `hasher`; otherwise identical to vx_merkle_new (which is hasher 0). */
+int32_t vx_merkle_new_hasher(vx_ctx* ctx, uint32_t hasher, const uint64_t* leaves, uint64_t n, uint32_t w,
+                             uint32_t cap_height, uint64_t* digests_out, uint64_t* cap_out, vx_tree** tree_out);
+/* PolynomialBatch::from_values / from_coeffs for a config whose Hasher is `hasher` (the wrap circuit's commitments). */
+int32_t vx_commit_from_values_hasher(vx_ctx* ctx, uint32_t hasher, const uint64_t* cols, uint32_t c, uint32_t log_n,
+                                     uint32_t rate_bits, uint32_t cap_height, vx_batch** out);
+int32_t vx_commit_from_coeffs_hasher(vx_ctx* ctx, uint32_t hasher, const uint64_t* coeffs, uint32_t c, uint32_t log_n,
+                                     uint32_t rate_bits, uint32_t cap_height, vx_batch** out);
+/* `count` independent permutations: states are 4 scalars x 4 u64 words (canonical, little-endian), host in/out.
+ * A word group >= the modulus is rejected with VX_EINVAL (Fr::from_repr fails in the reference). */
+int32_t vx_bn128_permute(vx_ctx* ctx, const uint64_t* states_in, uint64_t count, uint64_t* states_out);
+/* hash_no_pad (or_noop = 0) / hash_or_noop (or_noop = 1) of `count` inputs of `len` Goldilocks elements -> count x 4 */
+int32_t vx_bn128_hash(vx_ctx* ctx, const uint64_t* inputs, uint64_t count, uint32_t len, int32_t or_noop, uint64_t* out);
+/* The derived tables in the reference's layout (C_CONSTANTS[88], S_CONSTANTS[392], M_MATRIX[4][4], P_MATRIX[4][4] of
+ * P2X/backend/wrapper/poseidon_bn128_constants.rs), 4 u64 words per scalar, canonical.  Host only: needs no GPU and no
+ * context.  Any pointer may be NULL. */
+int32_t vx_bn128_constants(uint64_t* c88, uint64_t* s392, uint64_t* m16, uint64_t* p16);
+
 /* ---- hashing primitives (plonky2 hash/poseidon.rs, hash/hashing.rs; KAT at
  *      P2X/frontend/hash/poseidon/poseidon256.rs:163-202) --------------------------------------
  * Batched on the device: `count` independent permutations / hashes per call. Host in/out. */

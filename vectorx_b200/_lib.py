@@ -54,6 +54,12 @@ SIGNATURES = {
     "vx_batch_coeffs_device": (vp, [vp]),
     "vx_batch_digests_device": (vp, [vp]),
     "vx_merkle_new": (c_i32, [vp, vp, c_u64, c_u32, c_u32, vp, vp, ctypes.POINTER(vp)]),
+    "vx_merkle_new_hasher": (c_i32, [vp, c_u32, vp, c_u64, c_u32, c_u32, vp, vp, ctypes.POINTER(vp)]),
+    "vx_commit_from_values_hasher": (c_i32, [vp, c_u32, vp, c_u32, c_u32, c_u32, c_u32, ctypes.POINTER(vp)]),
+    "vx_commit_from_coeffs_hasher": (c_i32, [vp, c_u32, vp, c_u32, c_u32, c_u32, c_u32, ctypes.POINTER(vp)]),
+    "vx_bn128_permute": (c_i32, [vp, vp, c_u64, vp]),
+    "vx_bn128_hash": (c_i32, [vp, vp, c_u64, c_u32, c_i32, vp]),
+    "vx_bn128_constants": (c_i32, [vp, vp, vp, vp]),
     "vx_tree_prove": (c_i32, [vp, vp, c_u32, vp]),
     "vx_tree_leaves": (c_i32, [vp, vp, c_u32, vp]),
     "vx_tree_cap": (c_i32, [vp, vp]),

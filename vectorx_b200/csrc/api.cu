@@ -83,6 +83,7 @@ extern "C" int32_t vx_ctx_create(int32_t device, vx_ctx** out) {
     if (r == VX_OK) r = ntt_module_init(ctx);
     if (r == VX_OK) r = fri_module_init(ctx);
     if (r == VX_OK) r = prover_module_init(ctx);
+    if (r == VX_OK) r = bn128_module_init(ctx);
     if (r != VX_OK) { vx_ctx_destroy(ctx); return r; }
     *out = ctx;
     return VX_OK;
@@ -205,8 +206,8 @@ static int32_t commit_run(vx_ctx* ctx, vx_batch* b, const u64* src, bool is_valu
     }
     if (nchunks > 1) { EV(ctx, VX_EV_STAGED); EV(ctx, VX_EV_INTT); }      // phases interleave: all reported under "lde"
     EV(ctx, VX_EV_LDE);
-    VX_CHECK(merkle_build_device(ctx, b->lde.p, true, N_loc, N_loc, c, b->cap_height_loc(), b->digests.p, b->cap.p,
-                                 ctx->ev[VX_EV_LEAF]));
+    VX_CHECK(merkle_build_hasher(ctx, b->hasher, b->lde.p, true, N_loc, N_loc, c, b->cap_height_loc(), b->digests.p,
+                                 b->cap.p, ctx->ev[VX_EV_LEAF]));
     EV(ctx, VX_EV_TREE);
     VX_CUDA(cudaStreamSynchronize(ctx->stream));
     return VX_OK;
@@ -214,9 +215,10 @@ static int32_t commit_run(vx_ctx* ctx, vx_batch* b, const u64* src, bool is_valu
 
 static int32_t commit_impl(vx_ctx* ctx, const u64* src, bool is_values, uint32_t c, uint32_t log_n,
                            uint32_t rate_bits, uint32_t cap_height, uint32_t shard_index, uint32_t shard_count,
-                           vx_batch** out) {
+                           vx_batch** out, uint32_t hasher = VX_HASHER_POSEIDON) {
     VX_REQUIRE(ctx && src && out, "commit: NULL argument");
     *out = nullptr;
+    VX_REQUIRE(hasher <= VX_HASHER_POSEIDON_BN128, "commit: unknown hasher %u", hasher);
     VX_REQUIRE(c >= 1 && c < 16384, "commit: column count %u out of range", c);
     VX_REQUIRE(log_n + rate_bits <= 26, "commit: 2^%u LDE points unsupported", log_n + rate_bits);
     VX_REQUIRE(cap_height <= log_n + rate_bits, "commit: cap_height %u exceeds tree height %u", cap_height,
@@ -231,6 +233,7 @@ static int32_t commit_impl(vx_ctx* ctx, const u64* src, bool is_values, uint32_t
     vx_batch* b = new (std::nothrow) vx_batch();
     if (!b) return VX_ENOMEM;
     b->ctx = ctx; b->c = c; b->log_n = log_n; b->rate_bits = rate_bits; b->cap_height = cap_height;
+    b->hasher = hasher;
     b->blk_count = (1u << rate_bits) >> sbits;
     b->blk_first = shard_index * b->blk_count;
     int32_t r = commit_run(ctx, b, src, is_values);
@@ -250,6 +253,14 @@ extern "C" int32_t vx_commit_from_values(vx_ctx* ctx, const uint64_t* cols, uint
 extern "C" int32_t vx_commit_from_coeffs(vx_ctx* ctx, const uint64_t* coeffs, uint32_t c, uint32_t log_n,
                                          uint32_t rate_bits, uint32_t cap_height, vx_batch** out) {
     return commit_impl(ctx, (const u64*)coeffs, false, c, log_n, rate_bits, cap_height, 0, 1, out);
+}
+extern "C" int32_t vx_commit_from_values_hasher(vx_ctx* ctx, uint32_t hasher, const uint64_t* cols, uint32_t c,
+                                                uint32_t log_n, uint32_t rate_bits, uint32_t cap_height, vx_batch** out) {
+    return commit_impl(ctx, (const u64*)cols, true, c, log_n, rate_bits, cap_height, 0, 1, out, hasher);
+}
+extern "C" int32_t vx_commit_from_coeffs_hasher(vx_ctx* ctx, uint32_t hasher, const uint64_t* coeffs, uint32_t c,
+                                                uint32_t log_n, uint32_t rate_bits, uint32_t cap_height, vx_batch** out) {
+    return commit_impl(ctx, (const u64*)coeffs, false, c, log_n, rate_bits, cap_height, 0, 1, out, hasher);
 }
 extern "C" int32_t vx_commit_from_coeffs_shard(vx_ctx* ctx, const uint64_t* coeffs, uint32_t c, uint32_t log_n,
                                                uint32_t rate_bits, uint32_t cap_height, uint32_t shard_index,
@@ -372,10 +383,11 @@ struct vx_tree {
     DevBuf leaves, digests, cap;
 };
 
-extern "C" int32_t vx_merkle_new(vx_ctx* ctx, const uint64_t* leaves, uint64_t n, uint32_t w, uint32_t cap_height,
-                                 uint64_t* digests_out, uint64_t* cap_out, vx_tree** tree_out) {
+extern "C" int32_t vx_merkle_new_hasher(vx_ctx* ctx, uint32_t hasher, const uint64_t* leaves, uint64_t n, uint32_t w,
+                                        uint32_t cap_height, uint64_t* digests_out, uint64_t* cap_out, vx_tree** tree_out) {
     VX_REQUIRE(ctx && leaves, "vx_merkle_new: NULL argument");
     if (tree_out) *tree_out = nullptr;
+    VX_REQUIRE(hasher <= VX_HASHER_POSEIDON_BN128, "vx_merkle_new: unknown hasher %u", hasher);
     VX_REQUIRE(n >= 1 && (n & (n - 1)) == 0, "vx_merkle_new: leaf count %llu is not a power of two",
                (unsigned long long)n);
     VX_REQUIRE(w >= 1, "vx_merkle_new: empty leaves");
@@ -388,7 +400,7 @@ extern "C" int32_t vx_merkle_new(vx_ctx* ctx, const uint64_t* leaves, uint64_t n
     if (r == VX_OK) r = t->digests.alloc((size_t)2 * (n - (1ULL << cap_height)) * 4 * sizeof(u64), ctx->stream);
     if (r == VX_OK) r = t->cap.alloc((size_t)(1ULL << cap_height) * 4 * sizeof(u64), ctx->stream);
     if (r == VX_OK) r = copy_in(ctx, t->leaves.p, (const u64*)leaves, t->leaves.bytes);
-    if (r == VX_OK) r = merkle_build_device(ctx, t->leaves.p, false, 0, n, w, cap_height, t->digests.p, t->cap.p);
+    if (r == VX_OK) r = merkle_build_hasher(ctx, hasher, t->leaves.p, false, 0, n, w, cap_height, t->digests.p, t->cap.p);
     if (r == VX_OK && digests_out && t->digests.bytes) r = copy_out(ctx, (u64*)digests_out, t->digests.p, t->digests.bytes);
     if (r == VX_OK && cap_out) r = copy_out(ctx, (u64*)cap_out, t->cap.p, t->cap.bytes);
     if (r == VX_OK) {
@@ -402,6 +414,11 @@ extern "C" int32_t vx_merkle_new(vx_ctx* ctx, const uint64_t* leaves, uint64_t n
     }
     *tree_out = t;
     return VX_OK;
+}
+
+extern "C" int32_t vx_merkle_new(vx_ctx* ctx, const uint64_t* leaves, uint64_t n, uint32_t w, uint32_t cap_height,
+                                 uint64_t* digests_out, uint64_t* cap_out, vx_tree** tree_out) {
+    return vx_merkle_new_hasher(ctx, VX_HASHER_POSEIDON, leaves, n, w, cap_height, digests_out, cap_out, tree_out);
 }
 
 extern "C" int32_t vx_tree_prove(vx_tree* t, const uint64_t* idx, uint32_t k, uint64_t* siblings_out) {
@@ -455,6 +472,45 @@ extern "C" int32_t vx_hash_no_pad(vx_ctx* ctx, const uint64_t* in, uint64_t coun
     VX_CHECK(b.alloc(count * 4 * sizeof(u64), ctx->stream));
     if (len) VX_CHECK(copy_in(ctx, a.p, (const u64*)in, a.bytes));
     VX_CHECK(hash_no_pad_device(ctx, a.p, count, len, b.p));
+    VX_CHECK(copy_out(ctx, (u64*)out, b.p, b.bytes));
+    VX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VX_OK;
+}
+
+// ---- PoseidonBN128Hash primitives (bn128.cu)
+static bool bn128_words_canonical(const uint64_t* w) {
+    static const uint64_t N[4] = {0x43e1f593f0000001ULL, 0x2833e84879b97091ULL, 0xb85045b68181585dULL, 0x30644e72e131a029ULL};
+    for (int i = 3; i >= 0; i--)
+        if (w[i] != N[i]) return w[i] < N[i];
+    return false;
+}
+extern "C" int32_t vx_bn128_permute(vx_ctx* ctx, const uint64_t* in, uint64_t count, uint64_t* out) {
+    VX_REQUIRE(ctx && (count == 0 || (in && out)), "vx_bn128_permute: NULL argument");
+    if (count == 0) return VX_OK;
+    for (uint64_t i = 0; i < 4 * count; i++)
+        VX_REQUIRE(bn128_words_canonical(in + 4 * i), "vx_bn128_permute: scalar %llu is not below the BN254 scalar modulus",
+                   (unsigned long long)i);
+    CtxGuard g(ctx);
+    DevBuf a, b;
+    VX_CHECK(a.alloc(count * 16 * sizeof(u64), ctx->stream));
+    VX_CHECK(b.alloc(count * 16 * sizeof(u64), ctx->stream));
+    VX_CHECK(copy_in(ctx, a.p, (const u64*)in, a.bytes));
+    VX_CHECK(bn128_permute_device(ctx, a.p, count, b.p));
+    VX_CHECK(copy_out(ctx, (u64*)out, b.p, b.bytes));
+    VX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VX_OK;
+}
+extern "C" int32_t vx_bn128_hash(vx_ctx* ctx, const uint64_t* in, uint64_t count, uint32_t len, int32_t or_noop,
+                                 uint64_t* out) {
+    VX_REQUIRE(ctx && (count == 0 || out), "vx_bn128_hash: NULL argument");
+    VX_REQUIRE(len == 0 || in, "vx_bn128_hash: NULL input");
+    if (count == 0) return VX_OK;
+    CtxGuard g(ctx);
+    DevBuf a, b;
+    VX_CHECK(a.alloc((size_t)count * len * sizeof(u64), ctx->stream));
+    VX_CHECK(b.alloc(count * 4 * sizeof(u64), ctx->stream));
+    if (len) VX_CHECK(copy_in(ctx, a.p, (const u64*)in, a.bytes));
+    VX_CHECK(bn128_hash_device(ctx, a.p, count, len, or_noop != 0, b.p));
     VX_CHECK(copy_out(ctx, (u64*)out, b.p, b.bytes));
     VX_CUDA(cudaStreamSynchronize(ctx->stream));
     return VX_OK;

@@ -137,6 +137,7 @@ struct vx_batch {
     vx_ctx* ctx;
     uint32_t c, log_n, rate_bits, cap_height;
     uint32_t blk_first, blk_count;      // leaf blocks (cosets) held: all 2^rate_bits unless sharded
+    uint32_t hasher = 0;                // VX_HASHER_*
     DevBuf coeffs;    // c x n
     DevBuf lde;       // c x N_loc column-major, leaf order
     DevBuf digests;   // 2 (N_loc - caps_loc) x 4
@@ -169,6 +170,22 @@ int32_t transpose_to_rows_device(vx_ctx* ctx, const u64* colmajor, uint64_t stri
                                  u64* rows_dev);
 int32_t poseidon_permute_device(vx_ctx* ctx, const u64* in, uint64_t count, u64* out);
 int32_t hash_no_pad_device(vx_ctx* ctx, const u64* in, uint64_t count, uint32_t len, u64* out);
+
+// bn128.cu: the wrapper-stage hasher (PoseidonBN128Hash); same digest size and tree layout as above --------------
+int32_t bn128_module_init(vx_ctx* ctx);
+int32_t bn128_merkle_build_device(vx_ctx* ctx, const u64* leaves, bool col_major, uint64_t stride, uint64_t N,
+                                  uint32_t c, uint32_t cap_height, u64* digests, u64* cap,
+                                  cudaEvent_t after_leaves = nullptr);
+int32_t bn128_permute_device(vx_ctx* ctx, const u64* in, uint64_t count, u64* out);      // count x 4 scalars x 4 words
+int32_t bn128_hash_device(vx_ctx* ctx, const u64* in, uint64_t count, uint32_t len, bool or_noop, u64* out);
+// dispatch on VX_HASHER_*
+static inline int32_t merkle_build_hasher(vx_ctx* ctx, uint32_t hasher, const u64* leaves, bool col_major, uint64_t stride,
+                                          uint64_t N, uint32_t c, uint32_t cap_height, u64* digests, u64* cap,
+                                          cudaEvent_t after_leaves = nullptr) {
+    return hasher == VX_HASHER_POSEIDON_BN128
+               ? bn128_merkle_build_device(ctx, leaves, col_major, stride, N, c, cap_height, digests, cap, after_leaves)
+               : merkle_build_device(ctx, leaves, col_major, stride, N, c, cap_height, digests, cap, after_leaves);
+}
 
 // ntt.cu ------------------------------------------------------------------------------------------
 int32_t ntt_module_init(vx_ctx* ctx);

@@ -18,6 +18,11 @@ from ._lib import Context, VxError, check, default_context, load, ptr, vp
 
 P = 0xFFFFFFFF00000001
 
+# Hasher of a GenericConfig: PoseidonGoldilocksConfig::Hasher = PoseidonHash; the wrap circuit's
+# PoseidonBN128GoldilocksConfig::Hasher = PoseidonBN128Hash (P2X/backend/wrapper/plonky2_config.rs:19-27)
+POSEIDON_HASH = 0
+POSEIDON_BN128_HASH = 1
+
 
 def reverse_bits(x: int, bits: int) -> int:
     r = 0
@@ -47,23 +52,24 @@ class MerkleProof:
 
 
 class MerkleTree:
-    """plonky2 hash/merkle_tree.rs MerkleTree<F, PoseidonHash>."""
+    """plonky2 hash/merkle_tree.rs MerkleTree<F, H>, H = PoseidonHash (default) or PoseidonBN128Hash."""
 
-    def __init__(self, ctx: Context, handle, n: int, w: int, cap_height: int):
+    def __init__(self, ctx: Context, handle, n: int, w: int, cap_height: int, hasher: int = POSEIDON_HASH):
         self._ctx, self._h, self.n, self.w, self.cap_height = ctx, handle, n, w, cap_height
+        self.hasher = hasher
         self._cap = None
 
     @classmethod
-    def new(cls, leaves, cap_height: int, ctx: Context | None = None) -> "MerkleTree":
-        """MerkleTree::new(leaves, cap_height); leaves is an (n, w) uint64 array (host) or tensor."""
+    def new(cls, leaves, cap_height: int, ctx: Context | None = None, hasher: int = POSEIDON_HASH) -> "MerkleTree":
+        """MerkleTree::<F, H>::new(leaves, cap_height); leaves is an (n, w) uint64 array (host) or tensor."""
         ctx = ctx or default_context()
         n, w = int(leaves.shape[0]), int(leaves.shape[1])
         if isinstance(leaves, np.ndarray):
             leaves = np.ascontiguousarray(leaves, dtype=np.uint64)
         h = vp()
-        check(load().vx_merkle_new(ctx.handle, ptr(leaves), n, w, cap_height, None, None, ctypes.byref(h)),
-              "vx_merkle_new")
-        return cls(ctx, h, n, w, cap_height)
+        check(load().vx_merkle_new_hasher(ctx.handle, hasher, ptr(leaves), n, w, cap_height, None, None,
+                                          ctypes.byref(h)), "vx_merkle_new")
+        return cls(ctx, h, n, w, cap_height, hasher)
 
     @property
     def cap(self) -> MerkleCap:
@@ -104,15 +110,15 @@ class MerkleTree:
             pass
 
 
-def merkle_tree_digests(leaves: np.ndarray, cap_height: int, ctx: Context | None = None):
+def merkle_tree_digests(leaves: np.ndarray, cap_height: int, ctx: Context | None = None, hasher: int = POSEIDON_HASH):
     """MerkleTree::new returning the host-layout (digests, cap) -- what `.circuit` serialisation stores."""
     ctx = ctx or default_context()
     leaves = np.ascontiguousarray(leaves, dtype=np.uint64)
     n, w = leaves.shape
     digests = np.zeros((max(2 * (n - (1 << cap_height)), 0), 4), dtype=np.uint64)
     cap = np.zeros((1 << cap_height, 4), dtype=np.uint64)
-    check(load().vx_merkle_new(ctx.handle, ptr(leaves), n, w, cap_height,
-                               ptr(digests) if digests.size else None, ptr(cap), None), "vx_merkle_new")
+    check(load().vx_merkle_new_hasher(ctx.handle, hasher, ptr(leaves), n, w, cap_height,
+                                      ptr(digests) if digests.size else None, ptr(cap), None), "vx_merkle_new")
     return digests, cap
 
 
@@ -132,14 +138,14 @@ class PolynomialBatch:
 
     @classmethod
     def from_values(cls, values, rate_bits: int, blinding: bool, cap_height: int, timing=None,
-                    fft_root_table=None, ctx: Context | None = None) -> "PolynomialBatch":
+                    fft_root_table=None, ctx: Context | None = None, hasher: int = POSEIDON_HASH) -> "PolynomialBatch":
         """values: (c, n) uint64 array/tensor, polynomial j = values[j] (evaluations on the subgroup)."""
-        return cls._commit("vx_commit_from_values", values, rate_bits, blinding, cap_height, ctx)
+        return cls._commit("vx_commit_from_values_hasher", values, rate_bits, blinding, cap_height, ctx, hasher)
 
     @classmethod
     def from_coeffs(cls, polynomials, rate_bits: int, blinding: bool, cap_height: int, timing=None,
-                    fft_root_table=None, ctx: Context | None = None) -> "PolynomialBatch":
-        return cls._commit("vx_commit_from_coeffs", polynomials, rate_bits, blinding, cap_height, ctx)
+                    fft_root_table=None, ctx: Context | None = None, hasher: int = POSEIDON_HASH) -> "PolynomialBatch":
+        return cls._commit("vx_commit_from_coeffs_hasher", polynomials, rate_bits, blinding, cap_height, ctx, hasher)
 
     @classmethod
     def from_coeffs_shard(cls, polynomials, rate_bits: int, cap_height: int, shard_index: int, shard_count: int,
@@ -156,7 +162,7 @@ class PolynomialBatch:
         return cls(ctx, h)
 
     @classmethod
-    def _commit(cls, fn, data, rate_bits, blinding, cap_height, ctx):
+    def _commit(cls, fn, data, rate_bits, blinding, cap_height, ctx, hasher=POSEIDON_HASH):
         if blinding:
             raise VxError("blinding=true is unsupported (zero_knowledge=false in standard_recursion_config)")
         ctx = ctx or default_context()
@@ -167,7 +173,7 @@ class PolynomialBatch:
         if isinstance(data, np.ndarray):
             data = np.ascontiguousarray(data, dtype=np.uint64)
         h = vp()
-        check(getattr(load(), fn)(ctx.handle, ptr(data), c, log_n, rate_bits, cap_height, ctypes.byref(h)), fn)
+        check(getattr(load(), fn)(ctx.handle, hasher, ptr(data), c, log_n, rate_bits, cap_height, ctypes.byref(h)), fn)
         return cls(ctx, h)
 
     # -- merkle_tree view -------------------------------------------------------------------------
@@ -255,6 +261,33 @@ def hash_n_to_hash_no_pad(inputs: np.ndarray, ctx: Context | None = None) -> np.
     out = np.zeros((count, 4), dtype=np.uint64)
     check(load().vx_hash_no_pad(ctx.handle, ptr(inputs) if ln else None, count, ln, ptr(out)), "vx_hash_no_pad")
     return out
+
+
+def poseidon_bn128(states: np.ndarray, ctx: Context | None = None) -> np.ndarray:
+    """`permution` (P2X/backend/wrapper/poseidon_bn128.rs:20-25), batched: states (count, 4 scalars, 4 u64 words)."""
+    ctx = ctx or default_context()
+    states = np.ascontiguousarray(states, dtype=np.uint64).reshape(-1, 4, 4)
+    out = np.zeros_like(states)
+    check(load().vx_bn128_permute(ctx.handle, ptr(states), states.shape[0], ptr(out)), "vx_bn128_permute")
+    return out
+
+
+def poseidon_bn128_hash(inputs: np.ndarray, or_noop: bool = False, ctx: Context | None = None) -> np.ndarray:
+    """PoseidonBN128Hash::hash_no_pad / hash_or_noop (plonky2_config.rs:135-187), batched: (count, len) -> (count, 4)."""
+    ctx = ctx or default_context()
+    inputs = np.ascontiguousarray(inputs, dtype=np.uint64)
+    count, ln = inputs.shape
+    out = np.zeros((count, 4), dtype=np.uint64)
+    check(load().vx_bn128_hash(ctx.handle, ptr(inputs) if ln else None, count, ln, int(or_noop), ptr(out)),
+          "vx_bn128_hash")
+    return out
+
+
+def poseidon_bn128_constants():
+    """(C[88], S[392], M[16], P[16]) as Python ints, in the reference's layout (host-side derivation, no GPU)."""
+    bufs = [np.zeros((k, 4), dtype=np.uint64) for k in (88, 392, 16, 16)]
+    check(load().vx_bn128_constants(*[ptr(b) for b in bufs]), "vx_bn128_constants")
+    return tuple([sum(int(w) << (64 * i) for i, w in enumerate(row)) for row in b] for b in bufs)
 
 
 def poseidon_round_constants() -> np.ndarray:
