@@ -542,7 +542,7 @@ def verify(circ: Circuit, proof: dict) -> bool:
         return False
     for q in proof["queries"]:
         x_index = ch.get_challenge() % N
-        if x_index != q["x_index"]:
+        if q.get("x_index") is not None and x_index != q["x_index"]:      # not part of the proof bytes: derived here
             return False
         rows = []
         for (row, path), cap in zip(q["initial"], caps0):
@@ -587,3 +587,62 @@ def verify(circ: Circuit, proof: dict) -> bool:
         if not (fin == old):
             return False
     return True
+
+
+# ------------------------------------------------------------------------------------------------ proof bytes
+def proof_bytes(proof: dict) -> bytes:
+    """bincode 1.x (little-endian, fixed-width) of plonky2 v0.2.0's serde-derived `ProofWithPublicInputs`, the
+    bytes the reference hex-encodes at contracts/lib/succinctx/plonky2x/core/src/utils/serde/mod.rs:82-96.
+    Written field by field with struct.pack, independently of vectorx_b200/proof_io.py.  PARITY UNPINNED: the field
+    order restates plonk/proof.rs and fri/proof.rs of the un-vendored crate; the reference holds no golden bytes."""
+    import struct
+    b = bytearray()
+
+    def u64(v):
+        b.extend(struct.pack("<Q", int(v)))
+
+    def hash_vec(hs):
+        hs = [list(h) for h in np.asarray(hs).reshape(-1, 4)]
+        u64(len(hs))
+        for h in hs:
+            for x in h:
+                u64(x)
+
+    def ext_vec(es):
+        u64(len(es))
+        for e in es:
+            a, c = (e.a, e.b) if isinstance(e, E2) else (e[0], e[1])
+            u64(a)
+            u64(c)
+
+    hash_vec(proof["wires_cap"])
+    hash_vec(proof["zs_pp_cap"])
+    hash_vec(proof["quotient_cap"])
+    o = proof["openings"]
+    for name in ("constants", "plonk_sigmas", "wires", "plonk_zs", "plonk_zs_next", "partial_products", "quotient_polys"):
+        ext_vec(o[name])
+    u64(0)                                  # lookup_zs: no lookup tables anywhere in plonky2x / VectorX
+    u64(0)                                  # lookup_zs_next
+    u64(len(proof["fri_caps"]))
+    for cap in proof["fri_caps"]:
+        hash_vec(cap)
+    u64(len(proof["queries"]))
+    for q in proof["queries"]:
+        u64(len(q["initial"]))              # FriInitialTreeProof.evals_proofs: Vec<(Vec<F>, MerkleProof)>
+        for row, path in q["initial"]:
+            u64(len(row))
+            for x in row:
+                u64(x)
+            hash_vec(path)
+        u64(len(q["steps"]))                # Vec<FriQueryStep { evals: Vec<Ext>, merkle_proof }>
+        for evals, path in q["steps"]:
+            u64(len(evals) // 2)
+            for x in evals:
+                u64(x)
+            hash_vec(path)
+    ext_vec(proof["final_poly"])
+    u64(proof["pow_witness"])
+    u64(len(proof["public_inputs"]))
+    for x in proof["public_inputs"]:
+        u64(x)
+    return bytes(b)

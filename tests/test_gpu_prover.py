@@ -138,6 +138,11 @@ def test_full_proof_equals_oracle_and_verifies(case):
     for key in ("caps", "openings", "fri_caps", "final_poly", "pow_witness"):
         assert a[key] == b[key], key
     assert a["queries"] == b["queries"]
+    # proof BYTES (bincode of ProofWithPublicInputs, serde/mod.rs:82-96): product serializer on the GPU proof ==
+    # the oracle's own serializer on the oracle proof; and the bytes read back verify
+    data = vx.proof_to_bytes(gp)
+    assert data == plonk.proof_bytes(proof)
+    assert plonk.verify(circ, to_oracle_proof(vx.proof_from_bytes(data)))
     assert plonk.verify(circ, to_oracle_proof(gp))              # the unchanged (oracle) verifier accepts the GPU proof
     bad = to_oracle_proof(gp)
     bad["final_poly"][0] = bad["final_poly"][0] + 1
@@ -158,3 +163,4 @@ def test_proofs_of_other_shapes_verify(ctx, degree_bits, mix):
     if degree_bits <= 6:
         op = plonk.prove(circ, wires, pis)
         assert normalise(gp) == normalise(op)
+        assert vx.proof_to_bytes(gp) == plonk.proof_bytes(op)

@@ -10,3 +10,4 @@ from .plonky2 import (MerkleCap, MerkleProof, MerkleTree, PolynomialBatch, hash_
 from .prover import CircuitData, prove  # noqa: F401,E402
 from .challenger import Challenger, hash_no_pad_host, poseidon_host  # noqa: F401,E402
 from .local_prover import CircuitSpec, LocalProver  # noqa: F401,E402
+from .proof_io import proof_from_bytes, proof_from_hex, proof_to_bytes, proof_to_hex  # noqa: F401,E402
