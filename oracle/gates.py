@@ -652,3 +652,136 @@ class RandomAccessGate(Gate):
                 row[self.w_bit(i, cp)] = (idx >> i) & 1
         for i in range(self.num_extra):
             row[(2 + self.vs) * self.num_copies + i] = consts[i]
+
+
+def coset_interpolation_shape(subgroup_bits: int, max_degree: int):
+    """gates/coset_interpolation.rs `with_max_degree`: (degree, num_intermediates) for a 2^subgroup_bits-point coset."""
+    n_points = 1 << subgroup_bits
+    n_intermediates = (n_points - 2) // (max_degree - 1)
+    degree = (n_points - 2) // (n_intermediates + 1) + 2
+    return degree, (n_points - 2) // (degree - 1)
+
+
+def coset_interpolation_tables(subgroup_bits: int):
+    """(domain, barycentric weights): domain = two_adic_subgroup in natural order, w_i = 1 / prod_{j != i} (x_i - x_j)."""
+    P = pyref.P
+    g = pyref.primitive_root_of_unity(subgroup_bits)
+    dom = [pow(g, i, P) for i in range(1 << subgroup_bits)]
+    weights = []
+    for i, xi in enumerate(dom):
+        d = 1
+        for j, xj in enumerate(dom):
+            if j != i:
+                d = d * (xi - xj) % P
+        weights.append(pow(d, P - 2, P))
+    return dom, weights
+
+
+class CosetInterpolationGate(Gate):
+    """gates/coset_interpolation.rs (plonky2 v0.2.0; restated -- the upstream source is not in the reference tree, so wire
+    order and constraint order are anchored only by the honest-witness and prove -> verify self-checks): barycentric
+    interpolation of 2^subgroup_bits extension values given on the coset shift*<w>, evaluated at an extension point.
+    Wires: shift 0; values 1 + D i; evaluation point, evaluation value after them (end of the routed wires); then
+    `num_intermediates` partial evaluations, as many partial products, and the shifted evaluation point point/shift.
+    Constraints: point - shifted*shift; per intermediate (eval, prod) against the fold over the next degree-1 points;
+    value - final eval.  Fold step: eval' = eval (x - x_i) + w_i v_i prod, prod' = prod (x - x_i)."""
+
+    def __init__(self, subgroup_bits=4, max_degree=8):
+        self.bits = subgroup_bits
+        self.np = 1 << subgroup_bits
+        self.deg, self.ni = coset_interpolation_shape(subgroup_bits, max_degree)
+        self.domain, self.weights = coset_interpolation_tables(subgroup_bits)
+        self.name = (f"CosetInterpolationGate {{ subgroup_bits: {subgroup_bits}, degree: {self.deg}, "
+                     f"barycentric_weights: {self.weights}, _phantom: PhantomData<plonky2_field::goldilocks_field::"
+                     f"GoldilocksField> }}<D=2>")
+        self.degree, self.num_constants = self.deg, 0
+        self.num_constraints = D * (2 + 2 * self.ni)
+
+    def w_value(self, i): return 1 + D * i
+    def w_point(self): return 1 + D * self.np
+    def w_eval_value(self): return self.w_point() + D
+    def start_intermediates(self): return self.w_eval_value() + D
+    def num_routed(self): return self.start_intermediates()
+    def w_inter_eval(self, i): return self.start_intermediates() + D * i
+    def w_inter_prod(self, i): return self.start_intermediates() + D * (self.ni + i)
+    def w_shifted(self): return self.start_intermediates() + D * 2 * self.ni
+    def end(self): return self.start_intermediates() + D * (2 * self.ni + 1)
+
+    def chunks(self):
+        """Point ranges folded between consecutive (intermediate) constraints."""
+        out = [(0, self.deg)]
+        for i in range(self.ni):
+            s = 1 + (self.deg - 1) * (i + 1)
+            out.append((s, min(s + self.deg - 1, self.np)))
+        return out
+
+    def _fold(self, w, lo, hi, x, ev, pr):
+        for i in range(lo, hi):
+            term = (x[0] - self.domain[i], x[1])
+            v = (w[self.w_value(i)] * self.weights[i], w[self.w_value(i) + 1] * self.weights[i])
+            vp = ext_mul(v, pr)
+            et = ext_mul(ev, term)
+            ev = (et[0] + vp[0], et[1] + vp[1])
+            pr = ext_mul(pr, term)
+        return ev, pr
+
+    def eval(self, w, c, pi):
+        shift = w[0]
+        pt, sh = self.w_point(), self.w_shifted()
+        x = (w[sh], w[sh + 1])
+        out = [w[pt] - x[0] * shift, w[pt + 1] - x[1] * shift]
+        ch = self.chunks()
+        zero, one = w[0] * 0, w[0] * 0 + 1
+        ev, pr = self._fold(w, ch[0][0], ch[0][1], x, (zero, zero), (one, zero))
+        for i in range(self.ni):
+            ie, ip = self.w_inter_eval(i), self.w_inter_prod(i)
+            out += [w[ie] - ev[0], w[ie + 1] - ev[1], w[ip] - pr[0], w[ip + 1] - pr[1]]
+            ev, pr = self._fold(w, ch[i + 1][0], ch[i + 1][1], x, (w[ie], w[ie + 1]), (w[ip], w[ip + 1]))
+        e = self.w_eval_value()
+        out += [w[e] - ev[0], w[e + 1] - ev[1]]
+        return out
+
+    def fill_witness(self, row, rnd):
+        P = pyref.P
+        shift = rnd.randrange(1, P)
+        row[0] = shift
+        for i in range(D * self.np):
+            row[1 + i] = rnd.randrange(P)
+        point = (rnd.randrange(P), rnd.randrange(P))
+        inv = pow(shift, P - 2, P)
+        x = (point[0] * inv % P, point[1] * inv % P)
+        row[self.w_point()], row[self.w_point() + 1] = point
+        row[self.w_shifted()], row[self.w_shifted() + 1] = x
+
+        def fold(lo, hi, ev, pr):
+            for i in range(lo, hi):
+                term = ((x[0] - self.domain[i]) % P, x[1])
+                v = (row[self.w_value(i)] * self.weights[i] % P, row[self.w_value(i) + 1] * self.weights[i] % P)
+                vp, et = _ext_mul_int(v, pr), _ext_mul_int(ev, term)
+                ev = ((et[0] + vp[0]) % P, (et[1] + vp[1]) % P)
+                pr = _ext_mul_int(pr, term)
+            return ev, pr
+        ch = self.chunks()
+        ev, pr = fold(ch[0][0], ch[0][1], (0, 0), (1, 0))
+        for i in range(self.ni):
+            row[self.w_inter_eval(i)], row[self.w_inter_eval(i) + 1] = ev
+            row[self.w_inter_prod(i)], row[self.w_inter_prod(i) + 1] = pr
+            ev, pr = fold(ch[i + 1][0], ch[i + 1][1], ev, pr)
+        row[self.w_eval_value()], row[self.w_eval_value() + 1] = ev
+        return x, ev
+
+    def interpolate_direct(self, row, x):
+        """Lagrange interpolation of the wired values at x (independent of the fold): the value the gate must output."""
+        P = pyref.P
+        acc = (0, 0)
+        for i in range(self.np):
+            num = (1, 0)
+            den = 1
+            for j in range(self.np):
+                if j != i:
+                    num = _ext_mul_int(num, ((x[0] - self.domain[j]) % P, x[1]))
+                    den = den * (self.domain[i] - self.domain[j]) % P
+            li = pow(den, P - 2, P)
+            t = _ext_mul_int((row[self.w_value(i)], row[self.w_value(i) + 1]), num)
+            acc = ((acc[0] + t[0] * li) % P, (acc[1] + t[1] * li) % P)
+        return acc

@@ -11,13 +11,14 @@ import numpy as np
 
 from . import P, hash_no_pad
 from .gates import (ArithmeticExtensionGate, ArithmeticGate, BaseSumGate, ComparisonGate, ConstantGate,
+                    CosetInterpolationGate,
                     ExponentiationGate, MulExtensionGate, NoopGate, PoseidonGate, PoseidonMdsGate, PublicInputGate,
                     RandomAccessGate, ReducingExtensionGate, ReducingGate, U32AddManyGate, U32ArithmeticGate,
                     U32RangeCheckGate, U32SubtractionGate, NUM_WIRES)
 
-# every gate kind with a constraint program (18 of the 23 registered types)
+# every gate kind with a constraint program (19 of the 23 registered types)
 ALL_KINDS = ("poseidon", "arith", "const", "u32arith", "u32sub", "u32range", "basesum", "u32addmany", "comparison",
-             "arithext", "mulext", "reducing", "reducingext", "exp", "poseidonmds", "randomaccess")
+             "arithext", "mulext", "reducing", "reducingext", "exp", "poseidonmds", "randomaccess", "cosetinterp")
 from .plonk import Circuit, Config
 
 
@@ -29,10 +30,10 @@ def build(degree_bits: int, seed: int = 1, mix=("poseidon", "arith", "const", "u
     gates = [NoopGate(), PublicInputGate(), ConstantGate(2), ArithmeticGate(20), PoseidonGate(),
              U32ArithmeticGate(3), U32SubtractionGate(6), U32RangeCheckGate(7), BaseSumGate(63),
              U32AddManyGate(3), ComparisonGate(32, 16), ArithmeticExtensionGate(), MulExtensionGate(), ReducingGate(),
-             ReducingExtensionGate(), ExponentiationGate(), PoseidonMdsGate(), RandomAccessGate()]
+             ReducingExtensionGate(), ExponentiationGate(), PoseidonMdsGate(), RandomAccessGate(), CosetInterpolationGate()]
     G = {"noop": 0, "pi": 1, "const": 2, "arith": 3, "poseidon": 4, "u32arith": 5, "u32sub": 6, "u32range": 7, "basesum": 8,
          "u32addmany": 9, "comparison": 10, "arithext": 11, "mulext": 12, "reducing": 13, "reducingext": 14, "exp": 15,
-         "poseidonmds": 16, "randomaccess": 17}
+         "poseidonmds": 16, "randomaccess": 17, "cosetinterp": 18}
     used = sorted({G[m] for m in mix} | {0, 1})
     gates_used = [gates[i] for i in used]
     gidx = {g: i for i, g in enumerate(used)}
@@ -108,7 +109,7 @@ def build(degree_bits: int, seed: int = 1, mix=("poseidon", "arith", "const", "u
             w[0] = v
             for j in range(63):
                 w[1 + j] = (v >> j) & 1
-        elif kind in ("u32addmany", "comparison", "reducing", "reducingext", "exp", "poseidonmds"):
+        elif kind in ("u32addmany", "comparison", "reducing", "reducingext", "exp", "poseidonmds", "cosetinterp"):
             gates[G[kind]].fill_witness(w, rnd)
         elif kind == "arithext":
             c0, c1 = rnd.randrange(P), rnd.randrange(P)

@@ -154,7 +154,7 @@ def test_full_proof_equals_oracle_and_verifies(case):
                                              (6, ("u32addmany", "comparison", "exp", "randomaccess")),
                                              (6, ("arithext", "mulext", "reducing", "reducingext", "poseidonmds")),
                                              (7, synth.ALL_KINDS)],
-                         ids=["arith", "poseidon", "u32", "mixed-9", "addmany-cmp-exp-ra", "extension-gates", "all-18-gates"])
+                         ids=["arith", "poseidon", "u32", "mixed-9", "addmany-cmp-exp-ra", "extension-gates", "all-19-gates"])
 def test_proofs_of_other_shapes_verify(ctx, degree_bits, mix):
     circ, wires, pis = synth.build(degree_bits, seed=degree_bits, mix=mix)
     pc = product_circuit(circ, ctx)

@@ -144,7 +144,7 @@ def run_program(words, wires, consts_cols, pi_hash, apow, num_perm_terms):
     return total
 
 
-@pytest.mark.parametrize("mix", [None, synth.ALL_KINDS], ids=["default-mix", "all-18-gates"])
+@pytest.mark.parametrize("mix", [None, synth.ALL_KINDS], ids=["default-mix", "all-19-gates"])
 def test_gate_programs_match_oracle_formulas(mix):
     """Random wires / constants (not a satisfying witness): the assembled bytecode and the oracle's direct
     formulas give the same filtered, alpha-reduced constraint sum -- for every gate type at once."""
@@ -199,7 +199,9 @@ def test_every_gate_with_a_program_is_satisfied_by_its_honest_witness():
     cases = [(og.U32AddManyGate(3), (), ()), (og.U32AddManyGate(5), (), ()), (og.ComparisonGate(32, 16), (), ()),
              (og.ComparisonGate(10, 5), (), ()), (og.ArithmeticExtensionGate(), (11, 13), (11, 13)),
              (og.MulExtensionGate(), (17,), (17,)), (og.ReducingGate(), (), ()), (og.ReducingExtensionGate(), (), ()),
-             (og.ExponentiationGate(), (), ()), (og.PoseidonMdsGate(), (), ()), (og.RandomAccessGate(), ((5, 9),), (5, 9))]
+             (og.ExponentiationGate(), (), ()), (og.PoseidonMdsGate(), (), ()), (og.RandomAccessGate(), ((5, 9),), (5, 9)),
+             (og.CosetInterpolationGate(), (), ()), (og.CosetInterpolationGate(3, 8), (), ()),
+             (og.CosetInterpolationGate(4, 4), (), ())]
     for gate, fill_args, consts in cases:
         for _ in range(4):
             row = [0] * 135
@@ -223,12 +225,33 @@ def test_every_gate_with_a_program_is_satisfied_by_its_honest_witness():
         assert all(x.v == 0 for x in g.eval([FI(x) for x in row], [], [FI(0)] * 4))
 
 
-def test_oracle_proof_with_all_18_gate_types_verifies():
+def test_oracle_proof_with_all_19_gate_types_verifies():
     circ, wires, pis = synth.build(6, seed=11, mix=synth.ALL_KINDS)
-    assert len(circ.gates) == 18
+    assert len(circ.gates) == 19
     proof = plonk.prove(circ, wires, pis)
     assert plonk.verify(circ, proof)
     rows = [r for r in range(circ.n) if circ.gates[circ.row_gate[r]].name.startswith("ComparisonGate")]
     w2 = wires.copy()
     w2[2, rows[0]] ^= np.uint64(1)                     # flip the comparison result
     assert not plonk.verify(circ, plonk.prove(circ, w2, pis))
+
+
+def test_coset_interpolation_gate_outputs_the_lagrange_interpolant():
+    """The wired evaluation value equals a direct Lagrange interpolation of the 16 wired values at point / shift (an
+    independent formula), the shape follows `with_max_degree` (16 points, max degree 8 -> degree 6, 2 intermediates, 47
+    wires of which 37 routed, 12 constraints), and the weights are x_i / 16."""
+    from oracle import gates as og
+    g = og.CosetInterpolationGate()
+    assert (g.deg, g.ni, g.num_routed(), g.end(), g.num_constraints) == (6, 2, 37, 47, 12)
+    assert g.chunks() == [(0, 6), (6, 11), (11, 16)]
+    inv16 = pow(16, P - 2, P)
+    assert g.weights == [x * inv16 % P for x in g.domain]
+    assert vgates._coset_tables(4) == (g.domain, g.weights)
+    rnd = random.Random(3)
+    for gate in (g, og.CosetInterpolationGate(3, 8), og.CosetInterpolationGate(4, 4), og.CosetInterpolationGate(2, 8)):
+        row = [0] * 135
+        x, ev = gate.fill_witness(row, rnd)
+        assert gate.interpolate_direct(row, x) == ev
+        fn, params, degree, ncon, ncs = vgates.lookup(gate.id())
+        assert (degree, ncon, ncs) == (gate.degree, 0, gate.num_constraints)
+        assert gate.end() <= 135 and gate.num_routed() <= 80

@@ -8,9 +8,10 @@ bytecode of include/vectorx_b200.h.
 
 Formulas: U32* gates and ComparisonGate follow the in-tree sources (frontend/uint/num/u32/gates/
 arithmetic_u32.rs:290-349, subtraction_u32.rs:235-271, range_check_u32.rs:93-115, add_many_u32.rs:149-190,
-comparison.rs:333-410); the upstream plonky2 v0.2.0 gates follow SURVEY.md Appendix B.  18 of the 23 registered
-gate types have a program; CosetInterpolationGate, LookupGate, LookupTableGate (no lookups in VectorX),
-ArithmeticCubicGate and MulCubicGate (starkyx) need upstream source that is not in the reference tree.  PoseidonGate uses the fast partial-round tables exported by the library
+comparison.rs:333-410); the upstream plonky2 v0.2.0 gates follow SURVEY.md Appendix B.  19 of the 23 registered
+gate types have a program (CosetInterpolationGate restated from plonky2 v0.2.0 without the source at hand: anchored by the
+honest-witness, direct-Lagrange and prove -> verify checks only); LookupGate / LookupTableGate never occur (no lookup
+tables in VectorX), ArithmeticCubicGate and MulCubicGate (starkyx) need source that is not in the reference tree.  PoseidonGate uses the fast partial-round tables exported by the library
 (vx_poseidon_fast_tables), like upstream's gate does.
 """
 from __future__ import annotations
@@ -462,6 +463,53 @@ def gate_random_access(t, w, c, pi, params):
         t.emit(c(i) - w((2 + vs) * copies + i))
 
 
+def _coset_tables(bits):
+    """two_adic_subgroup(bits) in natural order and its barycentric weights 1 / prod_{j != i}(x_i - x_j) = x_i / 2^bits."""
+    g = pow(7277203076849721926, 1 << (32 - bits), P)
+    dom = [pow(g, i, P) for i in range(1 << bits)]
+    inv_n = pow(1 << bits, P - 2, P)
+    return dom, [x * inv_n % P for x in dom]
+
+
+def gate_coset_interpolation(t, w, c, pi, params):
+    """plonky2 v0.2.0 gates/coset_interpolation.rs (restated; see DESIGN.md gate coverage): barycentric interpolation over
+    shift*<w_16> in the quadratic extension with `num_intermediates` wired (eval, prod) checkpoints."""
+    bits, deg = params["subgroup_bits"], params["degree"]
+    npts = 1 << bits
+    ni = (npts - 2) // (deg - 1)
+    dom, wts = _coset_tables(bits)
+    p_pt = 1 + 2 * npts
+    p_val, p_int = p_pt + 2, p_pt + 4
+    p_sh = p_int + 4 * ni
+    x = (_val(w(p_sh)), _val(w(p_sh + 1)))
+    shift = _val(w(0))
+    t.emit(w(p_pt) - x[0] * shift)
+    t.emit(w(p_pt + 1) - x[1] * shift)
+
+    def fold(lo, hi, ev, pr):
+        for i in range(lo, hi):
+            term = (x[0] - dom[i], x[1])
+            v = (w(1 + 2 * i) * wts[i], w(2 + 2 * i) * wts[i])
+            if pr is None:                                   # first point: eval = 0, prod = 1
+                ev, pr = v, term
+                continue
+            vp, et = _ext_mul(v, pr), _ext_mul(ev, term)
+            ev = (et[0] + vp[0], et[1] + vp[1])
+            pr = _ext_mul(pr, term)
+        return ev, pr
+    ev, pr = fold(0, deg, None, None)
+    for i in range(ni):
+        ie, ip = p_int + 2 * i, p_int + 2 * (ni + i)
+        t.emit(w(ie) - ev[0])
+        t.emit(w(ie + 1) - ev[1])
+        t.emit(w(ip) - pr[0])
+        t.emit(w(ip + 1) - pr[1])
+        s = 1 + (deg - 1) * (i + 1)
+        ev, pr = fold(s, min(s + deg - 1, npts), (_val(w(ie)), _val(w(ie + 1))), (_val(w(ip)), _val(w(ip + 1))))
+    t.emit(w(p_val) - ev[0])
+    t.emit(w(p_val + 1) - ev[1])
+
+
 # id prefix -> (formula, parameter parser, degree, num_constants, num_constraints)
 def _p(name, key):
     import re
@@ -497,6 +545,9 @@ GATES = {
                          lambda s: {"bits": _p(s, "bits"), "num_copies": _p(s, "num_copies"),
                                     "num_extra_constants": _p(s, "num_extra_constants")},
                          lambda p: (p["bits"] + 1, p["num_extra_constants"], p["num_copies"] * (p["bits"] + 2) + p["num_extra_constants"])),
+    "CosetInterpolationGate": (gate_coset_interpolation,
+                               lambda s: {"subgroup_bits": _p(s, "subgroup_bits"), "degree": _p(s, "degree")},
+                               lambda p: (p["degree"], 0, 2 * (2 + 2 * (((1 << p["subgroup_bits"]) - 2) // (p["degree"] - 1))))),
 }
 
 
