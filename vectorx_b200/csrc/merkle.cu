@@ -75,6 +75,14 @@ int32_t poseidon_module_init(vx_ctx* ctx) {
     if (!poseidon_derive_tables(rc, &t)) { vx_set_error("poseidon: table derivation failed"); return VX_ECUDA; }
     VX_CUDA(poseidon_upload_constants(t, ctx->stream));
     VX_CUDA(cudaMemcpyToSymbolAsync(g_pos_rc, t.rc, sizeof t.rc, 0, cudaMemcpyHostToDevice, ctx->stream));
+    int naive = 0;                                           // A/B: hybrid partial rounds of leaf-hash variant 8
+    if (const char* v = getenv("VX_POSEIDON_NAIVE_ROUNDS")) naive = atoi(v);
+    if (naive < 0 || naive > 22) naive = 0;
+    PoseidonTables tk;
+    if (naive < 22 && !poseidon_derive_tables_hybrid(rc, naive, &tk)) { vx_set_error("poseidon: table derivation failed"); return VX_ECUDA; }
+    if (naive == 22) tk = t;
+    VX_CUDA(cudaMemcpyToSymbolAsync(c_posk, &tk, sizeof tk, 0, cudaMemcpyHostToDevice, ctx->stream));
+    VX_CUDA(cudaMemcpyToSymbolAsync(c_posk_naive, &naive, sizeof naive, 0, cudaMemcpyHostToDevice, ctx->stream));
     VX_CUDA(cudaStreamSynchronize(ctx->stream));
     return VX_OK;
 }
@@ -119,7 +127,8 @@ __global__ void __launch_bounds__(POSEIDON_BLOCK, MINB) leaf_hash_kernel(const u
 #pragma unroll
                 for (int i = 0; i < POSEIDON_RATE; i++)
                     if (off + i < c) s[i] = src[(uint64_t)(off + i) * step];   // overwrite-mode absorb
-                poseidon_permute<V == 2 ? 1 : (V == 3 ? 2 : 0)>(s, st);
+                if (V == 4) poseidon_permute_hybrid(s, st);
+                else poseidon_permute<V == 2 ? 1 : (V == 3 ? 2 : 0)>(s, st);
             } else {
 #pragma unroll
                 for (int i = 0; i < POSEIDON_RATE; i++)
@@ -295,6 +304,7 @@ int32_t merkle_build_device(vx_ctx* ctx, const u64* leaves, bool col_major, uint
             case 5: LEAF(true, 0, 10); break;     // 48 registers, 10 blocks per SM
             case 6: LEAF(true, 0, 9); break;      // 56 registers, 9 blocks per SM
             case 7: LEAF(true, 3, 8); break;      // lazy dot products accumulated on the ALU pipe
+            case 8: LEAF(true, 4, 8); break;      // hybrid partial rounds (VX_POSEIDON_NAIVE_ROUNDS spec-form rounds first)
             default: LEAF(true, 0, 8); break;     // state in registers, 64 registers / 8 blocks per SM
         }
     } else {

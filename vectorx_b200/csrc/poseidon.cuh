@@ -125,12 +125,13 @@ GL_D void poseidon_mds_add_freq(u64 s[12], const u32* __restrict__ kl) {
 // with the partial rounds' initial matrix).  Rows are produced in a rolled loop (small code) and
 // staged through this thread's shared-memory column: scratch[j * POSEIDON_BLOCK].
 template <int ALU = 0>
-GL_D void poseidon_dense_layer(u64 s[12], u64* __restrict__ scratch) {
+GL_D void poseidon_dense_layer(u64 s[12], u64* __restrict__ scratch, const u64* __restrict__ dense_d = c_pos.dense_d,
+                               const u64* __restrict__ dense_e = c_pos.dense_e) {
 #pragma unroll 1
     for (int j = 0; j < 12; j++) {
-        const u64* row = c_pos.dense_d + 12 * j;
+        const u64* row = dense_d + 12 * j;
         GlAcc acc;
-        gl_acc_init(acc, c_pos.dense_e[j]);
+        gl_acc_init(acc, dense_e[j]);
 #pragma unroll
         for (int i = 0; i < 12; i++) gl_acc_mad_v<ALU>(acc, row[i], s[i]);
         scratch[j * POSEIDON_BLOCK] = gl_acc_reduce(acc);
@@ -141,12 +142,13 @@ GL_D void poseidon_dense_layer(u64 s[12], u64* __restrict__ scratch) {
 
 // 22 partial rounds in the sparse form (see poseidon_tables.h)
 template <int ALU = 0>
-GL_D void poseidon_partial_rounds(u64 s[12]) {
+GL_D void poseidon_partial_rounds(u64 s[12], const int rounds = POSEIDON_PARTIAL_ROUNDS, const u64* __restrict__ pk = c_pos.pk,
+                                  const u64* __restrict__ pv = c_pos.pv, const u64* __restrict__ pw = c_pos.pw) {
 #pragma unroll 1
-    for (int r = 0; r < POSEIDON_PARTIAL_ROUNDS; r++) {
-        const u64* v = c_pos.pv + 11 * r;
-        const u64* w = c_pos.pw + 11 * r;
-        u64 x0 = gl_add_canon(gl_pow7_cc(s[0]), c_pos.pk[r]);
+    for (int r = 0; r < rounds; r++) {
+        const u64* v = pv + 11 * r;
+        const u64* w = pw + 11 * r;
+        u64 x0 = gl_add_canon(gl_pow7_cc(s[0]), pk[r]);
         // d = 25 * x0 + sum_i v_i s_i   (25 = MDS[0][0])
         GlAcc d;
         gl_acc_init(d, 0);
@@ -183,6 +185,43 @@ GL_D void poseidon_permute(u64 s[12], u64* __restrict__ scratch) {
 #pragma unroll
             for (int i = 0; i < 12; i++) s[i] = gl_add_canon(s[i], rc[26 * 12 + i]);
         }
+    }
+}
+
+// Hybrid partial rounds (A/B): the first c_posk_naive partial rounds in the spec form -- x0^7 then the frequency-domain
+// MDS layer, no IMAD.WIDE in the linear part -- and the remaining ones in the sparse form with tables derived for that
+// suffix (c_posk).  naive = 22 drops the dense layer and the sparse rounds altogether.
+static __constant__ PoseidonTables c_posk;
+static __constant__ int c_posk_naive;
+
+GL_D void poseidon_permute_hybrid(u64 s[12], u64* __restrict__ scratch) {
+    const u64* rc = c_pos.rc;
+    const int K = c_posk_naive;
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = gl_add_canon(s[i], rc[i]);
+#pragma unroll 1
+    for (int r = 0; r < 4; r++) {
+#pragma unroll
+        for (int i = 0; i < 12; i++) s[i] = gl_pow7_cc(s[i]);
+        if (r == 3 && K == 0) poseidon_dense_layer<0>(s, scratch, c_posk.dense_d, c_posk.dense_e);
+        else poseidon_mds_add_freq(s, c_pos.rc22 + 36 * (1 + r));
+    }
+#pragma unroll 1
+    for (int j = 0; j < K; j++) {                            // spec-form partial rounds 4 .. 4 + K - 1
+        s[0] = gl_pow7_cc(s[0]);
+        if (j == K - 1 && K < 22) poseidon_dense_layer<0>(s, scratch, c_posk.dense_d, c_posk.dense_e);
+        else poseidon_mds_add_freq(s, c_pos.rc22 + 36 * (5 + j));
+    }
+    if (K < 22) {
+        poseidon_partial_rounds<0>(s, 22 - K, c_posk.pk, c_posk.pv, c_posk.pw);
+#pragma unroll
+        for (int i = 0; i < 12; i++) s[i] = gl_add_canon(s[i], rc[26 * 12 + i]);
+    }
+#pragma unroll 1
+    for (int r = 0; r < 4; r++) {
+#pragma unroll
+        for (int i = 0; i < 12; i++) s[i] = gl_pow7_cc(s[i]);
+        poseidon_mds_add_freq(s, c_pos.rc22 + 36 * (27 + r));
     }
 }
 

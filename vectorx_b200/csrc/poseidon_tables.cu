@@ -61,8 +61,15 @@ bool invert(const Mat& A, Mat& out) {       // Gauss-Jordan mod p
 }  // namespace
 
 bool poseidon_derive_tables(const unsigned long long rc360[360], PoseidonTables* t) {
+    return poseidon_derive_tables_hybrid(rc360, 0, t);
+}
+
+// The same derivation for the LAST 22 - naive partial rounds only (rounds 4 + naive .. 25): the first `naive` partial
+// rounds then keep the spec form (x0^7, MDS, constants) and the dense layer replaces the MDS of round 3 + naive.
+bool poseidon_derive_tables_hybrid(const unsigned long long rc360[360], int naive, PoseidonTables* t) {
     static const uint64_t CIRC[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
-    const int R = 22, FIRST_PARTIAL = 4;
+    if (naive < 0 || naive > 21) return false;
+    const int R = 22 - naive, FIRST_PARTIAL = 4 + naive;
     memset(t, 0, sizeof *t);
     for (int i = 0; i < 360; i++) {
         t->rc[i] = rc360[i];

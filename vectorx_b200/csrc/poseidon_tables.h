@@ -26,3 +26,5 @@ struct PoseidonTables {
 
 // fills t from the 360 round constants; returns false if a matrix was singular (never happens)
 bool poseidon_derive_tables(const unsigned long long rc360[360], PoseidonTables* t);
+// hybrid form: the first `naive` (0..21) partial rounds stay in the spec form; pk/pv/pw hold 22 - naive rounds
+bool poseidon_derive_tables_hybrid(const unsigned long long rc360[360], int naive, PoseidonTables* t);
