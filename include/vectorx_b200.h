@@ -63,6 +63,14 @@ int32_t vx_dev_alloc(vx_ctx* ctx, size_t bytes, uint64_t** out);
 void vx_dev_free(vx_ctx* ctx, uint64_t* p);
 /* dst/src: host or device, any combination; blocking */
 int32_t vx_dev_copy(vx_ctx* ctx, void* dst, const void* src, size_t bytes);
+/* Page-locked host memory for buffers the caller fills and hands to the library (the witness matrix that plonky2's
+ * generate_partial_witness produces before prove_with_partition_witness, build.rs:69-75): a pageable source is staged by
+ * the driver at ~11 GB/s, a pinned one is copied at PCIe/C2C rate.  vx_host_register pins an existing allocation in place
+ * (the Rust Vec case); every pointer must be released with the matching call.  No context needed. */
+int32_t vx_host_alloc(size_t bytes, void** out);
+void vx_host_free(void* p);
+int32_t vx_host_register(void* p, size_t bytes);
+void vx_host_unregister(void* p);
 
 /* ---- PolynomialBatch (plonky2 fri/oracle.rs) ------------------------------------------------
  * vx_commit_from_values replaces PolynomialBatch::from_values(values, rate_bits, blinding=false,

@@ -199,6 +199,29 @@ def test_full_size_properties_config1(ctx):
     assert np.array_equal(((r1.astype(object) + r2.astype(object)) % P).astype(np.uint64), r3)
 
 
+def test_pinned_host_buffers(ctx):
+    """vx_host_alloc / vx_host_register: a commit whose values come from page-locked memory equals the pageable one."""
+    from vectorx_b200._lib import check, load
+    cols = oracle.random_field((9, 1 << 8), seed=31)
+    want = oracle.commit_from_values(cols, 3, 4)
+    pinned = vx.pinned_empty(cols.shape)
+    assert pinned.shape == cols.shape and pinned.dtype == np.uint64 and pinned.flags["C_CONTIGUOUS"]
+    pinned[:] = cols
+    b = vx.PolynomialBatch.from_values(pinned, 3, False, 4)
+    assert np.array_equal(b.cap.hashes, want["cap"])
+    b.close()
+    reg = cols.copy()
+    check(load().vx_host_register(reg.ctypes.data, reg.nbytes), "vx_host_register")
+    try:
+        b = vx.PolynomialBatch.from_values(reg, 3, False, 4)
+        assert np.array_equal(b.cap.hashes, want["cap"])
+        b.close()
+    finally:
+        load().vx_host_unregister(reg.ctypes.data)
+    assert load().vx_host_register(None, 0) != 0          # argument errors are codes, not crashes
+    del pinned
+
+
 def test_error_behaviour(ctx):
     cols = oracle.random_field((3, 6), seed=1)          # not a power of two
     with pytest.raises(vx.VxError):

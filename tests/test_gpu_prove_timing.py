@@ -26,15 +26,20 @@ def test_prove_verifies_and_times(ctx):
                         circ.sigmas, ctx=ctx)
     assert pc.circuit_digest == circ.circuit_digest
     vx.prove(pc, wires, pis)                                   # warm-up (pools, twiddle caches)
-    runs = []
-    proof = None
-    for _ in range(3):
-        tr = {"intermediates": False}
-        t = time.perf_counter()
-        proof = vx.prove(pc, wires, pis, trace=tr)
-        total = (time.perf_counter() - t) * 1e3
-        runs.append((total, tr["phase_ms"]))
-    total, phases = min(runs, key=lambda r: r[0])
+    pinned = vx.pinned_empty(wires.shape)                      # the witness written straight into page-locked memory
+    pinned[:] = wires
+
+    def best_of(w, reps=3):
+        runs = []
+        for _ in range(reps):
+            tr = {"intermediates": False}
+            t = time.perf_counter()
+            pr = vx.prove(pc, w, pis, trace=tr)
+            runs.append(((time.perf_counter() - t) * 1e3, tr["phase_ms"], pr))
+        return min(runs, key=lambda r: r[0])
+    total_pageable, phases_pageable, proof_pageable = best_of(wires)
+    total, phases, proof = best_of(pinned)
+    assert vx.proof_to_bytes(proof) == vx.proof_to_bytes(proof_pageable)
     oproof = dict(proof)
     oproof["openings"] = {k: [E2(int(e[0]), int(e[1])) for e in v] for k, v in proof["openings"].items()}
     oproof["final_poly"] = [E2(int(e[0]), int(e[1])) for e in proof["final_poly"]]
@@ -42,7 +47,9 @@ def test_prove_verifies_and_times(ctx):
     assert plonk.verify(circ, oproof), "GPU proof rejected by the oracle verifier"
     verify_s = time.perf_counter() - t
     rec = {"degree_bits": bits, "rows": 1 << bits, "wires": 135, "rate_bits": 3, "cap_height": 4,
-           "prove_ms": total, "phase_ms": phases, "circuit_build_s": build_s, "oracle_verify_s": verify_s,
+           "witness": "pinned host memory (vx_host_alloc)", "prove_ms": total, "phase_ms": phases,
+           "pageable_witness": {"prove_ms": total_pageable, "upload witness": phases_pageable.get("upload witness")},
+           "circuit_build_s": build_s, "oracle_verify_s": verify_s,
            "gates": [g.id() for g in circ.gates]}
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "prove_timing.json"), "w") as f:

@@ -31,6 +31,10 @@ SIGNATURES = {
     "vx_dev_alloc": (c_i32, [vp, ctypes.c_size_t, ctypes.POINTER(vp)]),
     "vx_dev_free": (None, [vp, vp]),
     "vx_dev_copy": (c_i32, [vp, vp, vp, ctypes.c_size_t]),
+    "vx_host_alloc": (c_i32, [ctypes.c_size_t, ctypes.POINTER(vp)]),
+    "vx_host_free": (None, [vp]),
+    "vx_host_register": (c_i32, [vp, ctypes.c_size_t]),
+    "vx_host_unregister": (None, [vp]),
     "vx_commit_from_coeffs_shard": (c_i32, [vp, vp, c_u32, c_u32, c_u32, c_u32, c_u32, c_u32, ctypes.POINTER(vp)]),
     "vx_batch_shard": (c_i32, [vp, u64p]),
     "vx_shard_group_create": (c_i32, [vp, c_u32, c_u32, c_u32, c_u32, c_u32, c_u32, ctypes.POINTER(vp)]),
@@ -179,6 +183,36 @@ def default_context(device: int = 0) -> Context:
     if device not in _default_ctx:
         _default_ctx[device] = Context(device)
     return _default_ctx[device]
+
+
+class _PinnedOwner:
+    """Keeps a vx_host_alloc allocation alive for the numpy array that views it."""
+
+    def __init__(self, nbytes: int):
+        h = vp()
+        check(load().vx_host_alloc(nbytes, ctypes.byref(h)), "vx_host_alloc")
+        self.ptr, self.nbytes = h.value, nbytes
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                load().vx_host_free(self.ptr)
+                self.ptr = 0
+        except Exception:
+            pass
+
+
+def pinned_empty(shape) -> np.ndarray:
+    """uint64 numpy array in page-locked host memory (vx_host_alloc): fill the witness matrix in place and every upload
+    from it runs at PCIe rate instead of being staged by the driver.  Freed when the last view is collected."""
+    shape = tuple(int(x) for x in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+    n = 1
+    for d in shape:
+        n *= d
+    owner = _PinnedOwner(max(8 * n, 8))
+    buf = (ctypes.c_uint64 * max(n, 1)).from_address(owner.ptr)
+    buf._vx_owner = owner                       # numpy keeps `buf` as .base, which keeps the allocation
+    return np.frombuffer(buf, dtype=np.uint64, count=n).reshape(shape)
 
 
 class DeviceArray:

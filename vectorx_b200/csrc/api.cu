@@ -160,6 +160,34 @@ extern "C" int32_t vx_dev_copy(vx_ctx* ctx, void* dst, const void* src, size_t b
     return VX_OK;
 }
 
+extern "C" int32_t vx_host_alloc(size_t bytes, void** out) {
+    VX_REQUIRE(out, "vx_host_alloc: NULL argument");
+    *out = nullptr;
+    cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 8, cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        vx_set_error("vx_host_alloc: %zu bytes: %s", bytes, cudaGetErrorString(e));
+        return e == cudaErrorMemoryAllocation ? VX_ENOMEM : VX_ECUDA;
+    }
+    return VX_OK;
+}
+extern "C" void vx_host_free(void* p) {
+    if (p && cudaFreeHost(p) != cudaSuccess) cudaGetLastError();
+}
+extern "C" int32_t vx_host_register(void* p, size_t bytes) {
+    VX_REQUIRE(p && bytes, "vx_host_register: NULL argument");
+    cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        vx_set_error("vx_host_register: %zu bytes at %p: %s", bytes, p, cudaGetErrorString(e));
+        return VX_ECUDA;
+    }
+    return VX_OK;
+}
+extern "C" void vx_host_unregister(void* p) {
+    if (p && cudaHostUnregister(p) != cudaSuccess) cudaGetLastError();
+}
+
 #define EV(ctx, i) VX_CUDA(cudaEventRecord((ctx)->ev[i], (ctx)->stream))
 
 static int32_t commit_run(vx_ctx* ctx, vx_batch* b, const u64* src, bool is_values) {
