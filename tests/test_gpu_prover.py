@@ -164,3 +164,30 @@ def test_proofs_of_other_shapes_verify(ctx, degree_bits, mix):
         op = plonk.prove(circ, wires, pis)
         assert normalise(gp) == normalise(op)
         assert vx.proof_to_bytes(gp) == plonk.proof_bytes(op)
+
+
+def _golden_cases():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "proof_golden.json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("gold", _golden_cases(), ids=lambda g: g["name"])
+def test_proof_bytes_match_committed_golden(ctx, gold):
+    """The GPU proof of the seeded circuit hashes to the committed fixture (tests/golden/make_proof_golden.py) without
+    running the oracle prover: circuit digest, caps, PoW witness, byte length and SHA-256 of the bincode bytes."""
+    import hashlib
+    mix = synth.ALL_KINDS if gold["mix"] == "ALL" else None
+    circ, wires, pis = synth.build(gold["degree_bits"], seed=gold["seed"]) if mix is None else \
+        synth.build(gold["degree_bits"], seed=gold["seed"], mix=mix)
+    pc = product_circuit(circ, ctx)
+    assert [int(x) for x in pc.circuit_digest] == gold["circuit_digest"]
+    gp = vx.prove(pc, wires, pis)
+    assert [int(x) for x in gp["wires_cap"][0]] == gold["wires_cap0"]
+    assert [int(x) for x in gp["zs_pp_cap"][0]] == gold["zs_pp_cap0"]
+    assert [int(x) for x in gp["quotient_cap"][0]] == gold["quotient_cap0"]
+    assert int(gp["pow_witness"]) == gold["pow_witness"]
+    data = vx.proof_to_bytes(gp)
+    assert len(data) == gold["proof_len"]
+    assert hashlib.sha256(data).hexdigest() == gold["proof_sha256"]

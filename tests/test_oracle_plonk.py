@@ -255,3 +255,20 @@ def test_coset_interpolation_gate_outputs_the_lagrange_interpolant():
         fn, params, degree, ncon, ncs = vgates.lookup(gate.id())
         assert (degree, ncon, ncs) == (gate.degree, 0, gate.num_constraints)
         assert gate.end() <= 135 and gate.num_routed() <= 80
+
+
+def test_oracle_proofs_match_committed_golden():
+    """tests/golden/proof_golden.json re-derived: the oracle prover is deterministic and frozen (any change to the oracle's
+    transcript, gate formulas, FRI or byte layout shows up here before it can silently move the GPU parity target)."""
+    import importlib.util
+    import json
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_proof_golden", os.path.join(here, "golden", "make_proof_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    with open(os.path.join(here, "golden", "proof_golden.json")) as f:
+        gold = json.load(f)
+    assert [g["name"] for g in gold] == [c["name"] for c in mod.CASES]
+    for case, want in zip(mod.CASES, gold):
+        assert mod.run_case(case)[4] == want

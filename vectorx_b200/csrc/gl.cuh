@@ -213,6 +213,60 @@ GL_D u64 gl_pow7_cc(u64 x) {
     return gl_mul_cc(x3, x4);
 }
 
+// ---- "z" forms: every IMAD.WIDE takes a zero-extended 32-bit addend (cannot overflow: (2^32-1)^2 + 2^32-1 < 2^64), so
+// no product carries out and no carry is ever materialised; the price is a dependent chain p0 -> t -> (u, v).
+// 64 x 64 -> 128: 4 IMAD.WIDE + one 64-bit add (A/B against gl_mul128_cc: 4 IMAD.WIDE, one with carry-out, + 4 carry ops)
+GL_D void gl_mul128_z(u64 a, u64 b, u32& r0, u32& r1, u32& r2, u32& r3) {
+    u32 a0 = lo32(a), a1 = hi32(a), b0 = lo32(b), b1 = hi32(b);
+    u64 p0 = mul_wide(a0, b0);
+    u64 t = mad_wide(a0, b1, (u64)hi32(p0));
+    u64 u = mad_wide(a1, b0, (u64)lo32(t));
+    u64 v = mad_wide(a1, b1, (u64)hi32(t));
+    asm("{\n\t"
+        "add.cc.u32 %0, %2, %4;\n\t"
+        "addc.u32 %1, %3, 0;\n\t"
+        "}"
+        : "=r"(r2), "=r"(r3)
+        : "r"(lo32(v)), "r"(hi32(v)), "r"(hi32(u)));
+    r0 = lo32(p0);
+    r1 = lo32(u);
+}
+GL_D u64 gl_mul_z(u64 a, u64 b) {
+    u32 r0, r1, r2, r3;
+    gl_mul128_z(a, b, r0, r1, r2, r3);
+    return gl_reduce128_cc(r0, r1, r2, r3);
+}
+// a * b + c: the addend's halves ride in the first product and in the final carry chain
+GL_D u64 gl_mul_add_z(u64 a, u64 b, u64 c) {
+    u32 a0 = lo32(a), a1 = hi32(a), b0 = lo32(b), b1 = hi32(b);
+    u64 p0 = mad_wide(a0, b0, (u64)lo32(c));
+    u64 t = mad_wide(a0, b1, (u64)hi32(p0));
+    u64 u = mad_wide(a1, b0, (u64)lo32(t));
+    u64 v = mad_wide(a1, b1, (u64)hi32(t));
+    u32 r1, r2, r3;
+    asm("{\n\t"
+        "add.cc.u32 %0, %3, %4;\n\t"
+        "addc.cc.u32 %1, %5, %6;\n\t"
+        "addc.u32 %2, %7, 0;\n\t"
+        "}"
+        : "=r"(r1), "=&r"(r2), "=&r"(r3)
+        : "r"(lo32(u)), "r"(hi32(c)), "r"(lo32(v)), "r"(hi32(u)), "r"(hi32(v)));
+    return gl_reduce128_cc(lo32(p0), r1, r2, r3);
+}
+// S-box variants: SB = 0 the shipped form; 1 = z-form multiplications, carry-chain squarings; 2 = z-form everywhere
+template <int SB>
+GL_D u64 gl_pow7_v(u64 x) {
+    if (SB == 0) return gl_pow7_cc(x);
+    u64 x2 = SB == 2 ? gl_mul_z(x, x) : gl_sqr_cc(x);
+    u64 x4 = SB == 2 ? gl_mul_z(x2, x2) : gl_sqr_cc(x2);
+    u64 x3 = gl_mul_z(x2, x);
+    return gl_mul_z(x3, x4);
+}
+template <int SB>
+GL_D u64 gl_mul_add_v(u64 a, u64 b, u64 c) {
+    return SB ? gl_mul_add_z(a, b, c) : gl_mul_add_cc(a, b, c);
+}
+
 // a + b and a - b for ANY u64 representatives, as pure carry chains (8 ALU instructions, no compare / select):
 //   a + b = s + C 2^64 = s + C eps (mod p); the fix-up itself can carry once more (only when s >= p), and then the
 //   second fix-up lands below 2 eps.  Same with borrows for the difference (-2^64 = -eps).

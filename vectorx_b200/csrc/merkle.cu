@@ -66,7 +66,9 @@ void poseidon_round_constants_host(u64 out[360]) {
     }
 }
 
-static __device__ u64 g_pos_rc[31 * 12];      // global-memory copy of c_pos.rc for kernels that index it per lane
+static __device__ u64 g_pos_rc[31 * 12];
+static __constant__ unsigned c_leaf_stagger;  // A/B: start delay (cycles) of every second resident block, 0 = off
+static __constant__ unsigned c_leaf_sms = 148;      // global-memory copy of c_pos.rc for kernels that index it per lane
 
 int32_t poseidon_module_init(vx_ctx* ctx) {
     u64 rc[360];
@@ -75,6 +77,10 @@ int32_t poseidon_module_init(vx_ctx* ctx) {
     if (!poseidon_derive_tables(rc, &t)) { vx_set_error("poseidon: table derivation failed"); return VX_ECUDA; }
     VX_CUDA(poseidon_upload_constants(t, ctx->stream));
     VX_CUDA(cudaMemcpyToSymbolAsync(g_pos_rc, t.rc, sizeof t.rc, 0, cudaMemcpyHostToDevice, ctx->stream));
+    unsigned stagger = 0, sms = (unsigned)ctx->sm_count;
+    if (const char* v = getenv("VX_LEAF_STAGGER")) stagger = (unsigned)atoi(v);
+    VX_CUDA(cudaMemcpyToSymbolAsync(c_leaf_stagger, &stagger, sizeof stagger, 0, cudaMemcpyHostToDevice, ctx->stream));
+    VX_CUDA(cudaMemcpyToSymbolAsync(c_leaf_sms, &sms, sizeof sms, 0, cudaMemcpyHostToDevice, ctx->stream));
     int naive = 0;                                           // A/B: hybrid partial rounds of leaf-hash variant 8
     if (const char* v = getenv("VX_POSEIDON_NAIVE_ROUNDS")) naive = atoi(v);
     if (naive < 0 || naive > 22) naive = 0;
@@ -107,6 +113,14 @@ __global__ void __launch_bounds__(POSEIDON_BLOCK, MINB) leaf_hash_kernel(const u
     __shared__ u64 scratch[12 * POSEIDON_BLOCK];
     uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= N) return;
+    if (c_leaf_stagger) {
+        // A/B (VX_LEAF_STAGGER=cycles): every second resident block of an SM starts late, so that the warps sharing a
+        // sub-partition are not all in the ALU-only MDS layer (or all in the multiplier-heavy S-box layer) together
+        if ((blockIdx.x / c_leaf_sms) & 1) {
+            const long long t0 = clock64();
+            while (clock64() - t0 < (long long)c_leaf_stagger) {}
+        }
+    }
     const u64* src = COL_MAJOR ? leaves + row : leaves + row * c;
     const uint64_t step = COL_MAJOR ? stride : 1;
     u64* st = scratch + threadIdx.x;
@@ -128,6 +142,8 @@ __global__ void __launch_bounds__(POSEIDON_BLOCK, MINB) leaf_hash_kernel(const u
                 for (int i = 0; i < POSEIDON_RATE; i++)
                     if (off + i < c) s[i] = src[(uint64_t)(off + i) * step];   // overwrite-mode absorb
                 if (V == 4) poseidon_permute_hybrid(s, st);
+                else if (V == 5) poseidon_permute<0, 1>(s, st);
+                else if (V == 6) poseidon_permute<0, 2>(s, st);
                 else poseidon_permute<V == 2 ? 1 : (V == 3 ? 2 : 0)>(s, st);
             } else {
 #pragma unroll
@@ -304,6 +320,8 @@ int32_t merkle_build_device(vx_ctx* ctx, const u64* leaves, bool col_major, uint
             case 5: LEAF(true, 0, 10); break;     // 48 registers, 10 blocks per SM
             case 6: LEAF(true, 0, 9); break;      // 56 registers, 9 blocks per SM
             case 7: LEAF(true, 3, 8); break;      // lazy dot products accumulated on the ALU pipe
+            case 9: LEAF(true, 5, 8); break;      // z-form multiplications in the S-box and the partial-round axpy
+            case 10: LEAF(true, 6, 8); break;     // z-form multiplications and squarings
             case 8: LEAF(true, 4, 8); break;      // hybrid partial rounds (VX_POSEIDON_NAIVE_ROUNDS spec-form rounds first)
             default: LEAF(true, 0, 8); break;     // state in registers, 64 registers / 8 blocks per SM
         }

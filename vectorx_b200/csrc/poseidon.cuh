@@ -141,14 +141,14 @@ GL_D void poseidon_dense_layer(u64 s[12], u64* __restrict__ scratch, const u64* 
 }
 
 // 22 partial rounds in the sparse form (see poseidon_tables.h)
-template <int ALU = 0>
+template <int ALU = 0, int SB = 0>
 GL_D void poseidon_partial_rounds(u64 s[12], const int rounds = POSEIDON_PARTIAL_ROUNDS, const u64* __restrict__ pk = c_pos.pk,
                                   const u64* __restrict__ pv = c_pos.pv, const u64* __restrict__ pw = c_pos.pw) {
 #pragma unroll 1
     for (int r = 0; r < rounds; r++) {
         const u64* v = pv + 11 * r;
         const u64* w = pw + 11 * r;
-        u64 x0 = gl_add_canon(gl_pow7_cc(s[0]), pk[r]);
+        u64 x0 = gl_add_canon(gl_pow7_v<SB>(s[0]), pk[r]);
         // d = 25 * x0 + sum_i v_i s_i   (25 = MDS[0][0])
         GlAcc d;
         gl_acc_init(d, 0);
@@ -156,7 +156,7 @@ GL_D void poseidon_partial_rounds(u64 s[12], const int rounds = POSEIDON_PARTIAL
 #pragma unroll
         for (int i = 1; i < 12; i++) gl_acc_mad_v<ALU>(d, v[i - 1], s[i]);
 #pragma unroll
-        for (int i = 1; i < 12; i++) s[i] = gl_mul_add_cc(w[i - 1], x0, s[i]);
+        for (int i = 1; i < 12; i++) s[i] = gl_mul_add_v<SB>(w[i - 1], x0, s[i]);
         s[0] = gl_acc_reduce(d);
     }
 }
@@ -164,7 +164,8 @@ GL_D void poseidon_partial_rounds(u64 s[12], const int rounds = POSEIDON_PARTIAL
 // scratch: this thread's column of a POSEIDON_BLOCK-wide shared array of 12 rows
 // MV = 0: frequency-domain MDS layer (shifts/adds on 22-bit limb planes); MV = 1: IMAD.WIDE MDS on 32-bit halves (A/B);
 // MV = 2: MV 0 with the lazy dot products accumulated on the ALU pipe (gl_acc_mad_alu, A/B)
-template <int MV = 0>
+// SB: S-box / multiply-add form (gl_pow7_v): 0 = carry-chain products (shipped), 1 / 2 = zero-extended-addend products (A/B)
+template <int MV = 0, int SB = 0>
 GL_D void poseidon_permute(u64 s[12], u64* __restrict__ scratch) {
     const u64* rc = c_pos.rc;
 #pragma unroll
@@ -175,13 +176,13 @@ GL_D void poseidon_permute(u64 s[12], u64* __restrict__ scratch) {
 #pragma unroll 1
         for (int r = 0; r < 4; r++) {
 #pragma unroll
-            for (int i = 0; i < 12; i++) s[i] = gl_pow7_cc(s[i]);
+            for (int i = 0; i < 12; i++) s[i] = gl_pow7_v<SB>(s[i]);
             if (half == 0 && r == 3) poseidon_dense_layer<MV == 2>(s, scratch);
             else if (MV != 1) poseidon_mds_add_freq(s, c_pos.rc22 + 36 * (first + r));
             else poseidon_mds_add(s, rc + 12 * (first + r));
         }
         if (half == 0) {
-            poseidon_partial_rounds<MV == 2>(s);
+            poseidon_partial_rounds<MV == 2, SB>(s);
 #pragma unroll
             for (int i = 0; i < 12; i++) s[i] = gl_add_canon(s[i], rc[26 * 12 + i]);
         }
