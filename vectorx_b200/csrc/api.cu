@@ -67,6 +67,10 @@ extern "C" int32_t vx_ctx_create(int32_t device, vx_ctx** out) {
     if (const char* v = getenv("VX_NTT_LEGACY")) ctx->ntt_legacy = atoi(v);
     if (const char* v = getenv("VX_TREE_FUSE")) ctx->tree_fuse = atoi(v);
     if (const char* v = getenv("VX_COOP_MAX_PAIRS")) ctx->coop_max_pairs = atoi(v);
+    if (const char* v = getenv("VX_STREAM_SPONGE")) ctx->stream_sponge = atoi(v);
+    if (const char* v = getenv("VX_STREAM_CHUNKS")) { int k = atoi(v); if (k >= 1 && k <= 8) ctx->stream_chunks = (uint32_t)k; }
+    if (const char* v = getenv("VX_H2D_FIRST_GROUPS")) { int k = atoi(v); if (k >= 1 && k <= 64) ctx->h2d_first_groups = (uint32_t)k; }
+    if (const char* v = getenv("VX_H2D_CHUNKS")) { int k = atoi(v); if (k >= 1 && k <= 8) ctx->h2d_chunks = (uint32_t)k; }
     cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete ctx; vx_set_error("stream create: %s", cudaGetErrorString(e)); return VX_ECUDA; }
     // keep freed blocks in the stream-ordered pool: commits allocate GBs per call
@@ -202,7 +206,7 @@ static int32_t commit_run(vx_ctx* ctx, vx_batch* b, const u64* src, bool is_valu
     EV(ctx, VX_EV_START);
     const bool from_host = !vx_is_device_ptr(src);
     // column chunks: with a host source the H2D copy of chunk k+1 (copy stream) overlaps the transforms of chunk k
-    const uint32_t nchunks = (from_host && c >= 16) ? 8 : 1;
+    const uint32_t nchunks = (from_host && c >= 16) ? ctx->h2d_chunks : 1;
     DevBuf stage;
     u64* work = nullptr;
     if (is_values) {
@@ -214,8 +218,25 @@ static int32_t commit_run(vx_ctx* ctx, vx_batch* b, const u64* src, bool is_valu
         VX_CUDA(cudaEventRecord(ctx->copy_free, ctx->stream));             // allocations above are stream-ordered
         VX_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_free, 0));
     }
-    for (uint32_t k = 0; k < nchunks; k++) {
-        const uint32_t c0 = (uint32_t)((uint64_t)c * k / nchunks), c1 = (uint32_t)((uint64_t)c * (k + 1) / nchunks);
+    // streaming sponge: chunk boundaries fall on multiples of the sponge rate and every chunk is absorbed into the per-leaf
+    // state right after its LDE, so only the LAST chunk's hashing is left when the last copy lands
+    const bool stream = nchunks > 1 && ctx->stream_sponge && b->hasher == VX_HASHER_POSEIDON && c > 4;
+    // Hashing a column costs ~8x its copy, so the chunks grow geometrically (8, 16, 32, ... columns, the rest in the last
+    // one): only the copy of the first 8 columns is exposed and the transforms run in few, large launches.
+    const uint32_t groups = (c + 7) / 8;
+    uint32_t bound[9] = {0};
+    uint32_t nchunks_eff = nchunks;
+    if (stream) {
+        uint32_t k = 0, g = 0, size = ctx->h2d_first_groups;
+        while (k + 1 < ctx->stream_chunks && g + size < groups) { g += size; bound[++k] = 8 * g; size *= 2; }
+        bound[++k] = c;
+        nchunks_eff = k;
+    }
+    DevBuf sponge;
+    if (stream) VX_CHECK(sponge.alloc((size_t)12 * N_loc * sizeof(u64), ctx->stream));
+    for (uint32_t k = 0; k < nchunks_eff; k++) {
+        uint32_t c0 = (uint32_t)((uint64_t)c * k / nchunks), c1 = (uint32_t)((uint64_t)c * (k + 1) / nchunks);
+        if (stream) { c0 = bound[k]; c1 = bound[k + 1]; }
         if (c1 == c0) continue;
         const size_t off = (size_t)c0 * n, bytes = (size_t)(c1 - c0) * n * sizeof(u64);
         u64* dst = is_values ? work + off : b->coeffs.p + off;
@@ -231,11 +252,19 @@ static int32_t commit_run(vx_ctx* ctx, vx_batch* b, const u64* src, bool is_valu
         if (nchunks == 1) EV(ctx, VX_EV_INTT);
         VX_CHECK(lde_batch(ctx, b->coeffs.p + off, b->lde.p + (size_t)c0 * N_loc, c1 - c0, b->log_n, b->rate_bits,
                            b->blk_first, b->blk_count));
+        if (stream)
+            VX_CHECK(merkle_absorb_device(ctx, b->lde.p, N_loc, N_loc, c, c0, c1, sponge.p, b->cap_height_loc(),
+                                          b->digests.p, b->cap.p));
     }
     if (nchunks > 1) { EV(ctx, VX_EV_STAGED); EV(ctx, VX_EV_INTT); }      // phases interleave: all reported under "lde"
     EV(ctx, VX_EV_LDE);
-    VX_CHECK(merkle_build_hasher(ctx, b->hasher, b->lde.p, true, N_loc, N_loc, c, b->cap_height_loc(), b->digests.p,
-                                 b->cap.p, ctx->ev[VX_EV_LEAF]));
+    if (stream) {
+        EV(ctx, VX_EV_LEAF);
+        VX_CHECK(merkle_levels_device(ctx, N_loc, b->cap_height_loc(), b->digests.p, b->cap.p));
+    } else {
+        VX_CHECK(merkle_build_hasher(ctx, b->hasher, b->lde.p, true, N_loc, N_loc, c, b->cap_height_loc(), b->digests.p,
+                                     b->cap.p, ctx->ev[VX_EV_LEAF]));
+    }
     EV(ctx, VX_EV_TREE);
     VX_CUDA(cudaStreamSynchronize(ctx->stream));
     return VX_OK;

@@ -54,6 +54,10 @@ struct vx_ctx {
     int ntt_legacy = 0;                 // VX_NTT_LEGACY=1: radix-2 shared-memory passes only (A/B switch)
     int coop_max_pairs = 4096;          // Merkle levels with at most this many pairs use 16 lanes per two_to_one (VX_COOP_MAX_PAIRS)
     int tree_fuse = 1;                  // VX_TREE_FUSE=0: one launch per small Merkle level (A/B switch)
+    uint32_t h2d_chunks = 8;            // VX_H2D_CHUNKS: column chunks of a commit from host memory (copy / transform overlap)
+    uint32_t stream_chunks = 3;         // VX_STREAM_CHUNKS: chunks of the streamed form (8, 16, rest columns measured best on B200)
+    uint32_t h2d_first_groups = 1;      // VX_H2D_FIRST_GROUPS: size of the first streamed chunk in 8-column groups (then doubling)
+    int stream_sponge = 1;              // VX_STREAM_SPONGE: hash each column chunk as it lands (0 = hash after the last chunk)
     int poseidon_variant = 0;           // VX_POSEIDON_VARIANT (A/B switch for profiling): 0 = default, 1 = shared-memory state, 2 = 128-register form
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr; // host->device staging of commit inputs, overlapped with the transforms
@@ -162,6 +166,11 @@ void poseidon_round_constants_host(u64 out[360]);          // merkle.cu: ChaCha8
 int32_t merkle_build_device(vx_ctx* ctx, const u64* leaves, bool col_major, uint64_t stride, uint64_t N,
                             uint32_t c, uint32_t cap_height, u64* digests, u64* cap,
                             cudaEvent_t after_leaves = nullptr);
+// streaming form: absorb columns [col0, col1) of the column-major leaves into the per-leaf sponge state (12 x N); the
+// chunk with col1 == c writes the leaf digests, merkle_levels_device then builds the interior levels
+int32_t merkle_absorb_device(vx_ctx* ctx, const u64* lde, uint64_t stride, uint64_t N, uint32_t c, uint32_t col0,
+                             uint32_t col1, u64* state, uint32_t cap_height, u64* digests, u64* cap);
+int32_t merkle_levels_device(vx_ctx* ctx, uint64_t N, uint32_t cap_height, u64* digests, u64* cap);
 int32_t merkle_paths_device(vx_ctx* ctx, const u64* digests, uint64_t N, uint32_t cap_height,
                             const u64* idx_dev, uint32_t k, u64* siblings_dev);
 int32_t gather_rows_device(vx_ctx* ctx, const u64* leaves, bool col_major, uint64_t stride, uint32_t c,

@@ -168,6 +168,43 @@ __global__ void __launch_bounds__(POSEIDON_BLOCK, MINB) leaf_hash_kernel(const u
     store_digest(dst, s);
 }
 
+// Streaming form of the leaf hash for a commit whose columns arrive in chunks (values uploaded from the host while earlier
+// columns are already transformed): absorb columns [col0, col1) of every leaf into the sponge state kept in `state`
+// (12 x N, lane-major so that a warp's accesses are contiguous).  col0 and every col1 < c are multiples of the rate, so a
+// chunk boundary is a permutation boundary of hash_no_pad; the launch with col1 == c writes the digests.
+__global__ void __launch_bounds__(POSEIDON_BLOCK, 8) leaf_absorb_kernel(const u64* __restrict__ lde, uint64_t stride, uint64_t N,
+                                                                        uint32_t c, uint32_t col0, uint32_t col1,
+                                                                        u64* __restrict__ state, uint32_t sub_bits,
+                                                                        u64* __restrict__ digests, u64* __restrict__ cap) {
+    __shared__ u64 scratch[12 * POSEIDON_BLOCK];
+    uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= N) return;
+    const u64* src = lde + row;
+    u64 s[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = col0 ? state[(uint64_t)i * N + row] : 0;
+    for (uint32_t off = col0; off < col1; off += POSEIDON_RATE) {
+#pragma unroll
+        for (int i = 0; i < POSEIDON_RATE; i++)
+            if (off + i < col1) s[i] = src[(uint64_t)(off + i) * stride];
+        poseidon_permute<0>(s, scratch + threadIdx.x);
+    }
+    if (col1 < c) {
+#pragma unroll
+        for (int i = 0; i < 12; i++) state[(uint64_t)i * N + row] = s[i];
+        return;
+    }
+    u64* dst;
+    if (sub_bits == 0) {
+        dst = cap + 4 * row;
+    } else {
+        uint64_t sub = 1ULL << sub_bits;
+        uint64_t sidx = row >> sub_bits, jj = row & (sub - 1);
+        dst = digests + 4 * (sidx * (2 * sub - 2) + 4 * (jj >> 1) + (jj & 1));
+    }
+    store_digest(dst, s);
+}
+
 // one thread per sibling pair of layer `lvl`: two_to_one -> parent slot (or cap at the top)
 __global__ void __launch_bounds__(POSEIDON_BLOCK) level_hash_kernel(u64* __restrict__ digests, u64* __restrict__ cap,
                                                          uint32_t lvl, uint32_t sub_bits, uint64_t total_pairs) {
@@ -331,6 +368,27 @@ int32_t merkle_build_device(vx_ctx* ctx, const u64* leaves, bool col_major, uint
 #undef LEAF
     VX_LAUNCH_COUNT(ctx, 1);
     if (after_leaves) VX_CUDA(cudaEventRecord(after_leaves, ctx->stream));
+    return merkle_levels_device(ctx, N, cap_height, digests, cap);
+}
+
+int32_t merkle_absorb_device(vx_ctx* ctx, const u64* lde, uint64_t stride, uint64_t N, uint32_t c, uint32_t col0,
+                             uint32_t col1, u64* state, uint32_t cap_height, u64* digests, u64* cap) {
+    const uint32_t log_N = ilog2(N);
+    VX_REQUIRE((1ULL << log_N) == N && cap_height <= log_N, "merkle: bad leaf count / cap height");
+    VX_REQUIRE(c > 4 && col0 < col1 && col1 <= c && col0 % POSEIDON_RATE == 0 && (col1 == c || col1 % POSEIDON_RATE == 0),
+               "merkle: column chunk [%u, %u) of %u is not aligned to the sponge rate", col0, col1, c);
+    unsigned threads = POSEIDON_BLOCK;
+    while (threads > 32 && (N + threads - 1) / threads < 8ULL * (uint64_t)ctx->sm_count) threads >>= 1;
+    leaf_absorb_kernel<<<(unsigned)((N + threads - 1) / threads), threads, 0, ctx->stream>>>(
+        lde, stride, N, c, col0, col1, state, log_N - cap_height, digests, cap);
+    VX_LAUNCH_COUNT(ctx, 1);
+    VX_CUDA(cudaGetLastError());
+    return VX_OK;
+}
+
+// interior levels over leaf digests already in place
+int32_t merkle_levels_device(vx_ctx* ctx, uint64_t N, uint32_t cap_height, u64* digests, u64* cap) {
+    const uint32_t sub_bits = ilog2(N) - cap_height;
     for (uint32_t lvl = 0; lvl < sub_bits;) {
         uint64_t total_pairs = N >> (lvl + 1);
         if (total_pairs <= (uint64_t)ctx->coop_max_pairs && !ctx->ntt_legacy && ctx->tree_fuse) {
