@@ -311,9 +311,16 @@ def main():
         if rank == 0:
             whole = vx.PolynomialBatch.from_values(full0, rate, False, cap, ctx=ctx)
             same = np.array_equal(whole.cap.hashes, cap_all.cpu().numpy().view(np.uint64))
-            whole.close()
             if not same:
                 raise SystemExit("bench.py: sharded commit cap differs from the single-GPU cap")
+        # the same through the end-to-end path (host values: the streamed column pipeline of csrc/shard.cu)
+        one_step(host_sets[0], True)
+        torch.cuda.synchronize()
+        if rank == 0:
+            same = np.array_equal(whole.cap.hashes, cap_host.numpy().view(np.uint64))
+            whole.close()
+            if not same:
+                raise SystemExit("bench.py: sharded commit cap (host values) differs from the single-GPU cap")
         del full0
     launches0 = ctx.launch_count
     phase_acc.clear()
@@ -400,7 +407,7 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u64 (Goldilocks field, 32-bit IMAD limbs)", "data": "synthetic",
             "config": {"workload": workload_name(w),
-                       "parallelism": "single GPU" if G == 1 else f"coset-sharded x{G}: column-sharded iNTT + " + ("NCCL all-gather of coefficients" if use_nccl else "coefficients stored into every rank's gather buffer by the library's own kernel over NVLink peer memory (flags, no NCCL on the data path)") + " + per-rank cosets/cap subtrees",
+                       "parallelism": "single GPU" if G == 1 else f"coset-sharded x{G}: column-sharded iNTT + " + ("NCCL all-gather of coefficients" if use_nccl else "coefficients stored into every rank's gather buffer by the library's own kernel over NVLink peer memory (flags, no NCCL on the data path)") + " + per-rank cosets/cap subtrees" + ("" if use_nccl else "; e2e: column pipeline (copy -> iNTT -> push of 8/16/rest columns, leaf sponge absorbs chunks as they land)"),
                        "l2": f"inputs rotate over {N_INPUT_SETS} sets ({N_INPUT_SETS * elems * 8 / 1e6:.0f} MB) and each step streams a {8 * N * c / 1e6:.0f} MB LDE, both > 126 MB L2",
                        "elements": "n*c input trace elements per commit"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": (1 << cap) * 32,

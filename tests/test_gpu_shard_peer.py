@@ -31,7 +31,28 @@ def test_peer_group_world1_matches_oracle(ctx):
     for _ in range(3):                                   # epochs advance, buffers are reused
         h = g.commit_from_values(cols, cap_out)
         assert np.array_equal(cap_out, want["cap"])
-        g.free_batch(h)
+        b = vx.PolynomialBatch(ctx, h)                   # the rank's shard behind the handle (here: the whole commitment)
+        leaves, digests = b.download()
+        assert np.array_equal(b.polynomials, want["coeffs"])
+        assert np.array_equal(leaves, want["leaves"]) and np.array_equal(digests, want["digests"])
+        b.close()
+    g.close()
+
+
+@pytest.mark.parametrize("c,log_n,rate,cap", [(3, 8, 1, 1), (8, 9, 3, 4), (9, 9, 2, 0), (135, 10, 3, 4), (64, 12, 1, 4)])
+def test_peer_group_world1_shapes(ctx, c, log_n, rate, cap):
+    """The streamed form (sub-blocks of 8 / 16 / rest columns, sponge state carried between chunks) over the shapes that
+    move its boundaries: narrow leaves (no hashing), exactly one rate group, a 1-column tail, the wires shape, STARK rate."""
+    cols = oracle.random_field((c, 1 << log_n), seed=c + log_n)
+    want = oracle.commit_from_values(cols, rate, cap)
+    g = PeerGroup(ctx, ShardPlan(1, 0, c, log_n, rate, cap))
+    cap_out = np.zeros((1 << cap, 4), dtype=np.uint64)
+    h = g.commit_from_values(cols, cap_out)
+    assert np.array_equal(cap_out, want["cap"])
+    b = vx.PolynomialBatch(ctx, h)
+    leaves, digests = b.download()
+    assert np.array_equal(leaves, want["leaves"]) and np.array_equal(digests, want["digests"])
+    b.close()
     g.close()
 
 
@@ -49,14 +70,26 @@ def test_peer_group_same_process(world):
     caps = [np.zeros((1 << cap, 4), dtype=np.uint64) for _ in range(world)]
     errs = []
 
+    N = (1 << log_n) << rate
+    shard_ok = [False] * world
+
     def run(r):
         try:
             p = plans[r]
             mine = np.zeros((p.cols_per_rank, 1 << log_n), dtype=np.uint64)
             mine[: p.col_hi - p.col_lo] = cols[p.col_lo:p.col_hi]
-            for _ in range(2):
+            for it in range(2):
                 h = groups[r].commit_from_values(mine, caps[r])
-                groups[r].free_batch(h)
+                if it == 0:
+                    groups[r].free_batch(h)
+                    continue
+                b = vx.PolynomialBatch(ctxs[r], h)      # this rank's leaf block and cap subtrees
+                leaves, digests = b.download()
+                lo, hi = r * N // world, (r + 1) * N // world
+                per = want["digests"].shape[0] // world
+                shard_ok[r] = (np.array_equal(leaves, want["leaves"][lo:hi])
+                               and np.array_equal(digests, want["digests"][r * per:(r + 1) * per]))
+                b.close()
         except Exception as e:                            # noqa: BLE001
             errs.append(e)
 
@@ -68,6 +101,7 @@ def test_peer_group_same_process(world):
     assert not errs, errs
     for r in range(world):
         assert np.array_equal(caps[r], want["cap"])
+    assert all(shard_ok), shard_ok
     for g in groups:
         g.close()
     for cx in ctxs:

@@ -61,6 +61,13 @@ struct vx_ctx {
     int poseidon_variant = 0;           // VX_POSEIDON_VARIANT (A/B switch for profiling): 0 = default, 1 = shared-memory state, 2 = 128-register form
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr; // host->device staging of commit inputs, overlapped with the transforms
+    cudaStream_t aux_stream = nullptr;  // producer side of a streamed sharded commit (iNTT + peer push of the own slice)
+    int shard_stream = 1;               // VX_SHARD_STREAM=0: sharded commit without the column pipeline (A/B switch)
+    // streamed leaf hashing: one event pair per leaf_absorb launch of the most recent commit (their sum is the leaf-hash
+    // time vx_ctx_phase_ms reports; the launches interleave with the transforms)
+    static constexpr int VX_MAX_ABSORB = 64;
+    cudaEvent_t absorb_ev[2 * VX_MAX_ABSORB] = {};
+    int absorb_count = 0;
     cudaEvent_t copy_ev[16] = {};       // one per column chunk in flight
     cudaEvent_t copy_free = nullptr;    // staging buffer no longer read by the compute stream
     std::mutex mu;                      // serialises calls on this context's stream

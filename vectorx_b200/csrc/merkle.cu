@@ -379,8 +379,11 @@ int32_t merkle_absorb_device(vx_ctx* ctx, const u64* lde, uint64_t stride, uint6
                "merkle: column chunk [%u, %u) of %u is not aligned to the sponge rate", col0, col1, c);
     unsigned threads = POSEIDON_BLOCK;
     while (threads > 32 && (N + threads - 1) / threads < 8ULL * (uint64_t)ctx->sm_count) threads >>= 1;
+    const int slot = ctx->absorb_count < vx_ctx::VX_MAX_ABSORB ? ctx->absorb_count++ : -1;
+    if (slot >= 0) VX_CUDA(cudaEventRecord(ctx->absorb_ev[2 * slot], ctx->stream));
     leaf_absorb_kernel<<<(unsigned)((N + threads - 1) / threads), threads, 0, ctx->stream>>>(
         lde, stride, N, c, col0, col1, state, log_N - cap_height, digests, cap);
+    if (slot >= 0) VX_CUDA(cudaEventRecord(ctx->absorb_ev[2 * slot + 1], ctx->stream));
     VX_LAUNCH_COUNT(ctx, 1);
     VX_CUDA(cudaGetLastError());
     return VX_OK;

@@ -22,6 +22,8 @@
 #include "common.cuh"
 
 #define VX_MAX_SHARDS 16
+#define VX_FLAG_PHASES 16          // 0: whole coefficient slice, 1: cap entries, 2 + j: sub-block j of a streamed commit
+#define VX_MAX_SUB 4               // sub-blocks per rank slice in the streamed form
 
 struct PeerTable {
     u64* base[VX_MAX_SHARDS];
@@ -115,7 +117,7 @@ extern "C" int32_t vx_shard_group_create(vx_ctx* ctx, uint32_t rank, uint32_t wo
     const size_t n = (size_t)1 << log_n;
     s->cap_off = align_up((size_t)world * s->cpr * n, 32);
     s->flag_off = align_up(s->cap_off + ((size_t)4 << cap_height), 32);
-    s->bytes = (s->flag_off + 2 * VX_MAX_SHARDS) * sizeof(u64);
+    s->bytes = (s->flag_off + VX_FLAG_PHASES * VX_MAX_SHARDS / 2) * sizeof(u64);    // u32 flags: [phase][rank]
     cudaError_t e = cudaMalloc((void**)&s->base, s->bytes);          // plain cudaMalloc: exportable through CUDA IPC
     if (e != cudaSuccess) {
         cudaGetLastError();
@@ -246,8 +248,109 @@ static int32_t wait_flags(vx_shard_group* s, uint32_t phase, uint32_t first, uin
 
 #define EV(ctx, i) VX_CUDA(cudaEventRecord((ctx)->ev[i], (ctx)->stream))
 
+// Streamed form (the default): the rank's slice is split into sub-blocks of 8 / 16 / the rest columns.
+//   producer (copy stream + aux stream): copy sub-block j in -> iNTT -> push to every rank's gather buffer, flag (2 + j, rank)
+//   consumer (context stream): global columns in sponge order -- for rank q = 0..G-1, sub-block j: wait for its flag,
+//            extend its columns (own cosets), and absorb every complete group of 8 columns into the leaf sponge.
+// The first rank's first 8 columns reach every consumer after one small copy + transform + push; from then on copies,
+// exchange and transforms hide behind the hashing.  No rank's producer ever waits for a peer, so every flag is raised.
+static int32_t shard_commit_run_stream(vx_shard_group* s, vx_batch* b, const u64* values_local, u64* cap_all_out) {
+    vx_ctx* ctx = s->ctx;
+    const uint64_t n = b->n(), N_loc = b->N_loc();
+    const uint64_t caps_loc = 1ULL << b->cap_height_loc();
+    const size_t slice_bytes = (size_t)s->cpr * n * sizeof(u64);
+    VX_CHECK(b->coeffs.alloc((size_t)s->c * n * sizeof(u64), ctx->stream));
+    VX_CHECK(b->lde.alloc((size_t)s->c * N_loc * sizeof(u64), ctx->stream));
+    VX_CHECK(b->digests.alloc((size_t)2 * (N_loc - caps_loc) * 4 * sizeof(u64), ctx->stream));
+    VX_CHECK(b->cap.alloc((size_t)caps_loc * 4 * sizeof(u64), ctx->stream));
+    DevBuf work, mine, sponge;
+    VX_CHECK(work.alloc(slice_bytes, ctx->stream));
+    VX_CHECK(mine.alloc(slice_bytes, ctx->stream));
+    VX_CHECK(sponge.alloc((size_t)12 * N_loc * sizeof(u64), ctx->stream));
+    EV(ctx, VX_EV_START);
+    ctx->absorb_count = 0;
+    // sub-block boundaries in local columns.  Only the slice that comes first in sponge order (rank 0's) is needed early:
+    // it travels as 8 / 16 / the rest columns; every other slice is consumed long after it has landed and stays whole
+    // (one transform launch instead of three).
+    auto sub_edges = [&](uint32_t q, uint32_t* sub) -> uint32_t {
+        uint32_t k = 0;
+        sub[0] = 0;
+        if (q == 0)
+            for (uint32_t edge = 8, step = 16; k + 1 < VX_MAX_SUB - 1 && edge < s->cpr; edge += step, step *= 2) sub[++k] = edge;
+        sub[++k] = s->cpr;
+        return k;
+    };
+    uint32_t sub[VX_MAX_SUB + 1];
+    const uint32_t nsub = sub_edges(s->rank, sub);
+    // ---- producer
+    VX_CUDA(cudaEventRecord(ctx->copy_free, ctx->stream));                 // allocations above are stream-ordered
+    VX_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_free, 0));
+    VX_CUDA(cudaStreamWaitEvent(ctx->aux_stream, ctx->copy_free, 0));
+    cudaStream_t main_stream = ctx->stream;
+    for (uint32_t j = 0; j < nsub; j++) {
+        const size_t off = (size_t)sub[j] * n, cnt = (size_t)(sub[j + 1] - sub[j]) * n;
+        VX_CUDA(cudaMemcpyAsync(work.p + off, values_local + off, cnt * sizeof(u64), cudaMemcpyDefault, ctx->copy_stream));
+        VX_CUDA(cudaEventRecord(ctx->copy_ev[j], ctx->copy_stream));
+        VX_CUDA(cudaStreamWaitEvent(ctx->aux_stream, ctx->copy_ev[j], 0));
+        ctx->stream = ctx->aux_stream;                                      // the transforms enqueue on ctx->stream
+        int32_t r = intt_batch(ctx, work.p + off, mine.p + off, sub[j + 1] - sub[j], b->log_n);
+        ctx->stream = main_stream;
+        VX_CHECK(r);
+        VX_CHECK(push_block(s, ctx->aux_stream, mine.p + off, cnt, (uint64_t)s->rank * s->cpr * n + off, 2 + j));
+    }
+    VX_CUDA(cudaEventRecord(ctx->copy_ev[VX_MAX_SUB], ctx->aux_stream));  // `work` / `mine` free after this
+    EV(ctx, VX_EV_STAGED);
+    EV(ctx, VX_EV_INTT);
+    // ---- consumer
+    uint32_t absorbed = 0;
+    for (uint32_t q = 0; q < s->world; q++) {
+        uint32_t qsub[VX_MAX_SUB + 1];
+        const uint32_t nq = sub_edges(q, qsub);
+        for (uint32_t j = 0; j < nq; j++) {
+            const uint32_t g0 = q * s->cpr + qsub[j], g1 = q * s->cpr + qsub[j + 1];
+            const uint32_t c0 = g0 < s->c ? g0 : s->c, c1 = g1 < s->c ? g1 : s->c;
+            VX_CHECK(wait_flags(s, 2 + j, q, 1));                           // also orders the reuse of the gather buffer
+            if (c0 >= c1) continue;
+            VX_CHECK(lde_batch(ctx, s->base + (size_t)c0 * n, b->lde.p + (size_t)c0 * N_loc, c1 - c0, b->log_n, b->rate_bits,
+                               b->blk_first, b->blk_count));
+            const uint32_t upto = c1 == s->c ? s->c : (c1 / 8) * 8;
+            if (upto > absorbed) {
+                VX_CHECK(merkle_absorb_device(ctx, b->lde.p, N_loc, N_loc, s->c, absorbed, upto, sponge.p, b->cap_height_loc(),
+                                              b->digests.p, b->cap.p));
+                absorbed = upto;
+            }
+        }
+    }
+    VX_CUDA(cudaMemcpyAsync(b->coeffs.p, s->base, b->coeffs.bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    EV(ctx, VX_EV_LDE);
+    EV(ctx, VX_EV_LEAF);
+    VX_CHECK(merkle_levels_device(ctx, N_loc, b->cap_height_loc(), b->digests.p, b->cap.p));
+    EV(ctx, VX_EV_TREE);
+    VX_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[VX_MAX_SUB], 0));
+    VX_CHECK(push_block(s, ctx->stream, b->cap.p, caps_loc * 4, s->cap_off + (uint64_t)s->rank * caps_loc * 4, 1));
+    VX_CHECK(wait_flags(s, 1, 0, s->world));
+    if (cap_all_out)
+        VX_CHECK(copy_out(ctx, cap_all_out, s->base + s->cap_off, ((size_t)4 << s->cap_height) * sizeof(u64)));
+    VX_CUDA(cudaStreamSynchronize(ctx->stream));
+    VX_CUDA(cudaStreamSynchronize(ctx->aux_stream));
+    if (*s->err_host) {
+        vx_set_error("vx_shard_commit_from_values: timed out waiting for rank %d (peer missing or failed)", *s->err_host - 1);
+        *s->err_host = 0;
+        return VX_ECUDA;
+    }
+    return VX_OK;
+}
+
 static int32_t shard_commit_run(vx_shard_group* s, vx_batch* b, const u64* values_local, u64* cap_all_out) {
     vx_ctx* ctx = s->ctx;
+    // When does the column pipeline pay?  Values in host memory on 2 ranks: the copy of a 68-column slice hides behind the
+    // hashing, 6.58 -> 6.25 ms end to end.  On 4 / 8 ranks the slices are short, a rank hashes only N/4 / N/8 leaves per
+    // column and the extra launches cost more than the copy they hide (3.64 -> 3.71 ms, 2.55 -> 2.79 ms); values already
+    // in HBM: whole-slice launches are faster (5.92 against 6.05 ms on 2 ranks).  VX_SHARD_STREAM = 0 / 2 forces off / on.
+    const bool want_stream = ctx->shard_stream == 2 ||
+                             (ctx->shard_stream == 1 && s->world <= 2 && !vx_is_device_ptr(values_local));
+    if (want_stream && s->c > 4) return shard_commit_run_stream(s, b, values_local, cap_all_out);
+    ctx->absorb_count = 0;
     const uint64_t n = b->n(), N_loc = b->N_loc();
     const uint64_t caps_loc = 1ULL << b->cap_height_loc();
     const size_t slice_bytes = (size_t)s->cpr * n * sizeof(u64);
