@@ -84,6 +84,11 @@ void vx_host_unregister(void* p);
  *   plonky2's interleaved layout. */
 int32_t vx_commit_from_values(vx_ctx* ctx, const uint64_t* cols, uint32_t c, uint32_t log_n,
                               uint32_t rate_bits, uint32_t cap_height, vx_batch** out);
+/* vx_commit_from_values that also leaves a device copy of the VALUES in values_dev_out (c x n, vx_dev_alloc): the wires
+ * commit of prove_with_partition_witness, whose witness values the next phase (Z / partial products) reads again.  With
+ * host `cols` the upload is the commit's own column pipeline -- no separate copy of the witness. */
+int32_t vx_commit_from_values_keep(vx_ctx* ctx, const uint64_t* cols, uint32_t c, uint32_t log_n, uint32_t rate_bits,
+                                   uint32_t cap_height, uint64_t* values_dev_out, vx_batch** out);
 int32_t vx_commit_from_coeffs(vx_ctx* ctx, const uint64_t* coeffs, uint32_t c, uint32_t log_n,
                               uint32_t rate_bits, uint32_t cap_height, vx_batch** out);
 /* Multi-GPU sharding of one commit (coset partition): shard s of S (S a power of two,

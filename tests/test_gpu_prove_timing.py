@@ -48,7 +48,7 @@ def test_prove_verifies_and_times(ctx):
     verify_s = time.perf_counter() - t
     rec = {"degree_bits": bits, "rows": 1 << bits, "wires": 135, "rate_bits": 3, "cap_height": 4,
            "witness": "pinned host memory (vx_host_alloc)", "prove_ms": total, "phase_ms": phases,
-           "pageable_witness": {"prove_ms": total_pageable, "upload witness": phases_pageable.get("upload witness")},
+           "pageable_witness": {"prove_ms": total_pageable, "commit wires": phases_pageable.get("commit wires")},
            "circuit_build_s": build_s, "oracle_verify_s": verify_s,
            "gates": [g.id() for g in circ.gates]}
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)

@@ -47,6 +47,7 @@ SIGNATURES = {
     "vx_shard_group_free": (None, [vp]),
     "vx_commit_from_values": (c_i32, [vp, vp, c_u32, c_u32, c_u32, c_u32, ctypes.POINTER(vp)]),
     "vx_commit_from_coeffs": (c_i32, [vp, vp, c_u32, c_u32, c_u32, c_u32, ctypes.POINTER(vp)]),
+    "vx_commit_from_values_keep": (c_i32, [vp, vp, c_u32, c_u32, c_u32, c_u32, vp, ctypes.POINTER(vp)]),
     "vx_batch_free": (None, [vp]),
     "vx_batch_shape": (c_i32, [vp, u32p]),
     "vx_batch_cap": (c_i32, [vp, vp]),

@@ -210,7 +210,7 @@ extern "C" void vx_host_unregister(void* p) {
 
 #define EV(ctx, i) VX_CUDA(cudaEventRecord((ctx)->ev[i], (ctx)->stream))
 
-static int32_t commit_run(vx_ctx* ctx, vx_batch* b, const u64* src, bool is_values) {
+static int32_t commit_run(vx_ctx* ctx, vx_batch* b, const u64* src, bool is_values, u64* keep = nullptr) {
     const uint32_t c = b->c;
     const uint64_t n = b->n(), N_loc = b->N_loc();
     const size_t coeff_bytes = (size_t)c * n * sizeof(u64);
@@ -257,14 +257,18 @@ static int32_t commit_run(vx_ctx* ctx, vx_batch* b, const u64* src, bool is_valu
         if (c1 == c0) continue;
         const size_t off = (size_t)c0 * n, bytes = (size_t)(c1 - c0) * n * sizeof(u64);
         u64* dst = is_values ? work + off : b->coeffs.p + off;
+        // `keep` (vx_commit_from_values_keep): the chunk lands in the caller's device copy of the values first and is
+        // duplicated into the work buffer on the device (the inverse transform runs in place)
+        u64* land = keep ? keep + off : dst;
         if (nchunks > 1) {
-            VX_CUDA(cudaMemcpyAsync(dst, src + off, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+            VX_CUDA(cudaMemcpyAsync(land, src + off, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
             VX_CUDA(cudaEventRecord(ctx->copy_ev[k], ctx->copy_stream));
             VX_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[k], 0));
         } else {
-            VX_CUDA(cudaMemcpyAsync(dst, src + off, bytes, cudaMemcpyDefault, ctx->stream));
-            EV(ctx, VX_EV_STAGED);
+            VX_CUDA(cudaMemcpyAsync(land, src + off, bytes, cudaMemcpyDefault, ctx->stream));
         }
+        if (keep) VX_CUDA(cudaMemcpyAsync(dst, land, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (nchunks == 1) EV(ctx, VX_EV_STAGED);
         if (is_values) VX_CHECK(intt_batch(ctx, work + off, b->coeffs.p + off, c1 - c0, b->log_n));
         if (nchunks == 1) EV(ctx, VX_EV_INTT);
         VX_CHECK(lde_batch(ctx, b->coeffs.p + off, b->lde.p + (size_t)c0 * N_loc, c1 - c0, b->log_n, b->rate_bits,
@@ -289,7 +293,7 @@ static int32_t commit_run(vx_ctx* ctx, vx_batch* b, const u64* src, bool is_valu
 
 static int32_t commit_impl(vx_ctx* ctx, const u64* src, bool is_values, uint32_t c, uint32_t log_n,
                            uint32_t rate_bits, uint32_t cap_height, uint32_t shard_index, uint32_t shard_count,
-                           vx_batch** out, uint32_t hasher = VX_HASHER_POSEIDON) {
+                           vx_batch** out, uint32_t hasher = VX_HASHER_POSEIDON, u64* keep = nullptr) {
     VX_REQUIRE(ctx && src && out, "commit: NULL argument");
     *out = nullptr;
     VX_REQUIRE(hasher <= VX_HASHER_POSEIDON_BN128, "commit: unknown hasher %u", hasher);
@@ -310,7 +314,7 @@ static int32_t commit_impl(vx_ctx* ctx, const u64* src, bool is_values, uint32_t
     b->hasher = hasher;
     b->blk_count = (1u << rate_bits) >> sbits;
     b->blk_first = shard_index * b->blk_count;
-    int32_t r = commit_run(ctx, b, src, is_values);
+    int32_t r = commit_run(ctx, b, src, is_values, keep);
     if (r != VX_OK) {
         cudaStreamSynchronize(ctx->stream);
         delete b;
@@ -323,6 +327,13 @@ static int32_t commit_impl(vx_ctx* ctx, const u64* src, bool is_values, uint32_t
 extern "C" int32_t vx_commit_from_values(vx_ctx* ctx, const uint64_t* cols, uint32_t c, uint32_t log_n,
                                          uint32_t rate_bits, uint32_t cap_height, vx_batch** out) {
     return commit_impl(ctx, (const u64*)cols, true, c, log_n, rate_bits, cap_height, 0, 1, out);
+}
+extern "C" int32_t vx_commit_from_values_keep(vx_ctx* ctx, const uint64_t* cols, uint32_t c, uint32_t log_n,
+                                              uint32_t rate_bits, uint32_t cap_height, uint64_t* values_dev_out,
+                                              vx_batch** out) {
+    VX_REQUIRE(values_dev_out && vx_is_device_ptr(values_dev_out), "vx_commit_from_values_keep: values_dev_out must be device memory");
+    return commit_impl(ctx, (const u64*)cols, true, c, log_n, rate_bits, cap_height, 0, 1, out, VX_HASHER_POSEIDON,
+                       (u64*)values_dev_out);
 }
 extern "C" int32_t vx_commit_from_coeffs(vx_ctx* ctx, const uint64_t* coeffs, uint32_t c, uint32_t log_n,
                                          uint32_t rate_bits, uint32_t cap_height, vx_batch** out) {

@@ -318,8 +318,12 @@ extern "C" int32_t vx_pow_grind(vx_ctx* ctx, const uint64_t state[12], uint32_t 
     VX_CUDA(cudaMemcpyAsync(ds.p, st, sizeof st, cudaMemcpyHostToDevice, ctx->stream));
     unsigned long long best = ~0ULL;
     VX_CUDA(cudaMemcpyAsync(db.p, &best, 8, cudaMemcpyHostToDevice, ctx->stream));
-    const uint64_t batch = 1ULL << 20;           // candidates per launch; expected work is 2^min_zeros
-    for (uint64_t base = 0; base < GL_P; base += batch) {
+    // candidates per launch: expected work is 2^min_zeros permutations, so the first launch tries twice that (86 % hit
+    // rate, ~0.14 ms for 16 bits) and every miss doubles the batch up to 2^22
+    uint64_t batch = 2ULL << min_zeros;
+    if (batch < (1ULL << 14)) batch = 1ULL << 14;
+    if (batch > (1ULL << 22)) batch = 1ULL << 22;
+    for (uint64_t base = 0; base < GL_P; base += batch, batch = batch < (1ULL << 22) ? batch * 2 : batch) {
         pow_kernel<<<(unsigned)(batch / POSEIDON_BLOCK), POSEIDON_BLOCK, 0, ctx->stream>>>(ds.p, pos, min_zeros, base,
                                                                                         (unsigned long long*)db.p);
         VX_LAUNCH_COUNT(ctx, 1);

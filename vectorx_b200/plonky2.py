@@ -148,6 +148,22 @@ class PolynomialBatch:
         return cls._commit("vx_commit_from_coeffs_hasher", polynomials, rate_bits, blinding, cap_height, ctx, hasher)
 
     @classmethod
+    def from_values_keep(cls, values, values_dev, rate_bits: int, cap_height: int, ctx: Context | None = None) -> "PolynomialBatch":
+        """from_values that also fills `values_dev` (a DeviceArray of the same shape) with the values: the wires commit of
+        the prover, which reads the witness again for Z / partial products."""
+        ctx = ctx or default_context()
+        c, n = int(values.shape[0]), int(values.shape[1])
+        log_n = n.bit_length() - 1
+        if (1 << log_n) != n:
+            raise VxError(f"polynomial length {n} is not a power of two")
+        if isinstance(values, np.ndarray):
+            values = np.ascontiguousarray(values, dtype=np.uint64)
+        h = vp()
+        check(load().vx_commit_from_values_keep(ctx.handle, ptr(values), c, log_n, rate_bits, cap_height, ptr(values_dev),
+                                                ctypes.byref(h)), "vx_commit_from_values_keep")
+        return cls(ctx, h)
+
+    @classmethod
     def from_coeffs_shard(cls, polynomials, rate_bits: int, cap_height: int, shard_index: int, shard_count: int,
                           ctx: Context | None = None) -> "PolynomialBatch":
         """One GPU's share of a commit: leaves [s*N/S, (s+1)*N/S) from all coefficient columns."""

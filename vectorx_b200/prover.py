@@ -115,9 +115,10 @@ def prove(circ: CircuitData, wires: np.ndarray, public_inputs, trace: dict | Non
     ch.observe_hash(circ.circuit_digest)
     ch.observe_hash(pi_hash)
     lap("host")
-    wires_d = DeviceArray.from_host(ctx, wires)          # the witness goes to the GPU once; every later phase reads it there
-    lap("upload witness")
-    wires_c = PolynomialBatch.from_values(wires_d, rate, False, cap_h, ctx=ctx)
+    # the witness goes to the GPU once, inside the commit's own column pipeline (copy of chunk k+1 under the transforms
+    # and hashing of chunk k); every later phase reads the device copy
+    wires_d = DeviceArray(ctx, wires.shape)
+    wires_c = PolynomialBatch.from_values_keep(wires, wires_d, rate, cap_h, ctx=ctx)
     lap("commit wires")
     ch.observe_cap(wires_c.cap.hashes.tolist())
     betas = ch.get_n_challenges(nch)
