@@ -46,6 +46,33 @@ struct QuotParams {
     TwiddleView tw;
 };
 
+GL_D u64 lds_u64(uint32_t addr) {
+    u64 v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+    return v;
+}
+GL_D u64 ldg_u64(const u64* p) {
+    u64 v;
+    asm volatile("ld.global.nc.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+// hot-operation flags in the top bits of a device instruction word's immediate (bits 0..25 stay the immediate)
+#define QF_LOADW 0x80000000u
+#define QF_EMIT 0x40000000u
+#define QF_MADK 0x20000000u
+#define QF_RANGE4 0x10000000u
+#define QF_SUB 0x08000000u
+#define QF_MUL 0x04000000u
+#define QF_WAIT 0x02000000u        // inserted by the host after every run of column loads: wait for the asynchronous copies
+#define QIMM_MASK 0x01ffffffu
+#define VX_OP_WAIT_INTERNAL 0xfe
+// column load: asynchronous 8-byte global -> shared copy straight into the register file (no stall until the run's WAIT)
+GL_D void cp_async_u64(uint32_t saddr, const u64* g) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(saddr), "l"(g) : "memory");
+}
+GL_D void cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+GL_D void sts_u64(uint32_t addr, u64 v) { asm volatile("st.shared.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory"); }
+
 // 12 register numbers from two operand words
 #define QREGS12(w0, w1, k) (((k) < 8 ? (uint32_t)((w0) >> (8 * (k))) : (uint32_t)((w1) >> (8 * ((k) - 8)))) & 0xffu)
 
@@ -79,75 +106,112 @@ __global__ void __launch_bounds__(QBLOCK) quotient_kernel(const QuotParams p) {
         if (nch > 1) gl_acc_mad(tot[1], _v, __ldg(apow1 + (idx))); \
     } while (0)
 
-    // ---- Z(1) = 1 and the permutation argument
+    // ---- Z(1) = 1 and the permutation argument.  The chunk loop is outermost so that every routed wire and sigma value is
+    // loaded ONCE and used for all challenges.
     const uint32_t chunks = (p.num_routed + p.max_degree - 1) / p.max_degree;
+    u64 prev[2] = {0, 0};
     for (uint32_t k = 0; k < nch; k++) {
-        u64 z = p.zpp[(uint64_t)k * N + j];
+        const u64 z = p.zpp[(uint64_t)k * N + j];
         ADD_TERM(k, gl_mul_cc(l0, gl_sub(z, 1)));
-        u64 prev = z;
-        const u64 beta = p.betas[k], gamma = p.gammas[k];
-        for (uint32_t c = 0; c < chunks; c++) {
-            u64 num = 1, den = 1;
-            uint32_t hi = min(p.num_routed, (c + 1) * p.max_degree);
-            for (uint32_t w = c * p.max_degree; w < hi; w++) {
-                u64 wv = p.wires[(uint64_t)w * N + j];
-                u64 sg = p.cs[(uint64_t)(p.num_constants + w) * N + j];
-                u64 a = gl_add(gl_mul_add_cc(x, __ldg(p.beta_k + k * p.num_routed + w), wv), gamma);
-                u64 b = gl_add(gl_mul_add_cc(sg, beta, wv), gamma);
-                num = gl_mul_cc(num, a);
-                den = gl_mul_cc(den, b);
+        prev[k] = z;
+    }
+    for (uint32_t c = 0; c < chunks; c++) {
+        u64 num[2] = {1, 1}, den[2] = {1, 1};
+        const uint32_t hi = min(p.num_routed, (c + 1) * p.max_degree);
+        for (uint32_t w = c * p.max_degree; w < hi; w++) {
+            const u64 wv = p.wires[(uint64_t)w * N + j];
+            const u64 sg = p.cs[(uint64_t)(p.num_constants + w) * N + j];
+#pragma unroll
+            for (uint32_t k = 0; k < 2; k++) {
+                if (k < nch) {
+                    const u64 a = gl_add(gl_mul_add_cc(x, __ldg(p.beta_k + k * p.num_routed + w), wv), p.gammas[k]);
+                    const u64 b = gl_add(gl_mul_add_cc(sg, p.betas[k], wv), p.gammas[k]);
+                    num[k] = gl_mul_cc(num[k], a);
+                    den[k] = gl_mul_cc(den[k], b);
+                }
             }
-            u64 next = (c + 1 < chunks) ? p.zpp[(uint64_t)(nch + k * p.num_pp + c) * N + j]
-                                        : p.zpp[(uint64_t)k * N + jn];
-            ADD_TERM(nch + k * chunks + c, gl_sub(gl_mul_cc(prev, num), gl_mul_cc(next, den)));
-            prev = next;
+        }
+#pragma unroll
+        for (uint32_t k = 0; k < 2; k++) {
+            if (k < nch) {
+                const u64 next = (c + 1 < chunks) ? p.zpp[(uint64_t)(nch + k * p.num_pp + c) * N + j]
+                                                  : p.zpp[(uint64_t)k * N + jn];
+                ADD_TERM(nch + k * chunks + c, gl_sub(gl_mul_cc(prev[k], num[k]), gl_mul_cc(next, den[k])));
+                prev[k] = next;
+            }
         }
     }
 
     // ---- gate constraints: bytecode interpreter.  The program is the same for every thread: the block stages it through
     // shared memory QCHUNK words at a time, so an instruction fetch is a broadcast LDS instead of a dependent global load.
+    // Register file and program are addressed with 32-bit shared-window addresses (ld/st.shared): an operand access is
+    // one shift-add + one LDS, and the per-point column pointers are pinned so that nothing is recomputed per
+    // instruction (the first form of this loop spent 41 of its ~87 instructions per bytecode operation on decode).
     GlAcc h[2];
     uint32_t cidx = 0;
     bool done = false;
+    uint32_t prog_sa = (uint32_t)__cvta_generic_to_shared(prog_s);
+    uint32_t reg_sa = (uint32_t)__cvta_generic_to_shared(R);
+    const u64* wires_j = p.wires + j;
+    const u64* cs_j = p.cs + j;
+    uint64_t Nq = N;
+    // opaque to the optimiser: held in registers instead of being recomputed from special registers per instruction
+    asm volatile("" : "+l"(wires_j), "+l"(cs_j), "+r"(prog_sa), "+r"(reg_sa), "+l"(Nq));
+#define RLD(i) lds_u64(reg_sa + ((i) << 10))
+#define RST(i, v) sts_u64(reg_sa + ((i) << 10), (v))
+    static_assert(QBLOCK * sizeof(u64) == 1024, "register-file row pitch is 1 KB");
     for (uint32_t base = 0; base < p.program_len && !done; base += QCHUNK) {
         __syncthreads();
         for (uint32_t t = threadIdx.x; t < QCHUNK; t += QBLOCK) prog_s[t] = __ldg(p.program + base + t);
         __syncthreads();
-        uint32_t pc = 0;
-        while (pc < QCHUNK) {
-            const u64 ins = prog_s[pc++];
-            const uint32_t op = (uint32_t)ins & 0xff, dst = (uint32_t)(ins >> 8) & 0xff;
-            const uint32_t ra = (uint32_t)(ins >> 16) & 0xff, rb = (uint32_t)(ins >> 24) & 0xff;
-            const uint32_t imm = (uint32_t)(ins >> 32);
+        uint32_t pa = prog_sa;                               // shared address of the next instruction word
+        const uint32_t pend = prog_sa + QCHUNK * 8;
+        while (pa < pend) {
+            const u64 ins = lds_u64(pa);
+            pa += 8;
+            // device word (re-laid by vx_quotient): the most frequent operations are flagged in the top bits of the
+            // immediate, tested one bit at a time in order of frequency (a switch compiles to a balanced tree instead)
+            const uint32_t lo = (uint32_t)ins, hi = (uint32_t)(ins >> 32), imm = hi & QIMM_MASK;
+            const uint32_t dst = (lo >> 8) & 0xff, ra = (lo >> 16) & 0xff, rb = lo >> 24;
+            if (hi & QF_LOADW) { cp_async_u64(reg_sa + (dst << 10), wires_j + (uint64_t)imm * Nq); continue; }
+            if (hi & QF_EMIT) {
+                const u64 v = RLD(ra);
+                gl_acc_mad(h[0], v, __ldg(apow0 + cidx));
+                if (nch > 1) gl_acc_mad(h[1], v, __ldg(apow1 + cidx));
+                cidx++;
+                continue;
+            }
+            if (hi & QF_MADK) { const u64 k = lds_u64(pa); pa += 8; RST(dst, gl_mul_add_cc(RLD(ra), k, RLD(rb))); continue; }
+            if (hi & QF_RANGE4) {
+                // a (a-1)(a-2)(a-3) = y (y + 2) with y = a (a - 3): two multiplications instead of three
+                const u64 a = RLD(ra);
+                const u64 y = gl_mul_cc(a, gl_sub(a, 3));
+                RST(dst, gl_mul_cc(y, gl_add(y, 2)));
+                continue;
+            }
+            if (hi & QF_WAIT) { cp_async_wait(); continue; }
+            if (hi & QF_SUB) { RST(dst, gl_sub(RLD(ra), RLD(rb))); continue; }
+            if (hi & QF_MUL) { RST(dst, gl_mul_cc(RLD(ra), RLD(rb))); continue; }
+            const uint32_t op = lo & 0xff;
             if (op == VX_OP_END) { done = true; break; }
             switch (op) {
-                case VX_OP_LOADW: REG(dst) = p.wires[(uint64_t)imm * N + j]; break;
-                case VX_OP_LOADC: REG(dst) = p.cs[(uint64_t)imm * N + j]; break;
-                case VX_OP_LOADPI: REG(dst) = p.pi_hash[imm & 3]; break;
-                case VX_OP_LOADK: REG(dst) = prog_s[pc++]; break;
-                case VX_OP_ADD: REG(dst) = gl_add(REG(ra), REG(rb)); break;
-                case VX_OP_SUB: REG(dst) = gl_sub(REG(ra), REG(rb)); break;
-                case VX_OP_MUL: REG(dst) = gl_mul_cc(REG(ra), REG(rb)); break;
-                case VX_OP_ADDK: REG(dst) = gl_add(REG(ra), prog_s[pc++]); break;
-                case VX_OP_MULK: REG(dst) = gl_mul_cc(REG(ra), prog_s[pc++]); break;
-                case VX_OP_RSUBK: REG(dst) = gl_sub(prog_s[pc++], REG(ra)); break;
-                case VX_OP_SUBK: REG(dst) = gl_sub(REG(ra), prog_s[pc++]); break;
-                case VX_OP_MADK: REG(dst) = gl_mul_add_cc(REG(ra), prog_s[pc++], REG(rb)); break;
-                case VX_OP_SBOX7: REG(dst) = gl_pow7_cc(REG(ra)); break;
-                case VX_OP_RANGE4: {
-                    const u64 a = gl_canon(REG(ra));
-                    const u64 t01 = gl_mul_cc(a, gl_sub(a, 1));
-                    REG(dst) = gl_mul_cc(t01, gl_mul_cc(gl_sub(a, 2), gl_sub(a, 3)));
-                    break;
-                }
+                case VX_OP_SBOX7: RST(dst, gl_pow7_cc(RLD(ra))); break;
+                case VX_OP_LOADC: cp_async_u64(reg_sa + (dst << 10), cs_j + (uint64_t)imm * Nq); break;
+                case VX_OP_LOADPI: RST(dst, p.pi_hash[imm & 3]); break;
+                case VX_OP_LOADK: RST(dst, lds_u64(pa)); pa += 8; break;
+                case VX_OP_ADD: RST(dst, gl_add(RLD(ra), RLD(rb))); break;
+                case VX_OP_ADDK: RST(dst, gl_add(RLD(ra), lds_u64(pa))); pa += 8; break;
+                case VX_OP_MULK: RST(dst, gl_mul_cc(RLD(ra), lds_u64(pa))); pa += 8; break;
+                case VX_OP_RSUBK: RST(dst, gl_sub(lds_u64(pa), RLD(ra))); pa += 8; break;
+                case VX_OP_SUBK: RST(dst, gl_sub(RLD(ra), lds_u64(pa))); pa += 8; break;
                 case VX_OP_MDS12K:
                 case VX_OP_DENSE12:
                 case VX_OP_PARTIAL12: {
-                    const u64 s0 = prog_s[pc], s1 = prog_s[pc + 1], d0 = prog_s[pc + 2], d1 = prog_s[pc + 3];
-                    pc += 4;
+                    const u64 s0 = lds_u64(pa), s1 = lds_u64(pa + 8), d0 = lds_u64(pa + 16), d1 = lds_u64(pa + 24);
+                    pa += 32;
                     u64 st[12];
 #pragma unroll
-                    for (int k = 0; k < 12; k++) st[k] = REG(QREGS12(s0, s1, k));
+                    for (int k = 0; k < 12; k++) st[k] = RLD(QREGS12(s0, s1, k));
                     if (op == VX_OP_MDS12K) {
                         poseidon_mds_add_freq(st, c_pos.rc22 + 36 * imm);
                     } else if (op == VX_OP_DENSE12) {
@@ -166,22 +230,15 @@ __global__ void __launch_bounds__(QBLOCK) quotient_kernel(const QuotParams p) {
                         st[0] = gl_acc_reduce(d);
                     }
 #pragma unroll
-                    for (int k = 0; k < 12; k++) REG(QREGS12(d0, d1, k)) = st[k];
+                    for (int k = 0; k < 12; k++) RST(QREGS12(d0, d1, k), st[k]);
                     break;
                 }
                 case VX_OP_BEGINGATE:
                     gl_acc_init(h[0], 0); gl_acc_init(h[1], 0);
                     cidx = p.num_perm_terms;
                     break;
-                case VX_OP_EMIT: {
-                    u64 v = REG(ra);
-                    gl_acc_mad(h[0], v, __ldg(apow0 + cidx));
-                    if (nch > 1) gl_acc_mad(h[1], v, __ldg(apow1 + cidx));
-                    cidx++;
-                    break;
-                }
                 case VX_OP_ENDGATE: {
-                    u64 f = (ra == 255) ? 1 : REG(ra);
+                    const u64 f = (ra == 255) ? 1 : RLD(ra);
                     gl_acc_mad(tot[0], f, gl_acc_reduce(h[0]));
                     if (nch > 1) gl_acc_mad(tot[1], f, gl_acc_reduce(h[1]));
                     break;
@@ -190,6 +247,8 @@ __global__ void __launch_bounds__(QBLOCK) quotient_kernel(const QuotParams p) {
             }
         }
     }
+#undef RLD
+#undef RST
     const u64 zi = p.zh_inv[coset];
     if (live)
         for (uint32_t k = 0; k < nch; k++) p.out[(uint64_t)k * N + j] = gl_canon(gl_mul_cc(gl_acc_reduce(tot[k]), zi));
@@ -242,6 +301,7 @@ extern "C" int32_t vx_quotient(vx_ctx* ctx, const vx_circuit_desc* d, vx_batch* 
     std::vector<u64> prog;
     prog.reserve(d->program_len + 2 * QCHUNK);
     uint32_t max_reg = 0;
+    bool loads_pending = false;
     auto oplen = [](uint32_t op) -> uint32_t {
         switch (op) {
             case VX_OP_LOADK: case VX_OP_ADDK: case VX_OP_MULK: case VX_OP_RSUBK: case VX_OP_SUBK: case VX_OP_MADK: return 2;
@@ -254,8 +314,27 @@ extern "C" int32_t vx_quotient(vx_ctx* ctx, const vx_circuit_desc* d, vx_batch* 
         const uint32_t op = (uint32_t)ins & 0xff, len = oplen(op);
         VX_REQUIRE(op <= VX_OP_MADK && pc + len <= d->program_len, "vx_quotient: malformed program at word %llu",
                    (unsigned long long)pc);
+        const bool is_load = op == VX_OP_LOADW || op == VX_OP_LOADC;
+        if (loads_pending && !is_load) {                       // end of a run of column loads: one wait for all of them
+            prog.push_back((u64)VX_OP_WAIT_INTERNAL | ((u64)QF_WAIT << 32));
+            loads_pending = false;
+        }
+        if (is_load) loads_pending = true;
         while (prog.size() % QCHUNK + len > QCHUNK) prog.push_back(VX_OP_NOP);
-        for (uint32_t k = 0; k < len; k++) prog.push_back(d->program[pc + k]);
+        VX_REQUIRE((ins >> 32) <= QIMM_MASK, "vx_quotient: immediate of the instruction at word %llu out of range",
+                   (unsigned long long)pc);
+        uint32_t flag = 0;
+        switch (op) {
+            case VX_OP_LOADW: flag = QF_LOADW; break;
+            case VX_OP_EMIT: flag = QF_EMIT; break;
+            case VX_OP_MADK: flag = QF_MADK; break;
+            case VX_OP_RANGE4: flag = QF_RANGE4; break;
+            case VX_OP_SUB: flag = QF_SUB; break;
+            case VX_OP_MUL: flag = QF_MUL; break;
+            default: break;
+        }
+        prog.push_back(ins | ((u64)flag << 32));
+        for (uint32_t k = 1; k < len; k++) prog.push_back(d->program[pc + k]);
         if (len == 5) {
             for (uint32_t w = 1; w < 5; w++)
                 for (int k = 0; k < ((w & 1) ? 8 : 4); k++)

@@ -25,6 +25,9 @@ OP = dict(END=0, LOADW=1, LOADC=2, LOADPI=3, LOADK=4, ADD=5, SUB=6, MUL=7, ADDK=
           EMIT=12, BEGINGATE=13, ENDGATE=14, NOP=15, SBOX7=16, MDS12K=17, DENSE12=18, PARTIAL12=19, RANGE4=20, MADK=21)
 MULTI = ("MDS12K", "DENSE12", "PARTIAL12")        # 12 registers in, 12 registers out
 NUM_REGS = 64
+LOAD_HOIST = 8          # column loads emitted together (one memory latency per group on the device)
+LOAD_WINDOW = 400       # how far ahead (in traced operations) a load may be pulled
+LOAD_RESERVE = 40       # registers that must stay free for the rest of the gate while hoisting
 MDS_CIRC = [17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20]
 MDS_DIAG0 = 8
 
@@ -590,8 +593,35 @@ def assemble(trace: Trace, filter_id):
     def enc(op, dst=0, a=0, b=0, imm=0):
         return OP[op] | (dst << 8) | (a << 16) | (b << 24) | ((imm & 0xFFFFFFFF) << 32)
 
+    # Column loads are hoisted in groups: when a LOADW / LOADC is reached, the next LOAD_HOIST - 1 loads of the gate are
+    # emitted with it (their registers stay allocated until their original last use).  The device issues loads as
+    # asynchronous global -> shared copies and waits once per run, so a group costs one memory latency instead of eight.
+    emitted = set()
+
+    def emit_load(i):
+        lop, _, _, limm = ops[i]
+        rd = free.pop()
+        reg[i] = rd
+        words.append(enc(lop, rd, 0, 0, limm))
+        emitted.add(i)
+        if i not in last:
+            free.append(rd)
+
     for idx, (op, a, b, imm) in enumerate(ops):
         if op == "RES":
+            continue
+        if op in ("LOADW", "LOADC"):
+            if idx in emitted:
+                continue
+            if not free:
+                raise RuntimeError("gate program needs more than %d registers" % NUM_REGS)
+            emit_load(idx)
+            k, j = 1, idx + 1
+            while k < LOAD_HOIST and j < len(ops) and j < idx + LOAD_WINDOW and len(free) > LOAD_RESERVE:
+                if ops[j][0] in ("LOADW", "LOADC") and j not in emitted:
+                    emit_load(j)
+                    k += 1
+                j += 1
             continue
         if op in MULTI:
             srcs = [reg[v] for v in a]
@@ -622,7 +652,7 @@ def assemble(trace: Trace, filter_id):
             raise RuntimeError("gate program needs more than %d registers" % NUM_REGS)
         rd = free.pop()
         reg[idx] = rd
-        if op in ("LOADW", "LOADC", "LOADPI"):
+        if op == "LOADPI":
             words.append(enc(op, rd, 0, 0, imm))
         elif op == "LOADK":
             words += [enc(op, rd), imm]
