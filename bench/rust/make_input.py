@@ -1,0 +1,29 @@
+"""Writes the value matrices the Rust harness reads (run from the repo root):
+  golden  : the 2^10 x 135 case whose cap / rows / paths are frozen in tests/golden/commit_golden.npz (seed 302)
+  config1 : BASELINE.json config 1 (2^16 x 135, rate 3, cap 4), the bench.py input set 0
+"""
+import os
+import struct
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+import oracle  # noqa: E402  (test infrastructure: input generator only)
+
+
+def write(path, cols, rate_bits, cap_height):
+    c, n = cols.shape
+    with open(path, "wb") as f:
+        f.write(struct.pack("<4I", c, n.bit_length() - 1, rate_bits, cap_height))
+        f.write(np.ascontiguousarray(cols, dtype="<u8").tobytes())
+    print(path, cols.shape)
+
+
+if __name__ == "__main__":
+    here = os.path.dirname(os.path.abspath(__file__))
+    write(os.path.join(here, "golden_values.bin"), oracle.random_field((135, 1 << 10), seed=302), 3, 4)
+    rng = np.random.default_rng(0x5EED0001)
+    write(os.path.join(here, "config1_values.bin"),
+          rng.integers(0, 0xFFFFFFFF00000001, size=(135, 1 << 16), dtype=np.uint64), 3, 4)
