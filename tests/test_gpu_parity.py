@@ -199,6 +199,27 @@ def test_full_size_properties_config1(ctx):
     assert np.array_equal(((r1.astype(object) + r2.astype(object)) % P).astype(np.uint64), r3)
 
 
+@pytest.mark.parametrize("c,log_n,src", [(135, 9, "host"), (24, 10, "host"), (9, 8, "host"), (40, 9, "device")])
+def test_commit_from_values_keep(ctx, c, log_n, src):
+    """vx_commit_from_values_keep: the commitment equals from_values and the caller's device buffer holds the values
+    (chunked streaming path for wide host inputs, single-copy path for narrow or device-resident ones)."""
+    from vectorx_b200._lib import DeviceArray
+    cols = oracle.random_field((c, 1 << log_n), seed=7 * c + log_n)
+    want = oracle.commit_from_values(cols, 3, 4)
+    keep = DeviceArray(ctx, cols.shape)
+    source = cols if src == "host" else DeviceArray.from_host(ctx, cols)
+    b = vx.PolynomialBatch.from_values_keep(source, keep, 3, 4, ctx=ctx)
+    assert np.array_equal(b.cap.hashes, want["cap"])
+    assert np.array_equal(b.polynomials, want["coeffs"])
+    leaves, digests = b.download()
+    assert np.array_equal(leaves, want["leaves"]) and np.array_equal(digests, want["digests"])
+    assert np.array_equal(keep.to_host(), cols)
+    b.close()
+    keep.close()
+    with pytest.raises(vx.VxError):
+        vx.PolynomialBatch.from_values_keep(cols, cols.copy(), 3, 4, ctx=ctx)      # keep buffer must be device memory
+
+
 def test_pinned_host_buffers(ctx):
     """vx_host_alloc / vx_host_register: a commit whose values come from page-locked memory equals the pageable one."""
     from vectorx_b200._lib import check, load
