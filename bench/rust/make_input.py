@@ -4,13 +4,21 @@
 """
 import os
 import struct
-import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, ROOT)
-import oracle  # noqa: E402  (test infrastructure: input generator only)
+P = 0xFFFFFFFF00000001
+
+
+def random_field(shape, seed):
+    """The generator the golden fixtures were made with (tests/golden/make_golden.py): numpy PCG64 with rejection."""
+    rng = np.random.default_rng(seed)
+    a = rng.integers(0, 2**64, size=shape, dtype=np.uint64)
+    bad = a >= np.uint64(P)
+    while bad.any():
+        a[bad] = rng.integers(0, 2**64, size=int(bad.sum()), dtype=np.uint64)
+        bad = a >= np.uint64(P)
+    return a
 
 
 def write(path, cols, rate_bits, cap_height):
@@ -23,7 +31,7 @@ def write(path, cols, rate_bits, cap_height):
 
 if __name__ == "__main__":
     here = os.path.dirname(os.path.abspath(__file__))
-    write(os.path.join(here, "golden_values.bin"), oracle.random_field((135, 1 << 10), seed=302), 3, 4)
+    write(os.path.join(here, "golden_values.bin"), random_field((135, 1 << 10), seed=302), 3, 4)
     rng = np.random.default_rng(0x5EED0001)
     write(os.path.join(here, "config1_values.bin"),
           rng.integers(0, 0xFFFFFFFF00000001, size=(135, 1 << 16), dtype=np.uint64), 3, 4)
