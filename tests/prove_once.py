@@ -1,4 +1,6 @@
-"""Runs warm-up + one timed proof of a synthetic 2^k-row circuit (test infrastructure builds the circuit); used under ncu."""
+"""Profiling helper (lives under tests/ because the synthetic circuit comes from the test oracle): warm-up + one timed
+proof of a 2^k-row circuit, bracketed by cudaProfilerStart/Stop.  Used under ncu:
+  VX_PROVE_BITS=16 ncu --set full -k regex:quotient_kernel -s 1 -c 1 -o out python tests/prove_once.py"""
 import os, sys, json, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import vectorx_b200 as vx
