@@ -69,7 +69,7 @@ extern "C" int32_t vx_ctx_create(int32_t device, vx_ctx** out) {
     if (const char* v = getenv("VX_COOP_MAX_PAIRS")) ctx->coop_max_pairs = atoi(v);
     if (const char* v = getenv("VX_STREAM_SPONGE")) ctx->stream_sponge = atoi(v);
     if (const char* v = getenv("VX_SHARD_STREAM")) ctx->shard_stream = atoi(v);
-    if (const char* v = getenv("VX_STREAM_CHUNKS")) { int k = atoi(v); if (k >= 1 && k <= 8) ctx->stream_chunks = (uint32_t)k; }
+    if (const char* v = getenv("VX_STREAM_CHUNKS")) { int k = atoi(v); if (k >= 1 && k <= 15) ctx->stream_chunks = (uint32_t)k; }
     if (const char* v = getenv("VX_H2D_FIRST_GROUPS")) { int k = atoi(v); if (k >= 1 && k <= 64) ctx->h2d_first_groups = (uint32_t)k; }
     if (const char* v = getenv("VX_H2D_CHUNKS")) { int k = atoi(v); if (k >= 1 && k <= 8) ctx->h2d_chunks = (uint32_t)k; }
     cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
@@ -238,14 +238,22 @@ static int32_t commit_run(vx_ctx* ctx, vx_batch* b, const u64* src, bool is_valu
     // streaming sponge: chunk boundaries fall on multiples of the sponge rate and every chunk is absorbed into the per-leaf
     // state right after its LDE, so only the LAST chunk's hashing is left when the last copy lands
     const bool stream = nchunks > 1 && ctx->stream_sponge && b->hasher == VX_HASHER_POSEIDON && c > 4;
-    // Hashing a column costs ~8x its copy, so the chunks grow geometrically (8, 16, 32, ... columns, the rest in the last
-    // one): only the copy of the first 8 columns is exposed and the transforms run in few, large launches.
+    // Chunks grow geometrically (8, 16, 32, ... columns) so that the copy of chunk k+1 is never longer than the work on
+    // the chunks before it; the doubling stops once the rest can hide too.  Work per column / copy per column is about
+    // 2^rate_bits (hashing is per LDE row, the copy per trace row): ~8 at rate_bits 3 -- 2^16 x 135 goes as 8 / 16 / 111
+    // columns -- and ~2 at rate_bits 1, where a 2502-column STARK trace needs nine chunks.
     const uint32_t groups = (c + 7) / 8;
-    uint32_t bound[9] = {0};
+    uint32_t bound[17] = {0};
     uint32_t nchunks_eff = nchunks;
     if (stream) {
+        const double ratio = (double)(1u << b->rate_bits) + 0.3;
         uint32_t k = 0, g = 0, size = ctx->h2d_first_groups;
-        while (k + 1 < ctx->stream_chunks && g + size < groups) { g += size; bound[++k] = 8 * g; size *= 2; }
+        while (k + 1 < ctx->stream_chunks && g + size < groups) {
+            g += size;
+            bound[++k] = 8 * g;
+            size *= 2;
+            if ((double)(groups - g) <= 0.6 * ratio * (double)g) break;      // the rest hides behind what is queued
+        }
         bound[++k] = c;
         nchunks_eff = k;
     }

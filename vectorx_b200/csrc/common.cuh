@@ -55,7 +55,7 @@ struct vx_ctx {
     int coop_max_pairs = 4096;          // Merkle levels with at most this many pairs use 16 lanes per two_to_one (VX_COOP_MAX_PAIRS)
     int tree_fuse = 1;                  // VX_TREE_FUSE=0: one launch per small Merkle level (A/B switch)
     uint32_t h2d_chunks = 8;            // VX_H2D_CHUNKS: column chunks of a commit from host memory (copy / transform overlap)
-    uint32_t stream_chunks = 3;         // VX_STREAM_CHUNKS: chunks of the streamed form (8, 16, rest columns measured best on B200)
+    uint32_t stream_chunks = 15;        // VX_STREAM_CHUNKS: upper bound on the chunks of the streamed form (sizes double until the rest hides)
     uint32_t h2d_first_groups = 1;      // VX_H2D_FIRST_GROUPS: size of the first streamed chunk in 8-column groups (then doubling)
     int stream_sponge = 1;              // VX_STREAM_SPONGE: hash each column chunk as it lands (0 = hash after the last chunk)
     int poseidon_variant = 0;           // VX_POSEIDON_VARIANT (A/B switch for profiling): 0 = default, 1 = shared-memory state, 2 = 128-register form
