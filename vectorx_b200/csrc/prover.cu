@@ -394,15 +394,18 @@ extern "C" int32_t vx_quotient(vx_ctx* ctx, const vx_circuit_desc* d, vx_batch* 
 }
 
 // ------------------------------------------------------------------------------------------------ Z / partial products
-// phase 1: per (challenge, row): chunk quotients q_c = prod num / prod den and their row product
+// phase 1: per (challenge, row): chunk quotients q_c = prod num / prod den and their row product.  The `chunks`
+// denominators of a row are inverted together (Montgomery's trick: one field inversion per row instead of one per
+// chunk); numerators, denominators and their running products pass through global scratch (coalesced, chunk-major).
 __global__ void zpp_rows_kernel(const u64* __restrict__ wires, const u64* __restrict__ sigmas, uint64_t n,
                                 uint32_t log_n, uint32_t num_routed, uint32_t max_degree, uint32_t chunks,
                                 const u64* __restrict__ beta_k, u64 beta, u64 gamma, TwiddleView tw,
-                                u64* __restrict__ q /* [chunks][n] */, u64* __restrict__ rowprod /* [n] */) {
+                                u64* __restrict__ q /* [chunks][n] */, u64* __restrict__ dtmp /* [chunks][n] */,
+                                u64* __restrict__ ptmp /* [chunks][n] */, u64* __restrict__ rowprod /* [n] */) {
     uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
     u64 s = tw_pow_view(tw, (u32)(r << (32 - log_n)));          // w_n^r
-    u64 rp = 1;
+    u64 run = 1;
     for (uint32_t c = 0; c < chunks; c++) {
         u64 num = 1, den = 1;
         uint32_t hi = min(num_routed, (c + 1) * max_degree);
@@ -413,28 +416,55 @@ __global__ void zpp_rows_kernel(const u64* __restrict__ wires, const u64* __rest
             num = gl_mul_cc(num, a);
             den = gl_mul_cc(den, b);
         }
-        u64 qc = gl_canon(gl_mul_cc(num, gl_inv(den)));
+        q[(uint64_t)c * n + r] = num;
+        dtmp[(uint64_t)c * n + r] = den;
+        ptmp[(uint64_t)c * n + r] = run;                          // product of the denominators before chunk c
+        run = gl_mul_cc(run, den);
+    }
+    u64 inv = gl_inv(run);                                        // 1 / (den_0 ... den_{chunks-1})
+    u64 rp = 1;
+    for (uint32_t c = chunks; c-- > 0;) {
+        const u64 inv_den = gl_mul_cc(inv, ptmp[(uint64_t)c * n + r]);
+        inv = gl_mul_cc(inv, dtmp[(uint64_t)c * n + r]);
+        const u64 qc = gl_canon(gl_mul_cc(q[(uint64_t)c * n + r], inv_den));
         q[(uint64_t)c * n + r] = qc;
         rp = gl_mul_cc(rp, qc);
     }
     rowprod[r] = gl_canon(rp);
 }
 
-// phase 2: exclusive prefix product over rows, one block; thread t owns a contiguous run of rows
+// phase 2: exclusive prefix product over rows, one block of 1024 threads; thread t owns a contiguous run of rows and the
+// 1024 run products are scanned with warp shuffles (5 + 5 dependent multiplications instead of a serial loop)
 __global__ void __launch_bounds__(1024) zpp_scan_kernel(const u64* __restrict__ rowprod, uint64_t n, u64* __restrict__ z) {
-    __shared__ u64 part[1024];
+    __shared__ u64 warp_tot[32];
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint64_t per = (n + blockDim.x - 1) / blockDim.x;
     uint64_t lo = min(n, (uint64_t)threadIdx.x * per), hi = min(n, lo + per);
     u64 acc = 1;
     for (uint64_t r = lo; r < hi; r++) acc = gl_mul_cc(acc, rowprod[r]);
-    part[threadIdx.x] = acc;
+    // inclusive scan inside the warp
+    u64 inc = acc;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        u64 up = __shfl_up_sync(0xffffffffu, inc, d);
+        if ((int)lane >= d) inc = gl_mul_cc(inc, up);
+    }
+    if (lane == 31) warp_tot[wid] = inc;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        u64 run = 1;
-        for (uint32_t t = 0; t < blockDim.x; t++) { u64 v = part[t]; part[t] = run; run = gl_mul_cc(run, v); }
+    if (wid == 0) {
+        u64 t = warp_tot[lane], ti = t;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            u64 up = __shfl_up_sync(0xffffffffu, ti, d);
+            if ((int)lane >= d) ti = gl_mul_cc(ti, up);
+        }
+        u64 ex = __shfl_up_sync(0xffffffffu, ti, 1);              // exclusive: product of the warps before this one
+        warp_tot[lane] = lane ? ex : 1;
     }
     __syncthreads();
-    acc = part[threadIdx.x];
+    u64 before = __shfl_up_sync(0xffffffffu, inc, 1);             // product of the lanes before this one in the warp
+    if (lane == 0) before = 1;
+    acc = gl_mul_cc(warp_tot[wid], before);
     for (uint64_t r = lo; r < hi; r++) { z[r] = gl_canon(acc); acc = gl_mul_cc(acc, rowprod[r]); }
 }
 
@@ -457,35 +487,48 @@ extern "C" int32_t vx_zs_partial_products(vx_ctx* ctx, const vx_circuit_desc* d,
     CtxGuard g(ctx);
     const uint64_t n = 1ULL << d->degree_bits;
     const uint32_t nch = d->num_challenges, R = d->num_routed_wires;
+    VX_REQUIRE(nch >= 1 && nch <= 4, "vx_zs_partial_products: num_challenges %u unsupported", nch);
     const uint32_t chunks = (R + d->max_degree - 1) / d->max_degree;
     VX_REQUIRE(chunks == d->num_partial_products + 1, "vx_zs_partial_products: num_partial_products inconsistent");
-    DevBuf dw, ds, dq, drp, dout, dbk;
-    VX_CHECK(dw.alloc((size_t)R * n * 8, ctx->stream));           // only routed wires take part
-    VX_CHECK(ds.alloc((size_t)R * n * 8, ctx->stream));
+    // inputs / output already in device memory (the prover keeps them there) are used in place
+    const bool w_dev = vx_is_device_ptr(wires), s_dev = vx_is_device_ptr(sigmas), o_dev = vx_is_device_ptr(out);
+    DevBuf dw, ds, dq, dd, dp, drp, dout, dbk;
+    if (!w_dev) {
+        VX_CHECK(dw.alloc((size_t)R * n * 8, ctx->stream));       // only routed wires take part
+        VX_CUDA(cudaMemcpyAsync(dw.p, wires, (size_t)R * n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (!s_dev) {
+        VX_CHECK(ds.alloc((size_t)R * n * 8, ctx->stream));
+        VX_CUDA(cudaMemcpyAsync(ds.p, sigmas, (size_t)R * n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    const u64* pw = w_dev ? (const u64*)wires : dw.p;
+    const u64* ps = s_dev ? (const u64*)sigmas : ds.p;
     VX_CHECK(dq.alloc((size_t)chunks * n * 8, ctx->stream));
+    VX_CHECK(dd.alloc((size_t)chunks * n * 8, ctx->stream));
+    VX_CHECK(dp.alloc((size_t)chunks * n * 8, ctx->stream));
     VX_CHECK(drp.alloc(n * 8, ctx->stream));
-    VX_CHECK(dout.alloc((size_t)nch * chunks * n * 8, ctx->stream));
-    VX_CHECK(dbk.alloc((size_t)R * 8, ctx->stream));
-    VX_CUDA(cudaMemcpyAsync(dw.p, wires, (size_t)R * n * 8, cudaMemcpyDefault, ctx->stream));
-    VX_CUDA(cudaMemcpyAsync(ds.p, sigmas, (size_t)R * n * 8, cudaMemcpyDefault, ctx->stream));
+    if (!o_dev) VX_CHECK(dout.alloc((size_t)nch * chunks * n * 8, ctx->stream));
+    u64* po = o_dev ? (u64*)out : dout.p;
+    VX_CHECK(dbk.alloc((size_t)nch * R * 8, ctx->stream));
     TwiddleView tw; tw.lo = ctx->w_lo; tw.hi = ctx->w_hi; tw.roots12 = ctx->roots12; tw.full12 = ctx->roots12f;
-    std::vector<u64> bk(R);
+    std::vector<u64> bk((size_t)nch * R);
+    for (uint32_t k = 0; k < nch; k++)
+        for (uint32_t w = 0; w < R; w++) bk[(size_t)k * R + w] = gl_mul_slow(betas[k] % GL_P, d->k_is[w] % GL_P);
+    VX_CUDA(cudaMemcpyAsync(dbk.p, bk.data(), bk.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
     for (uint32_t k = 0; k < nch; k++) {
-        for (uint32_t w = 0; w < R; w++) bk[w] = gl_mul_slow(betas[k] % GL_P, d->k_is[w] % GL_P);
-        VX_CUDA(cudaMemcpyAsync(dbk.p, bk.data(), R * 8, cudaMemcpyHostToDevice, ctx->stream));
-        VX_CUDA(cudaStreamSynchronize(ctx->stream));               // bk is reused next iteration
         unsigned blocks = (unsigned)((n + 127) / 128);
-        u64* z = dout.p + (size_t)k * n;
-        u64* pp = dout.p + (size_t)nch * n + (size_t)k * (chunks - 1) * n;
-        zpp_rows_kernel<<<blocks, 128, 0, ctx->stream>>>(dw.p, ds.p, n, d->degree_bits, R, d->max_degree, chunks,
-                                                         dbk.p, betas[k] % GL_P, gammas[k] % GL_P, tw, dq.p, drp.p);
+        u64* z = po + (size_t)k * n;
+        u64* pp = po + (size_t)nch * n + (size_t)k * (chunks - 1) * n;
+        zpp_rows_kernel<<<blocks, 128, 0, ctx->stream>>>(pw, ps, n, d->degree_bits, R, d->max_degree, chunks,
+                                                         dbk.p + (size_t)k * R, betas[k] % GL_P, gammas[k] % GL_P, tw,
+                                                         dq.p, dd.p, dp.p, drp.p);
         zpp_scan_kernel<<<1, 1024, 0, ctx->stream>>>(drp.p, n, z);
         zpp_fill_kernel<<<blocks, 128, 0, ctx->stream>>>(dq.p, z, n, chunks, pp);
         VX_LAUNCH_COUNT(ctx, 3);
     }
     VX_CUDA(cudaGetLastError());
-    VX_CUDA(cudaMemcpyAsync(out, dout.p, (size_t)nch * chunks * n * 8, cudaMemcpyDefault, ctx->stream));
-    VX_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (!o_dev) VX_CUDA(cudaMemcpyAsync(out, dout.p, (size_t)nch * chunks * n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    VX_CUDA(cudaStreamSynchronize(ctx->stream));                 // also keeps `bk` alive until its copy has been issued
     return VX_OK;
 }
 
