@@ -389,6 +389,40 @@ GL_D u64 gl_acc_reduce(const GlAcc& t) {
     return pack64(r0, r1);
 }
 
+// The same accumulator with each 64-bit column held as ONE 64-bit register (an aligned pair): for accumulators that live
+// across a long loop (the quotient interpreter's alpha sums) the register allocator otherwise parks the halves in
+// unpaired registers and moves them in and out of IMAD.WIDE pairs around every use.
+struct GlAcc2 {
+    u64 t0, t1, t2;
+    u32 c0, c1, c2;
+};
+GL_D void gl_acc2_init(GlAcc2& t, u64 init) { t.t0 = init; t.t1 = t.t2 = 0; t.c0 = t.c1 = t.c2 = 0; }
+GL_D void gl_acc2_mad(GlAcc2& t, u64 a, u64 b) {
+    u32 a0 = lo32(a), a1 = hi32(a), b0 = lo32(b), b1 = hi32(b);
+    asm("{\n\t"
+        ".reg .u32 l, h;\n\t"
+        "mov.b64 {l, h}, %0;\n\t"
+        "mad.lo.cc.u32 l, %6, %8, l;\n\t"  "madc.hi.cc.u32 h, %6, %8, h;\n\t"  "addc.u32 %3, %3, 0;\n\t"
+        "mov.b64 %0, {l, h};\n\t"
+        "mov.b64 {l, h}, %1;\n\t"
+        "mad.lo.cc.u32 l, %6, %9, l;\n\t"  "madc.hi.cc.u32 h, %6, %9, h;\n\t"  "addc.u32 %4, %4, 0;\n\t"
+        "mad.lo.cc.u32 l, %7, %8, l;\n\t"  "madc.hi.cc.u32 h, %7, %8, h;\n\t"  "addc.u32 %4, %4, 0;\n\t"
+        "mov.b64 %1, {l, h};\n\t"
+        "mov.b64 {l, h}, %2;\n\t"
+        "mad.lo.cc.u32 l, %7, %9, l;\n\t"  "madc.hi.cc.u32 h, %7, %9, h;\n\t"  "addc.u32 %5, %5, 0;\n\t"
+        "mov.b64 %2, {l, h};\n\t"
+        "}"
+        : "+l"(t.t0), "+l"(t.t1), "+l"(t.t2), "+r"(t.c0), "+r"(t.c1), "+r"(t.c2)
+        : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+}
+GL_D u64 gl_acc2_reduce(const GlAcc2& t) {
+    GlAcc g;
+    g.l0 = lo32(t.t0); g.h0 = hi32(t.t0); g.c0 = t.c0;
+    g.l1 = lo32(t.t1); g.h1 = hi32(t.t1); g.c1 = t.c1;
+    g.l2 = lo32(t.t2); g.h2 = hi32(t.t2); g.c2 = t.c2;
+    return gl_acc_reduce(g);
+}
+
 // full 64x64 -> 128 product on IMAD.WIDE.U32: 4 multiplies, no carry chains
 // (each partial sum provably fits 64 bits).
 GL_D void gl_mul128(u64 a, u64 b, u64& lo, u64& hi) {

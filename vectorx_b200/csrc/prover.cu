@@ -94,16 +94,16 @@ __global__ void __launch_bounds__(QBLOCK) quotient_kernel(const QuotParams p) {
     const u64 l0 = gl_mul_cc(gl_mul_cc(zh, p.n_inv), gl_inv(gl_sub(x, 1)));
     const uint64_t jn = bitrev_u64((i + (1u << p.rate_bits)) & (N - 1), p.bits);   // leaf of g_n * x
 
-    GlAcc tot[2];
-    for (uint32_t k = 0; k < p.num_challenges; k++) gl_acc_init(tot[k], 0);
+    GlAcc2 tot[2];
+    for (uint32_t k = 0; k < p.num_challenges; k++) gl_acc2_init(tot[k], 0);
     const uint32_t nch = p.num_challenges;
     const u64* apow0 = p.apow;
     const u64* apow1 = p.apow + p.num_terms;
 #define ADD_TERM(idx, val)                                        \
     do {                                                          \
         u64 _v = (val);                                           \
-        gl_acc_mad(tot[0], _v, __ldg(apow0 + (idx)));             \
-        if (nch > 1) gl_acc_mad(tot[1], _v, __ldg(apow1 + (idx))); \
+        gl_acc2_mad(tot[0], _v, __ldg(apow0 + (idx)));            \
+        if (nch > 1) gl_acc2_mad(tot[1], _v, __ldg(apow1 + (idx))); \
     } while (0)
 
     // ---- Z(1) = 1 and the permutation argument.  The chunk loop is outermost so that every routed wire and sigma value is
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(QBLOCK) quotient_kernel(const QuotParams p) {
     // Register file and program are addressed with 32-bit shared-window addresses (ld/st.shared): an operand access is
     // one shift-add + one LDS, and the per-point column pointers are pinned so that nothing is recomputed per
     // instruction (the first form of this loop spent 41 of its ~87 instructions per bytecode operation on decode).
-    GlAcc h[2];
+    GlAcc2 h[2];
     uint32_t cidx = 0;
     bool done = false;
     uint32_t prog_sa = (uint32_t)__cvta_generic_to_shared(prog_s);
@@ -176,8 +176,8 @@ __global__ void __launch_bounds__(QBLOCK) quotient_kernel(const QuotParams p) {
             if (hi & QF_LOADW) { cp_async_u64(reg_sa + (dst << 10), wires_j + (uint64_t)imm * Nq); continue; }
             if (hi & QF_EMIT) {
                 const u64 v = RLD(ra);
-                gl_acc_mad(h[0], v, __ldg(apow0 + cidx));
-                if (nch > 1) gl_acc_mad(h[1], v, __ldg(apow1 + cidx));
+                gl_acc2_mad(h[0], v, __ldg(apow0 + cidx));
+                if (nch > 1) gl_acc2_mad(h[1], v, __ldg(apow1 + cidx));
                 cidx++;
                 continue;
             }
@@ -234,13 +234,13 @@ __global__ void __launch_bounds__(QBLOCK) quotient_kernel(const QuotParams p) {
                     break;
                 }
                 case VX_OP_BEGINGATE:
-                    gl_acc_init(h[0], 0); gl_acc_init(h[1], 0);
+                    gl_acc2_init(h[0], 0); gl_acc2_init(h[1], 0);
                     cidx = p.num_perm_terms;
                     break;
                 case VX_OP_ENDGATE: {
                     const u64 f = (ra == 255) ? 1 : RLD(ra);
-                    gl_acc_mad(tot[0], f, gl_acc_reduce(h[0]));
-                    if (nch > 1) gl_acc_mad(tot[1], f, gl_acc_reduce(h[1]));
+                    gl_acc2_mad(tot[0], f, gl_acc2_reduce(h[0]));
+                    if (nch > 1) gl_acc2_mad(tot[1], f, gl_acc2_reduce(h[1]));
                     break;
                 }
                 default: break;                     // VX_OP_NOP
@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(QBLOCK) quotient_kernel(const QuotParams p) {
 #undef RST
     const u64 zi = p.zh_inv[coset];
     if (live)
-        for (uint32_t k = 0; k < nch; k++) p.out[(uint64_t)k * N + j] = gl_canon(gl_mul_cc(gl_acc_reduce(tot[k]), zi));
+        for (uint32_t k = 0; k < nch; k++) p.out[(uint64_t)k * N + j] = gl_canon(gl_mul_cc(gl_acc2_reduce(tot[k]), zi));
 #undef REG
 #undef ADD_TERM
 }
