@@ -41,10 +41,15 @@ __global__ void fri_reduce_kernel(const u64* const* __restrict__ cols, uint32_t 
 }
 
 // q = (comp - comp(z)) / (X - z), i.e. q_m = c_{m+1} + z q_{m+1} (c_n = q_n = 0);  final = final * shift + q.
-// One block: thread t owns a contiguous run of m; runs are stitched by a short sequential carry pass.
+// One block: thread t owns a contiguous run of m.  The carry into a run is an affine function of the carry into the next
+// one (carry_t = l_t + z^len_t carry_{t+1}); the 1024 runs are stitched in two levels -- lane 0 of every warp walks its 32
+// runs (recording, per run, the carry for a zero warp carry-in and the multiplier of the true one), thread 0 walks the 32
+// warps -- 64 dependent steps instead of 1024.
 __global__ void __launch_bounds__(1024) fri_divide_accumulate_kernel(const u64* __restrict__ comp, uint64_t n, gl2 z,
                                                                     gl2 shift, u64* __restrict__ fin) {
-    __shared__ u64 ca[1024], cb[1024];
+    __shared__ u64 ca[1024], cb[1024];          // run results l_t, then the zero-carry-in carries
+    __shared__ u64 pa[1024], pb[1024];          // multiplier of the warp's true carry-in for run t
+    __shared__ u64 wa[32], wb[32], ma[32], mb[32], xa[32], xb[32];
     const uint64_t per = (n + blockDim.x - 1) / blockDim.x;
     const uint64_t lo = min(n, (uint64_t)threadIdx.x * per), hi = min(n, lo + per);
     auto coef = [&](uint64_t m) { return (m < n) ? gl2_make(comp[m], comp[n + m]) : gl2_make(0, 0); };
@@ -52,21 +57,34 @@ __global__ void __launch_bounds__(1024) fri_divide_accumulate_kernel(const u64* 
     for (uint64_t m = hi; m > lo; m--) q = gl2_add(gl2_mul(q, z), coef(m));      // q_{m-1} with zero carry-in
     ca[threadIdx.x] = q.a; cb[threadIdx.x] = q.b;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        gl2 carry = gl2_make(0, 0);
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) {
         const gl2 zp = gl2_pow(z, per);
-        for (int t = (int)blockDim.x - 1; t >= 0; t--) {
-            uint64_t tlo = min(n, (uint64_t)t * per), thi = min(n, tlo + per);
-            gl2 l = gl2_make(ca[t], cb[t]);
-            ca[t] = carry.a; cb[t] = carry.b;                                     // carry-in of thread t = true q_{hi_t}
+        gl2 carry = gl2_make(0, 0), mult = gl2_make(1, 0);
+        for (int t = (int)(32 * wid + 31); t >= (int)(32 * wid); t--) {
+            const uint64_t tlo = min(n, (uint64_t)t * per), thi = min(n, tlo + per);
+            const gl2 l = gl2_make(ca[t], cb[t]);
+            ca[t] = carry.a; cb[t] = carry.b;                                     // carry into run t for a zero warp carry-in
+            pa[t] = mult.a; pb[t] = mult.b;                                       // ... plus mult * (true warp carry-in)
             if (thi > tlo) {
-                gl2 zl = (thi - tlo == per) ? zp : gl2_pow(z, thi - tlo);
+                const gl2 zl = (thi - tlo == per) ? zp : gl2_pow(z, thi - tlo);
                 carry = gl2_add(l, gl2_mul(zl, carry));
+                mult = gl2_mul(zl, mult);
             }
+        }
+        wa[wid] = carry.a; wb[wid] = carry.b; ma[wid] = mult.a; mb[wid] = mult.b; // the warp as one affine step
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        gl2 x = gl2_make(0, 0);
+        for (int w = 31; w >= 0; w--) {
+            xa[w] = x.a; xb[w] = x.b;                                             // true carry into warp w
+            x = gl2_add(gl2_make(wa[w], wb[w]), gl2_mul(gl2_make(ma[w], mb[w]), x));
         }
     }
     __syncthreads();
-    q = gl2_make(ca[threadIdx.x], cb[threadIdx.x]);
+    q = gl2_add(gl2_make(ca[threadIdx.x], cb[threadIdx.x]),
+                gl2_mul(gl2_make(pa[threadIdx.x], pb[threadIdx.x]), gl2_make(xa[wid], xb[wid])));
     for (uint64_t m = hi; m > lo; m--) {
         q = gl2_add(gl2_mul(q, z), coef(m));                                      // q_{m-1}
         gl2 f = gl2_make(fin[m - 1], fin[n + m - 1]);
