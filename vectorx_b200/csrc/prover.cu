@@ -533,21 +533,27 @@ extern "C" int32_t vx_zs_partial_products(vx_ctx* ctx, const vx_circuit_desc* d,
 }
 
 // ------------------------------------------------------------------------------------------------ openings
-// One block per polynomial: thread t evaluates its contiguous run of coefficients by Horner, scales it by
-// point^(t*run) and the block sums the pieces.  out[col] = sum_m coeffs[col][m] * point^m  (extension value).
-__global__ void __launch_bounds__(256) eval_ext_kernel(const u64* __restrict__ coeffs, uint32_t log_n, gl2 point,
+// One block per polynomial: thread t evaluates the coefficients m = t (mod block) by Horner in point^block, scales by
+// point^t and the block sums the pieces.  out[col] = sum_m coeffs[col][m] * point^m  (extension value).
+#define EVAL_BLOCK 1024
+__global__ void __launch_bounds__(EVAL_BLOCK) eval_ext_kernel(const u64* __restrict__ coeffs, uint32_t log_n, gl2 point,
                                                        u64* __restrict__ out) {
-    __shared__ u64 sa[256], sb[256];
+    __shared__ u64 sa[EVAL_BLOCK], sb[EVAL_BLOCK];
     const uint64_t n = 1ULL << log_n;
     const u64* col = coeffs + ((uint64_t)blockIdx.x << log_n);
-    uint64_t per = (n + 255) / 256;
-    uint64_t lo = min(n, (uint64_t)threadIdx.x * per), hi = min(n, lo + per);
+    // thread t takes the coefficients m = t (mod EVAL_BLOCK): Horner in point^EVAL_BLOCK over coalesced loads, then x point^t
+    const gl2 step = gl2_pow(point, EVAL_BLOCK);
     gl2 acc = gl2_make(0, 0);
-    for (uint64_t m = hi; m > lo; m--) acc = gl2_add_base(gl2_mul(acc, point), col[m - 1]);
-    acc = gl2_mul(acc, gl2_pow(point, lo));
+    const uint64_t runs = (n + EVAL_BLOCK - 1) / EVAL_BLOCK;
+    for (uint64_t k = runs; k > 0; k--) {
+        const uint64_t m = (k - 1) * EVAL_BLOCK + threadIdx.x;
+        acc = gl2_mul(acc, step);
+        if (m < n) acc = gl2_add_base(acc, col[m]);
+    }
+    acc = gl2_mul(acc, gl2_pow(point, threadIdx.x));
     sa[threadIdx.x] = gl_canon(acc.a); sb[threadIdx.x] = gl_canon(acc.b);
     __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {
+    for (int s = EVAL_BLOCK / 2; s > 0; s >>= 1) {
         if ((int)threadIdx.x < s) {
             sa[threadIdx.x] = gl_canon(gl_add(sa[threadIdx.x], sa[threadIdx.x + s]));
             sb[threadIdx.x] = gl_canon(gl_add(sb[threadIdx.x], sb[threadIdx.x + s]));
@@ -563,7 +569,7 @@ extern "C" int32_t vx_batch_eval_ext(vx_batch* b, const uint64_t point[2], uint6
     CtxGuard g(ctx);
     DevBuf d;
     VX_CHECK(d.alloc((size_t)b->c * 2 * 8, ctx->stream));
-    eval_ext_kernel<<<b->c, 256, 0, ctx->stream>>>(b->coeffs.p, b->log_n, gl2_make(point[0] % GL_P, point[1] % GL_P), d.p);
+    eval_ext_kernel<<<b->c, EVAL_BLOCK, 0, ctx->stream>>>(b->coeffs.p, b->log_n, gl2_make(point[0] % GL_P, point[1] % GL_P), d.p);
     VX_LAUNCH_COUNT(ctx, 1);
     VX_CUDA(cudaGetLastError());
     VX_CUDA(cudaMemcpyAsync(out, d.p, d.bytes, cudaMemcpyDefault, ctx->stream));
