@@ -128,6 +128,13 @@ def cpu_commit_seconds(w, log_n_sample, repeats=1):
     c = w["cols"]
     cols = gen_values(c, 1 << log_n_sample, seed=99)
     L = oracle.lib(native=True)
+    # all the host threads this process may use: torchrun exports OMP_NUM_THREADS=1 to every rank, which would time the
+    # CPU arm single-threaded -- ask the scheduler instead of the environment
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    L.vxo_set_num_threads(int(avail))
     threads = L.vxo_num_threads()
     best = None
     for _ in range(repeats):
