@@ -146,11 +146,17 @@ def cpu_commit_seconds(w, log_n_sample, repeats=1):
 
 
 def run_reference(a, w, rank):
-    """--impl reference: the reference's CPU path (port) on host cores; rank 0 only."""
+    """--impl reference: the reference's CPU path (port) on host cores; rank 0 only.  Every step is one FULL commit of
+    the configured shape (same config as the GPU arm); only shapes whose CPU commit would not fit the time budget
+    (> 2^17 rows x 135 cols worth of elements) fall back to a row sample, and then the workload name says so."""
     if rank != 0:
         return
-    sample_log_n = min(w["log_n"], 14)
-    for _ in range(max(a.warmup, 1) if a.warmup < 2 else 2):     # CPU needs no long warm-up; bound the run
+    budget_elems = 135 << 17
+    sample_log_n = w["log_n"]
+    while sample_log_n > 10 and (w["cols"] << sample_log_n) > budget_elems:
+        sample_log_n -= 1
+    full = sample_log_n == w["log_n"]
+    for _ in range(min(max(a.warmup, 1), 2)):                    # CPU needs no long warm-up; bound the run
         cpu_commit_seconds(w, sample_log_n)
     times = []
     elems = 0
@@ -160,11 +166,14 @@ def run_reference(a, w, rank):
         times.append(dt)
     ms = 1e3 * sum(times) / len(times)
     val = elems / (ms * 1e-3) / 1e6
-    sample = f"2^{sample_log_n} rows x {w['cols']} cols (1/{1 << (w['log_n'] - sample_log_n)} of the rows), same rate_bits/cap"
+    ws = dict(w, log_n=sample_log_n)
+    sample = ("one full commit of the configured shape per step" if full else
+              f"2^{sample_log_n} rows x {w['cols']} cols (1/{1 << (w['log_n'] - sample_log_n)} of the rows), same rate_bits/cap")
     line = {"metric": METRIC, "value": val, "unit": UNIT, "impl": "reference", "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "u64 (Goldilocks)", "data": "synthetic",
-            "config": {"workload": workload_name(w), "note": "CPU restatement of plonky2 v0.2.0 (oracle/), OpenMP; "
+            "dtype": "u64 (Goldilocks)", "data": "synthetic", "same_config": full,
+            "config": {"workload": workload_name(w) if full else workload_name(ws) + f" (row sample of 2^{w['log_n']})",
+                       "note": "CPU restatement of plonky2 v0.2.0 (oracle/), OpenMP; "
                        "the Rust reference is unbuildable here (no cargo, plonky2 not vendored)"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

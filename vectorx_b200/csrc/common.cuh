@@ -76,6 +76,12 @@ struct vx_ctx {
     u64 *g_lo = nullptr, *g_hi = nullptr, *gi_lo = nullptr, *gi_hi = nullptr;
     u64 *roots12 = nullptr, *iroots12 = nullptr;
     u64 *roots12f = nullptr, *iroots12f = nullptr;      // w_4096^e, e < 4096 (radix-16 group twiddles)
+    u64 *inner_fwd = nullptr, *inner_inv = nullptr;     // [16][16] w_256^(+-r bitrev_4(q)): between the two groups of a 256-row pass
+    // per-shape derived tables (four-step twiddles of a pass, coset factors of an LDE), built on first use (ntt.cu)
+    struct NttTable { uint64_t key; u64* p; size_t bytes; };
+    std::vector<NttTable> ntt_cache;
+    size_t ntt_cache_bytes = 0;
+    std::mutex ntt_cache_mu;
     // phase events of the most recent commit on this context (see vx_ctx_phase_ms)
     cudaEvent_t ev[VX_NUM_PHASE_EVENTS] = {};
 };

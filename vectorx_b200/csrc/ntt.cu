@@ -16,6 +16,7 @@
 //    coefficients: point i = 2^r k + rho is the n-point transform of (g w_N^rho)^m c_m at k, and its
 //    leaf-order block is bitrev_r(rho).
 #include "common.cuh"
+#include "ntt_l3.cuh"
 
 // ------------------------------------------------------------------------------------------------ tables
 static int32_t upload(vx_ctx* ctx, const std::vector<u64>& h, u64** d) {
@@ -33,6 +34,9 @@ static void two_level(u64 base, unsigned lo_bits, unsigned hi_count, std::vector
     u64 step = acc, a2 = 1;       // base^(2^lo_bits)
     for (size_t i = 0; i < hi.size(); i++) { hi[i] = a2; a2 = gl_mul_slow(a2, step); }
 }
+
+static TwiddleView tw_view(vx_ctx* ctx, bool inverse);
+__global__ void inner_table_kernel(u64* __restrict__ tab, TwiddleView tw);
 
 int32_t ntt_module_init(vx_ctx* ctx) {
     std::vector<u64> lo, hi;
@@ -60,13 +64,23 @@ int32_t ntt_module_init(vx_ctx* ctx) {
     acc = 1;
     for (int i = 0; i < 4096; i++) { r[i] = acc; acc = gl_mul_slow(acc, w12i); }
     VX_CHECK(upload(ctx, r, &ctx->iroots12f));
+    VX_CUDA(cudaMalloc(&ctx->inner_fwd, 256 * sizeof(u64)));
+    VX_CUDA(cudaMalloc(&ctx->inner_inv, 256 * sizeof(u64)));
+    inner_table_kernel<<<1, 256, 0, ctx->stream>>>(ctx->inner_fwd, tw_view(ctx, false));
+    inner_table_kernel<<<1, 256, 0, ctx->stream>>>(ctx->inner_inv, tw_view(ctx, true));
+    VX_CUDA(cudaGetLastError());
+    VX_CUDA(cudaStreamSynchronize(ctx->stream));
     return VX_OK;
 }
 
 void ntt_module_destroy(vx_ctx* ctx) {
     u64* ptrs[] = {ctx->w_lo, ctx->w_hi, ctx->wi_lo, ctx->wi_hi, ctx->g_lo, ctx->g_hi,
-                   ctx->gi_lo, ctx->gi_hi, ctx->roots12, ctx->iroots12, ctx->roots12f, ctx->iroots12f};
+                   ctx->gi_lo, ctx->gi_hi, ctx->roots12, ctx->iroots12, ctx->roots12f, ctx->iroots12f,
+                   ctx->inner_fwd, ctx->inner_inv};
     for (u64* p : ptrs) if (p) cudaFree(p);
+    for (auto& e : ctx->ntt_cache) cudaFree(e.p);
+    ctx->ntt_cache.clear();
+    ctx->ntt_cache_bytes = 0;
 }
 
 static TwiddleView tw_view(vx_ctx* ctx, bool inverse) {
@@ -85,55 +99,97 @@ GL_D u64 tw_pow(const TwiddleView& tw, u32 E) {
     return l ? gl_mul(h, __ldg(tw.lo + l)) : h;
 }
 
+// ------------------------------------------------------------------------------------------------ derived tables
+// Three kinds of device tables are derived once per shape and cached in the context (all canonical):
+//   outer(log_M, inv)  [P < 256][i0 < M/256]  w_M^(+-i0 bitrev_8(P))      the four-step twiddles of a 256-row pass
+//   scale(log_n, rate_bits, blk_first, blk_count)  [b][m < n]  (g w_N^rho_b)^m   the coset factors of the LDE
+//   inner(inv)  [q < 16][r < 16]  w_256^(+-r bitrev_4(q))                 between the two radix-16 groups of a pass
+// so that a twiddle costs one coalesced load and one multiplication (the two-level W tables cost two loads and two
+// multiplications per twiddle).  Shapes whose table would be too big fall back to the two-level tables.
+#define NTT_OUTER_MAX_LOG 20          // outer table: 8 * 2^log_M bytes (8 MB at 2^20)
+#define NTT_SCALE_MAX_LOG 23          // scale table: 8 * blk_count * n bytes (64 MB at 2^23 entries)
+
+__global__ void outer_table_kernel(u64* __restrict__ tab, uint32_t log_M, TwiddleView tw) {
+    const uint32_t low = log_M - 8;
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (1ULL << log_M)) return;
+    const uint32_t P = (uint32_t)(i >> low), i0 = (uint32_t)(i & ((1u << low) - 1));
+    const uint32_t k1 = __brev(P) >> 24;
+    tab[i] = gl_canon(tw_pow_view(tw, (i0 * k1) << (32 - log_M)));
+}
+__global__ void inner_table_kernel(u64* __restrict__ tab, TwiddleView tw) {
+    const uint32_t q = threadIdx.x >> 4, r = threadIdx.x & 15;
+    tab[threadIdx.x] = gl_canon(tw_pow_view(tw, (r * (__brev(q) >> 28)) << 24));      // w_256^e = W^(e << 24)
+}
+// tab[b][m] = g^m w_N^(rho_b m), rho_b = bitrev_r(blk_first + b)
+__global__ void scale_table_kernel(u64* __restrict__ tab, uint32_t log_n, uint32_t rate_bits, uint32_t blk_first,
+                                   const u64* __restrict__ g_lo, const u64* __restrict__ g_hi, TwiddleView tw) {
+    const uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >> log_n) return;
+    const uint32_t b = blockIdx.y;
+    const uint32_t rho = rate_bits ? (__brev(blk_first + b) >> (32 - rate_bits)) : 0;
+    u64 f = gl_mul_cc(__ldg(g_hi + (m >> 12)), __ldg(g_lo + (m & 4095)));
+    const u32 E = ((u32)m * rho) << (32 - (log_n + rate_bits));
+    if (E) f = gl_mul_cc(f, tw_pow_view(tw, E));
+    tab[((uint64_t)b << log_n) + m] = gl_canon(f);
+}
+
+// Callers hold ctx->ntt_cache_mu.  A table is built on the context's main stream and the build is waited for, so any stream
+// of the context may read it afterwards.
+static const u64* cache_find(vx_ctx* ctx, uint64_t key) {
+    for (auto& e : ctx->ntt_cache) if (e.key == key) return e.p;
+    return nullptr;
+}
+static int32_t cache_add(vx_ctx* ctx, uint64_t key, size_t bytes, u64** out) {
+    // derived tables are bounded by the number of distinct shapes a process commits; drop everything past 1 GB
+    if (ctx->ntt_cache_bytes + bytes > (1ULL << 30)) {
+        VX_CUDA(cudaDeviceSynchronize());
+        for (auto& e : ctx->ntt_cache) cudaFree(e.p);
+        ctx->ntt_cache.clear();
+        ctx->ntt_cache_bytes = 0;
+    }
+    VX_CUDA(cudaMalloc(out, bytes));
+    ctx->ntt_cache.push_back({key, *out, bytes});
+    ctx->ntt_cache_bytes += bytes;
+    return VX_OK;
+}
+static int32_t outer_table(vx_ctx* ctx, uint32_t log_M, bool inverse, const u64** out) {
+    *out = nullptr;
+    if (log_M > NTT_OUTER_MAX_LOG) return VX_OK;
+    const uint64_t key = (1ULL << 60) | ((uint64_t)inverse << 8) | log_M;
+    std::lock_guard<std::mutex> lk(ctx->ntt_cache_mu);
+    if ((*out = cache_find(ctx, key))) return VX_OK;
+    u64* p;
+    VX_CHECK(cache_add(ctx, key, sizeof(u64) << log_M, &p));
+    outer_table_kernel<<<(unsigned)(((1ULL << log_M) + 255) / 256), 256, 0, ctx->stream>>>(p, log_M, tw_view(ctx, inverse));
+    VX_CUDA(cudaGetLastError());
+    VX_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out = p;
+    return VX_OK;
+}
+static int32_t scale_table(vx_ctx* ctx, uint32_t log_n, uint32_t rate_bits, uint32_t blk_first, uint32_t blk_count,
+                           const u64** out) {
+    *out = nullptr;
+    if (((uint64_t)blk_count << log_n) > (1ULL << NTT_SCALE_MAX_LOG)) return VX_OK;
+    const uint64_t key = (2ULL << 60) | ((uint64_t)blk_count << 32) | ((uint64_t)blk_first << 16) | (rate_bits << 8) | log_n;
+    std::lock_guard<std::mutex> lk(ctx->ntt_cache_mu);
+    if ((*out = cache_find(ctx, key))) return VX_OK;
+    u64* p;
+    VX_CHECK(cache_add(ctx, key, ((size_t)blk_count << log_n) * sizeof(u64), &p));
+    dim3 grid((unsigned)(((1ULL << log_n) + 255) / 256), blk_count);
+    scale_table_kernel<<<grid, 256, 0, ctx->stream>>>(p, log_n, rate_bits, blk_first, ctx->g_lo, ctx->g_hi, tw_view(ctx, false));
+    VX_CUDA(cudaGetLastError());
+    VX_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out = p;
+    return VX_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ passes
 #define NTT_TW 16          // tile width along the contiguous dimension (16 x 8 B = one 128 B line)
 #define NTT_PITCH 17       // padded shared-memory row pitch (in u64)
 
-// Strided pass: A DIF stages over the high A bits of each 2^log_M block, then the four-step
-// twiddle w_M^(i0 * k1).  grid.x = tiles, grid.y = transforms.  smem: 2^A x NTT_PITCH u64.
-__global__ void __launch_bounds__(256) ntt_strided_pass(u64* __restrict__ data, uint32_t log_n, uint32_t log_M,
-                                                        uint32_t A, TwiddleView tw) {
-    extern __shared__ u64 sm[];
-    const uint32_t low = log_M - A;
-    const uint32_t tiles_per_blk = 1u << (low - 4);
-    const uint64_t blk = blockIdx.x / tiles_per_blk;
-    const uint32_t i0_base = (blockIdx.x % tiles_per_blk) * NTT_TW;
-    u64* base = data + (((uint64_t)blockIdx.z * gridDim.y + blockIdx.y) << log_n) + (blk << log_M) + i0_base;
-    const uint32_t R = 1u << A;
-    const uint32_t elems = R * NTT_TW;
-
-    for (uint32_t e = threadIdx.x; e < elems; e += blockDim.x) {
-        uint32_t j1 = e >> 4, t = e & 15;
-        sm[j1 * NTT_PITCH + t] = base[((uint64_t)j1 << low) + t];
-    }
-    __syncthreads();
-    for (uint32_t s = 0; s < A; s++) {
-        const uint32_t half_bits = A - 1 - s;
-        const uint32_t half = 1u << half_bits;
-        for (uint32_t b = threadIdx.x; b < elems / 2; b += blockDim.x) {
-            uint32_t t = b & 15, bb = b >> 4;
-            uint32_t j = bb & (half - 1);
-            uint32_t i = ((bb >> half_bits) << (half_bits + 1)) + j;
-            u64 u = sm[i * NTT_PITCH + t], v = sm[(i + half) * NTT_PITCH + t];
-            u64 w = __ldg(tw.roots12 + (j << (11 - half_bits)));      // w_{2 half}^j
-            sm[i * NTT_PITCH + t] = gl_add(u, v);
-            u64 d = gl_sub(u, v);
-            sm[(i + half) * NTT_PITCH + t] = j ? gl_mul(d, w) : d;
-        }
-        __syncthreads();
-    }
-    for (uint32_t e = threadIdx.x; e < elems; e += blockDim.x) {
-        uint32_t j1 = e >> 4, t = e & 15;
-        uint32_t k1 = __brev(j1) >> (32 - A);
-        uint32_t i0 = i0_base + t;
-        u64 x = sm[j1 * NTT_PITCH + t];
-        uint32_t E = (i0 * k1) << (32 - log_M);
-        if (E) x = gl_mul(x, tw_pow(tw, E));
-        base[((uint64_t)j1 << low) + t] = gl_canon(x);
-    }
-}
-
-// Final pass: F DIF stages on contiguous 2^F blocks; a CTA owns `chunk` (>= 2^F) contiguous elements.
+// Final pass for shapes the 4096-element kernel does not cover (fewer than 4096 elements in total): F radix-2 DIF stages on
+// contiguous 2^F blocks; a CTA owns `chunk` (>= 2^F) contiguous elements.
 __global__ void __launch_bounds__(256) ntt_final_pass(u64* __restrict__ data, uint32_t F, uint32_t chunk_bits,
                                                       TwiddleView tw) {
     extern __shared__ u64 sm[];
@@ -158,160 +214,128 @@ __global__ void __launch_bounds__(256) ntt_final_pass(u64* __restrict__ data, ui
     for (uint32_t e = threadIdx.x; e < chunk; e += blockDim.x) base[e] = gl_canon(sm[e]);
 }
 
-// ------------------------------------------------------------------------------------------------ radix-16 register passes
-// In Goldilocks w_64 = 8, so every root of unity of order <= 64 is a power of two: a 2^R-point DFT (R <= 4) needs no
-// real multiplication, only products by the compile-time constants 2^(96 j / half) below (ptxas folds the zero halves).
-// A "group" is R DIF stages at once on 2^R elements held in registers:
-//   y_j = sum_k x_k w_{2^R}^{jk}   (multiplication-free),   then   y_j *= w_M^{b j}   (M = 2^R S, b = index below S),
-// with y_j left at position bitrev_R(j) -- exactly what R radix-2 DIF stages over blocks of size M would produce.
-// The inverse transform is the same network on x_{(-k) mod 2^R} with the inverse twiddle tables.
-template <int S_BITS>
-GL_D u64 gl_mul_2exp(u64 x) {      // x * 2^S_BITS mod p, S_BITS < 96
-    constexpr u64 C = S_BITS < 64 ? (1ULL << (S_BITS & 63))
-                                  : (((1ULL << ((S_BITS - 64) & 31)) << 32) - (1ULL << ((S_BITS - 64) & 31)));   // 2^k * (2^32 - 1)
-    return gl_mul_cc(x, C);
-}
-
-template <int R, int STAGE, int J>
-GL_D u64 dft_twiddle(u64 d) {      // d * w_{2 half}^J with half = 2^(R - 1 - STAGE): w_{2 half} = 2^(96 / half)
-    constexpr int half = 1 << (R - 1 - STAGE);
-    constexpr int sh = (96 / half) * J;
-    if constexpr (J == 0) return d;
-    else return gl_mul_2exp<sh>(d);
-}
-
-template <int R, int STAGE, int B, int J>
-GL_D void dft_stage_pair(u64* x) {
-    constexpr int half = 1 << (R - 1 - STAGE);
-    u64 u = x[B + J], v = x[B + J + half];
-    x[B + J] = gl_add_cc(u, v);
-    x[B + J + half] = dft_twiddle<R, STAGE, J>(gl_sub_cc(u, v));
-}
-template <int R, int STAGE, int B, int J>
-GL_D void dft_stage_js(u64* x) {
-    constexpr int half = 1 << (R - 1 - STAGE);
-    if constexpr (J < half) {
-        dft_stage_pair<R, STAGE, B, J>(x);
-        dft_stage_js<R, STAGE, B, J + 1>(x);
-    }
-}
-template <int R, int STAGE, int B>
-GL_D void dft_stage_blocks(u64* x) {
-    constexpr int half = 1 << (R - 1 - STAGE);
-    if constexpr (B < (1 << R)) {
-        dft_stage_js<R, STAGE, B, 0>(x);
-        dft_stage_blocks<R, STAGE, B + 2 * half>(x);
-    }
-}
-template <int R, int STAGE>
-GL_D void dft_stages(u64* x) {
-    if constexpr (STAGE < R) {
-        dft_stage_blocks<R, STAGE, 0>(x);
-        dft_stages<R, STAGE + 1>(x);
-    }
-}
-// in place: x[q] <- y_{bitrev_R(q)}
-template <int R>
-GL_D void dft_dif(u64* x, bool inverse) {
-    if (inverse) {
-#pragma unroll
-        for (int k = 1; k < (1 << R) / 2; k++) { u64 t = x[k]; x[k] = x[(1 << R) - k]; x[(1 << R) - k] = t; }
-    }
-    dft_stages<R, 0>(x);
-}
+// ------------------------------------------------------------------------------------------------ radix-16 passes
+// A "group" is 4 DIF stages at once on 16 register-resident elements: the multiplication-free 16-point DFT of ntt_l3.cuh
+// (lazy 3-limb additions, products by powers of two), then ONE general twiddle per element.
 __host__ __device__ constexpr int brev_small(int q, int bits) {
     int r = 0;
     for (int i = 0; i < bits; i++) r |= ((q >> i) & 1) << (bits - 1 - i);
     return r;
 }
 
-struct LdeScale {               // coset scaling fused into the first pass of the LDE: x_m *= (g w_N^rho)^m
-    const u64 *g_lo, *g_hi;     // g^m = g_hi[m >> 12] * g_lo[m & 4095]
-    TwiddleView fwd;            // forward W tables for w_N^(rho m)
+struct PassTables {
+    const u64* inner;           // [16][16]
+    const u64* outer;           // [256][M / 256] or nullptr (then the two-level W tables in `tw`)
+    const u64* scale;           // SCALE: [blk_count][n] or nullptr (then g tables + `fwd`)
+    const u64 *g_lo, *g_hi;
+    TwiddleView tw, fwd;
     uint32_t log_N, rate_bits, blk_first, blk_count;
-    u64 step[8][16];            // step[b][k] = (g w_N^rho_b)^(k * 16 * 2^low), b < blk_count <= 8
 };
 
-// Strided pass: the top 8 bits of every 2^log_M block, as two radix-16 groups.  A CTA owns a tile of 256 rows (row
-// stride 2^low elements, low = log_M - 8) x 16 contiguous elements (one 128-byte line per row); thread (r, t) holds
-// rows r + 16 k of column t for the first group and rows 16 r + k for the second (exchange through shared memory).
-// grid.x = tiles per transform, grid.y = transforms.  SCALE: in = coefficients (one transform per column), out = LDE
-// (blk_count transforms per column), log_M = log_n.
-template <bool SCALE>
-__global__ void __launch_bounds__(256) ntt_strided256_kernel(const u64* in, u64* out, uint32_t log_n, uint32_t log_M,
-                                                             TwiddleView tw, bool inverse,
-                                                             const __grid_constant__ LdeScale sc) {
+// Strided pass: the top 8 bits of every 2^log_M block as a 256-point DFT = two radix-16 groups with the w_256 twiddles
+// between them, then the four-step twiddle w_M^(i0 k1).  A CTA owns a tile of 256 rows (row stride 2^low elements,
+// low = log_M - 8) x 16 contiguous elements (one 128-byte line per row); thread (r, t) holds rows r + 16 k of column t for
+// the first group and rows 16 r + k for the second (exchange through shared memory).  grid.x = tiles per transform,
+// grid.y x grid.z = transforms.  SCALE: in = coefficients (one transform per column), out = LDE (blk_count transforms per
+// column, each the coset transform of (g w_N^rho)^m c_m), log_M = log_n.
+// DIRECT: the per-shape tables exist (tb.outer, and tb.scale when SCALE); otherwise the two-level W / g tables.
+template <bool SCALE, bool INV, bool DIRECT>
+__global__ void __launch_bounds__(256) ntt_pass256_kernel(const u64* in, u64* out, uint32_t log_n,
+                                                          uint32_t log_M, const __grid_constant__ PassTables tb) {
     __shared__ u64 sm[256 * NTT_PITCH];
     const uint32_t low = log_M - 8;
     const uint32_t tiles_per_blk = 1u << (low - 4);
     const uint64_t blk = blockIdx.x / tiles_per_blk;
-    const uint32_t i0 = (blockIdx.x % tiles_per_blk) * NTT_TW + (threadIdx.x & 15);
     const uint32_t t = threadIdx.x & 15, r = threadIdx.x >> 4;
+    const uint32_t i0 = (blockIdx.x % tiles_per_blk) * NTT_TW + t;
     const uint64_t tr = (uint64_t)blockIdx.z * gridDim.y + blockIdx.y;       // transform index (grid.y x grid.z)
-    uint64_t src_tr = tr, dst_tr = tr;
+    uint64_t src_tr = tr;
     uint32_t cb = 0;
-    if (SCALE) { cb = (uint32_t)(tr % sc.blk_count); src_tr = tr / sc.blk_count; }
+    if (SCALE) { cb = (uint32_t)(tr % tb.blk_count); src_tr = tr / tb.blk_count; }
+    const size_t rs = (size_t)1 << low;                                        // row stride
     const u64* src = in + (src_tr << log_n) + (blk << log_M) + i0;
-    u64* dst = out + (dst_tr << log_n) + (blk << log_M) + i0;
-    u64 x[16];
+    u64* dst = out + (tr << log_n) + (blk << log_M) + i0;
+    u64 v[16];
 #pragma unroll
-    for (int k = 0; k < 16; k++) x[k] = src[(uint64_t)(r + 16 * k) << low];
-    const uint32_t b1 = (r << low) + i0;                      // index below S1 = 16 * 2^low
+    for (int k = 0; k < 16; k++) v[k] = src[(r + 16 * k) * rs];
     if (SCALE) {
-        const uint32_t rho = sc.rate_bits ? (__brev(sc.blk_first + cb) >> (32 - sc.rate_bits)) : 0;
-        u64 f = gl_mul_cc(__ldg(sc.g_hi + (b1 >> 12)), __ldg(sc.g_lo + (b1 & 4095)));
-        const u32 E = (b1 * rho) << (32 - sc.log_N);
-        if (E) f = gl_mul_cc(f, tw_pow_view(sc.fwd, E));
+        if (DIRECT) {
+            const u64* st = tb.scale + ((uint64_t)cb << log_n) + i0;
 #pragma unroll
-        for (int k = 0; k < 16; k++) x[k] = gl_mul_cc(x[k], k ? gl_mul_cc(f, sc.step[cb][k]) : f);
+            for (int k = 0; k < 16; k++) v[k] = gl_mul_cc(v[k], __ldg(st + (r + 16 * k) * rs));
+        } else {
+            // shapes without a scale table: f = s^b1 from the two-level tables, then s^(b1 + k S1) = f * step^k
+            const uint32_t b1 = (r << low) + i0;
+            const uint32_t rho = tb.rate_bits ? (__brev(tb.blk_first + cb) >> (32 - tb.rate_bits)) : 0;
+            u64 f = gl_mul_cc(__ldg(tb.g_hi + (b1 >> 12)), __ldg(tb.g_lo + (b1 & 4095)));
+            const u32 E = (b1 * rho) << (32 - tb.log_N);
+            if (E) f = gl_mul_cc(f, tw_pow_view(tb.fwd, E));
+            const uint32_t S1 = 16u << low;
+            u64 st = gl_mul_cc(__ldg(tb.g_hi + (S1 >> 12)), __ldg(tb.g_lo + (S1 & 4095)));
+            const u32 Es = (S1 * rho) << (32 - tb.log_N);
+            if (Es) st = gl_mul_cc(st, tw_pow_view(tb.fwd, Es));
+#pragma unroll
+            for (int k = 0; k < 16; k++) { v[k] = gl_mul_cc(v[k], f); f = gl_mul_cc(f, st); }
+        }
     }
-    dft_dif<4>(x, inverse);
+    L3 x[16];
 #pragma unroll
-    for (int q = 1; q < 16; q++) {
-        const u32 E = (b1 * (u32)brev_small(q, 4)) << (32 - log_M);
-        if (E) x[q] = gl_mul_cc(x[q], tw_pow_view(tw, E));
-    }
+    for (int k = 0; k < 16; k++) x[k] = l3_from(v[k]);
+    l3_dft<4, INV>(x);
+    const u64* inner = tb.inner + r;
+    sm[r * NTT_PITCH + t] = l3_reduce(x[0]);
 #pragma unroll
-    for (int q = 0; q < 16; q++) sm[(r + 16 * q) * NTT_PITCH + t] = x[q];
+    for (int q = 1; q < 16; q++) sm[(r + 16 * q) * NTT_PITCH + t] = gl_mul_cc(l3_reduce(x[q]), __ldg(inner + 16 * q));
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < 16; k++) x[k] = sm[(16 * r + k) * NTT_PITCH + t];
-    dft_dif<4>(x, inverse);
+    for (int k = 0; k < 16; k++) x[k] = l3_from(sm[(16 * r + k) * NTT_PITCH + t]);
+    l3_dft<4, INV>(x);
+    if (DIRECT) {
+        const u64* ow = tb.outer + 16 * r * rs + i0;
+        u64* d2 = dst + 16 * r * rs;
 #pragma unroll
-    for (int q = 1; q < 16; q++) {
-        const u32 E = (i0 * (u32)brev_small(q, 4)) << (32 - (log_M - 4));      // w_{M/16}^(i0 j)
-        if (E) x[q] = gl_mul_cc(x[q], tw_pow_view(tw, E));
+        for (int q = 0; q < 16; q++) d2[q * rs] = gl_mul_cc(l3_reduce(x[q]), __ldg(ow + q * rs));     // any representative: a final pass follows
+    } else {
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            const uint32_t k1 = (uint32_t)brev_small(q, 4) * 16 + (__brev(r) >> 28);      // bitrev_8(16 r + q)
+            const u32 E = (i0 * k1) << (32 - log_M);
+            u64 y = l3_reduce(x[q]);
+            if (E) y = gl_mul_cc(y, tw_pow_view(tb.tw, E));
+            dst[(16 * r + q) * rs] = y;
+        }
     }
-#pragma unroll
-    for (int q = 0; q < 16; q++) dst[(uint64_t)(16 * r + q) << low] = gl_canon(x[q]);
 }
 
 // one radix-2^R group over a 4096-element chunk held in (padded) shared memory; S = elements below the group
 #define NTT_PAD(i) ((i) + ((i) >> 4))
-template <int R>
-GL_D void ntt_smem_group(u64* sm, uint32_t s_bits, const u64* __restrict__ full12, bool inverse) {
+template <int R, bool INV>
+GL_D void ntt_smem_group(u64* sm, uint32_t s_bits, const u64* __restrict__ full12) {
     const uint32_t S = 1u << s_bits;
     for (uint32_t u = threadIdx.x; u < (4096u >> R); u += 256) {
         const uint32_t b = u & (S - 1);
         const uint32_t base = ((u >> s_bits) << (s_bits + R)) + b;
-        u64 x[1 << R];
+        L3 x[1 << R];
 #pragma unroll
-        for (int k = 0; k < (1 << R); k++) x[k] = sm[NTT_PAD(base + ((uint32_t)k << s_bits))];
-        dft_dif<R>(x, inverse);
+        for (int k = 0; k < (1 << R); k++) x[k] = l3_from(sm[NTT_PAD(base + ((uint32_t)k << s_bits))]);
+        l3_dft<R, INV>(x);
+        sm[NTT_PAD(base)] = l3_reduce(x[0]);
         if (s_bits) {
 #pragma unroll
             for (int q = 1; q < (1 << R); q++) {
-                const uint32_t e = (b * (uint32_t)brev_small(q, R)) << (12 - s_bits - R);
-                if (e) x[q] = gl_mul_cc(x[q], __ldg(full12 + e));
+                const uint32_t e = (b * (uint32_t)brev_small(q, R)) << (12 - s_bits - R);      // w_(2^R S)^(b j), full12[0] = 1
+                sm[NTT_PAD(base + ((uint32_t)q << s_bits))] = gl_mul_cc(l3_reduce(x[q]), __ldg(full12 + e));
             }
-        }
+        } else {
 #pragma unroll
-        for (int q = 0; q < (1 << R); q++) sm[NTT_PAD(base + ((uint32_t)q << s_bits))] = x[q];
+            for (int q = 1; q < (1 << R); q++) sm[NTT_PAD(base + (uint32_t)q)] = l3_reduce(x[q]);
+        }
     }
 }
 
 // Final pass: F DIF stages on contiguous 2^F blocks (F <= 12); a CTA owns 4096 contiguous elements.
-__global__ void __launch_bounds__(256) ntt_final4096_kernel(u64* __restrict__ data, uint32_t F, TwiddleView tw, bool inverse) {
+template <bool INV>
+__global__ void __launch_bounds__(256) ntt_final4096_kernel(u64* __restrict__ data, uint32_t F, const u64* __restrict__ full12) {
     __shared__ u64 sm[4096 + 256];
     u64* base = data + ((uint64_t)blockIdx.x << 12);
     for (uint32_t e = threadIdx.x; e < 4096; e += 256) sm[NTT_PAD(e)] = base[e];
@@ -320,18 +344,26 @@ __global__ void __launch_bounds__(256) ntt_final4096_kernel(u64* __restrict__ da
     const uint32_t r1 = ((F - 1) & 3) + 1;                  // first group takes F mod 4 bits (or 4)
     rem -= r1;
     switch (r1) {
-        case 1: ntt_smem_group<1>(sm, rem, tw.full12, inverse); break;
-        case 2: ntt_smem_group<2>(sm, rem, tw.full12, inverse); break;
-        case 3: ntt_smem_group<3>(sm, rem, tw.full12, inverse); break;
-        default: ntt_smem_group<4>(sm, rem, tw.full12, inverse); break;
+        case 1: ntt_smem_group<1, INV>(sm, rem, full12); break;
+        case 2: ntt_smem_group<2, INV>(sm, rem, full12); break;
+        case 3: ntt_smem_group<3, INV>(sm, rem, full12); break;
+        default: ntt_smem_group<4, INV>(sm, rem, full12); break;
     }
     __syncthreads();
     while (rem) {
         rem -= 4;
-        ntt_smem_group<4>(sm, rem, tw.full12, inverse);
+        ntt_smem_group<4, INV>(sm, rem, full12);
         __syncthreads();
     }
     for (uint32_t e = threadIdx.x; e < 4096; e += 256) base[e] = gl_canon(sm[NTT_PAD(e)]);
+}
+
+// transforms are spread over grid.y x grid.z (count must factor as gy * gz with gy <= 65535)
+static int32_t grid_yz(uint64_t count, uint64_t* gy, uint64_t* gz) {
+    *gy = count; *gz = 1;
+    while (*gy > 32768 && (*gy & 1) == 0) { *gy >>= 1; *gz <<= 1; }
+    VX_REQUIRE(*gy <= 65535 && *gz <= 65535, "ntt: cannot tile %llu transforms over the grid", (unsigned long long)count);
+    return VX_OK;
 }
 
 int32_t ntt_dif_inplace(vx_ctx* ctx, u64* data, uint64_t count, uint32_t log_n, bool inverse) {
@@ -339,35 +371,32 @@ int32_t ntt_dif_inplace(vx_ctx* ctx, u64* data, uint64_t count, uint32_t log_n, 
     VX_REQUIRE(log_n <= 32, "ntt: log_n %u exceeds the field's two-adicity", log_n);
     TwiddleView tw = tw_view(ctx, inverse);
     uint32_t rem = log_n;
-    const bool fast = !ctx->ntt_legacy;
-    while (rem > 12) {
-        uint64_t tiles;
-        // transforms are spread over grid.y x grid.z (count must factor as gy * gz with gy a power of two <= 32768)
-        uint64_t gy = count, gz = 1;
-        while (gy > 32768 && (gy & 1) == 0) { gy >>= 1; gz <<= 1; }
-        VX_REQUIRE(gy <= 65535 && gz <= 65535, "ntt: cannot tile %llu transforms over the grid", (unsigned long long)count);
-        if (fast && rem >= 16) {                       // radix-16 register pass over the top 8 bits
-            tiles = (1ULL << log_n) >> 12;
-            VX_REQUIRE(tiles < (1ULL << 31), "ntt: transform too large");
-            dim3 grid((unsigned)tiles, (unsigned)gy, (unsigned)gz);
-            ntt_strided256_kernel<false><<<grid, 256, 0, ctx->stream>>>(data, data, log_n, rem, tw, inverse, LdeScale{});
-            VX_LAUNCH_COUNT(ctx, 1);
-            rem -= 8;
-            continue;
-        }
-        uint32_t A = rem - 8 < 8 ? rem - 8 : 8;
-        tiles = (1ULL << log_n) / ((1ULL << A) * NTT_TW);
+    while (rem > 12) {                                  // radix-16 register pass over the top 8 bits (rem - 8 >= 5 is left)
+        uint64_t gy, gz;
+        VX_CHECK(grid_yz(count, &gy, &gz));
+        const uint64_t tiles = (1ULL << log_n) >> 12;
         VX_REQUIRE(tiles < (1ULL << 31), "ntt: transform too large");
+        PassTables tb;
+        memset(&tb, 0, sizeof tb);
+        tb.inner = inverse ? ctx->inner_inv : ctx->inner_fwd;
+        tb.tw = tw;
+        VX_CHECK(outer_table(ctx, rem, inverse, &tb.outer));
         dim3 grid((unsigned)tiles, (unsigned)gy, (unsigned)gz);
-        size_t smem = (size_t)(1u << A) * NTT_PITCH * sizeof(u64);
-        ntt_strided_pass<<<grid, 256, smem, ctx->stream>>>(data, log_n, rem, A, tw);
+        if (tb.outer) {
+            if (inverse) ntt_pass256_kernel<false, true, true><<<grid, 256, 0, ctx->stream>>>(data, data, log_n, rem, tb);
+            else ntt_pass256_kernel<false, false, true><<<grid, 256, 0, ctx->stream>>>(data, data, log_n, rem, tb);
+        } else {
+            if (inverse) ntt_pass256_kernel<false, true, false><<<grid, 256, 0, ctx->stream>>>(data, data, log_n, rem, tb);
+            else ntt_pass256_kernel<false, false, false><<<grid, 256, 0, ctx->stream>>>(data, data, log_n, rem, tb);
+        }
         VX_LAUNCH_COUNT(ctx, 1);
-        rem -= A;
+        rem -= 8;
     }
     uint64_t total = count << log_n;
-    if (fast && rem >= 1 && (total & 4095) == 0) {
+    if ((total & 4095) == 0) {
         VX_REQUIRE((total >> 12) < (1ULL << 31), "ntt: too many blocks");
-        ntt_final4096_kernel<<<(unsigned)(total >> 12), 256, 0, ctx->stream>>>(data, rem, tw, inverse);
+        if (inverse) ntt_final4096_kernel<true><<<(unsigned)(total >> 12), 256, 0, ctx->stream>>>(data, rem, tw.full12);
+        else ntt_final4096_kernel<false><<<(unsigned)(total >> 12), 256, 0, ctx->stream>>>(data, rem, tw.full12);
         VX_LAUNCH_COUNT(ctx, 1);
         VX_CUDA(cudaGetLastError());
         return VX_OK;
@@ -431,27 +460,24 @@ __global__ void lde_scale_kernel(const u64* __restrict__ coeffs, u64* __restrict
 
 int32_t lde_batch(vx_ctx* ctx, const u64* coeffs, u64* lde_out, uint32_t c, uint32_t log_n, uint32_t rate_bits,
                   uint32_t blk_first, uint32_t blk_count) {
-    VX_REQUIRE(log_n + rate_bits <= 26, "lde: 2^%u points exceeds the coset table (2^26)", log_n + rate_bits);
+    VX_REQUIRE(log_n <= 26 && log_n + rate_bits <= 32, "lde: 2^%u rows at rate_bits %u exceed the coset tables", log_n, rate_bits);
     VX_REQUIRE(blk_count >= 1 && blk_first + blk_count <= (1u << rate_bits), "lde: coset block range out of bounds");
     uint64_t n = 1ULL << log_n;
-    if (!ctx->ntt_legacy && log_n >= 16 && blk_count <= 8) {
+    if (log_n >= 13) {
         // first pass fused with the coset scaling: reads the coefficients once per coset (L2-resident), writes the LDE
-        LdeScale sc;
-        memset(&sc, 0, sizeof sc);
-        sc.g_lo = ctx->g_lo; sc.g_hi = ctx->g_hi; sc.fwd = tw_view(ctx, false);
-        sc.log_N = log_n + rate_bits; sc.rate_bits = rate_bits; sc.blk_first = blk_first; sc.blk_count = blk_count;
-        const u64 wN = gl_root_of_unity_host(log_n + rate_bits);
-        for (uint32_t b = 0; b < blk_count; b++) {
-            uint32_t rho = (uint32_t)bitrev_u64(blk_first + b, rate_bits);
-            u64 base = gl_mul_slow(GL_GENERATOR, gl_pow_host(wN, rho));          // g w_N^rho
-            u64 st = gl_pow_host(base, n >> 4), acc = 1;                         // ^(16 * 2^low), low = log_n - 8
-            for (int k = 0; k < 16; k++) { sc.step[b][k] = acc; acc = gl_mul_slow(acc, st); }
-        }
-        uint64_t gy = (uint64_t)c * blk_count, gz = 1;
-        while (gy > 32768 && (gy & 1) == 0) { gy >>= 1; gz <<= 1; }
-        VX_REQUIRE(gy <= 65535, "lde: cannot tile %u x %u transforms over the grid", c, blk_count);
+        PassTables tb;
+        memset(&tb, 0, sizeof tb);
+        tb.inner = ctx->inner_fwd;
+        tb.tw = tb.fwd = tw_view(ctx, false);
+        tb.g_lo = ctx->g_lo; tb.g_hi = ctx->g_hi;
+        tb.log_N = log_n + rate_bits; tb.rate_bits = rate_bits; tb.blk_first = blk_first; tb.blk_count = blk_count;
+        VX_CHECK(outer_table(ctx, log_n, false, &tb.outer));
+        VX_CHECK(scale_table(ctx, log_n, rate_bits, blk_first, blk_count, &tb.scale));
+        uint64_t gy, gz;
+        VX_CHECK(grid_yz((uint64_t)c * blk_count, &gy, &gz));
         dim3 grid((unsigned)(n >> 12), (unsigned)gy, (unsigned)gz);
-        ntt_strided256_kernel<true><<<grid, 256, 0, ctx->stream>>>(coeffs, lde_out, log_n, log_n, sc.fwd, false, sc);
+        if (tb.outer && tb.scale) ntt_pass256_kernel<true, false, true><<<grid, 256, 0, ctx->stream>>>(coeffs, lde_out, log_n, log_n, tb);
+        else ntt_pass256_kernel<true, false, false><<<grid, 256, 0, ctx->stream>>>(coeffs, lde_out, log_n, log_n, tb);
         VX_LAUNCH_COUNT(ctx, 1);
         VX_CUDA(cudaGetLastError());
         // remaining stages: every 2^(log_n - 8) block is an independent transform
