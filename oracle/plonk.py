@@ -15,6 +15,17 @@ import numpy as np
 from . import P, GENERATOR, commit_from_coeffs, commit_from_values, hash_no_pad, lib, _ptr, merkle_new, merkle_prove, \
     merkle_verify, poseidon
 from . import pyref
+
+
+def hash_pad(inputs, block=8):
+    """Hasher::hash_pad: pad10*1 up to a multiple of `block`, then hash_no_pad.  In-tree statement of the rule:
+    contracts/lib/succinctx/plonky2x/core/src/backend/wrapper/plonky2_config.rs:174-182 (pads to the elements absorbed per
+    permutation).  Unpinned against plonky2 v0.2.0 itself (rate 8 vs width 12) -- see DESIGN.md section 5."""
+    padded = [int(x) % P for x in inputs] + [1]
+    while (len(padded) + 1) % block:
+        padded.append(0)
+    padded.append(1)
+    return [int(x) for x in hash_no_pad(padded)]
 from .field import E2, FA, FI, finv, fpow
 from .gates import NUM_ROUTED, NUM_WIRES, Gate, NoopGate, PublicInputGate
 
@@ -132,8 +143,10 @@ class Circuit:
         self.constants_sigmas = cs
         self.cs_commit = commit_from_values(cs, self.cfg.rate_bits, self.cfg.cap_height)
         cap = self.cs_commit["cap"]
+        # CircuitBuilder::build: hash_no_pad(cap.flatten() ++ hash_pad(domain_separator = []) ++ [degree_bits])
+        self.domain_separator_digest = hash_pad([])
         self.circuit_digest = [int(x) for x in hash_no_pad(
-            [int(x) for x in cap.reshape(-1)] + [0, 0, 0, 0] + [self.d])]
+            [int(x) for x in cap.reshape(-1)] + self.domain_separator_digest + [self.d])]
 
     def _selectors(self):
         md = self.cfg.max_degree

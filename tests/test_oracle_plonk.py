@@ -272,3 +272,15 @@ def test_oracle_proofs_match_committed_golden():
     assert [g["name"] for g in gold] == [c["name"] for c in mod.CASES]
     for case, want in zip(mod.CASES, gold):
         assert mod.run_case(case)[4] == want
+
+
+def test_hash_pad_host_matches_oracle_and_is_not_the_zero_digest():
+    """circuit_digest's middle slot is hash_pad(domain_separator = []) (pad10*1), not four zeros: the product-side host
+    hash and the oracle agree, and the value is what hash_no_pad gives on the padded block."""
+    from oracle import hash_no_pad
+    from vectorx_b200.challenger import hash_pad_host
+    got = hash_pad_host([])
+    assert got == plonk.hash_pad([]) == [int(x) for x in hash_no_pad([1, 0, 0, 0, 0, 0, 0, 1])]
+    assert any(got)
+    assert hash_pad_host([5, 6, 7]) == plonk.hash_pad([5, 6, 7]) == [int(x) for x in hash_no_pad([5, 6, 7, 1, 0, 0, 0, 1])]
+    assert hash_pad_host([], block=12) == [int(x) for x in hash_no_pad([1] + [0] * 10 + [1])]

@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvectorx_b200.so")
+# VX_B200_LIB: development override used for A/B builds (csrc/Makefile VARIANT=...); the shipped library otherwise
+LIB_PATH = os.environ.get("VX_B200_LIB") or os.path.join(_HERE, "libvectorx_b200.so")
 
 u64p = ctypes.POINTER(ctypes.c_uint64)
 u32p = ctypes.POINTER(ctypes.c_uint32)

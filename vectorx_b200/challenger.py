@@ -27,6 +27,20 @@ def hash_no_pad_host(inputs):
     return st[:4]
 
 
+def hash_pad_host(inputs, block=8):
+    """`Hasher::hash_pad` (pad10*1 then `hash_no_pad`): push 1, zeros until one short of a multiple of `block`, push 1.
+    The only statement of the rule inside the reference tree is the in-tree `Hasher` implementation at
+    contracts/lib/succinctx/plonky2x/core/src/backend/wrapper/plonky2_config.rs:174-182, which pads to the number of
+    field elements one permutation absorbs (the rate: 8 for Poseidon over Goldilocks, the default here).  plonky2
+    releases have also padded to the sponge WIDTH (12); which one v0.2.0 uses cannot be checked in this container, so the
+    value is overridable wherever it is consumed (`CircuitData(domain_separator_digest=..., circuit_digest=...)`)."""
+    padded = [int(x) % P for x in inputs] + [1]
+    while (len(padded) + 1) % block:
+        padded.append(0)
+    padded.append(1)
+    return hash_no_pad_host(padded)
+
+
 class Challenger:
     def __init__(self):
         self.sponge_state = [0] * 12

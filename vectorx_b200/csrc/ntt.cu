@@ -307,17 +307,33 @@ __global__ void __launch_bounds__(256) ntt_pass256_kernel(const u64* in, u64* ou
     }
 }
 
-// one radix-2^R group over a 4096-element chunk held in (padded) shared memory; S = elements below the group
+// one radix-2^R group over a 4096-element chunk; S = 2^s_bits elements below the group.  The chunk lives in (padded) shared
+// memory; the FIRST group of a pass reads its inputs straight from global memory instead (all 16 loads of a thread in flight
+// at once, every warp access a run of full 128-byte lines) and so needs no staging copy and no barrier before it.
 #define NTT_PAD(i) ((i) + ((i) >> 4))
-template <int R, bool INV>
-GL_D void ntt_smem_group(u64* sm, uint32_t s_bits, const u64* __restrict__ full12) {
+template <int R, bool INV, bool FROM_GLOBAL>
+GL_D void ntt_smem_group(const u64* __restrict__ gin, u64* sm, uint32_t s_bits, const u64* __restrict__ full12) {
+    constexpr int ITERS = 16 >> R;                          // (4096 >> R) units over 256 threads
     const uint32_t S = 1u << s_bits;
-    for (uint32_t u = threadIdx.x; u < (4096u >> R); u += 256) {
+    u64 v[16];
+    if (FROM_GLOBAL) {
+#pragma unroll
+        for (int it = 0; it < ITERS; it++) {
+            const uint32_t u = threadIdx.x + 256 * it;
+            const uint32_t base = ((u >> s_bits) << (s_bits + R)) + (u & (S - 1));
+#pragma unroll
+            for (int k = 0; k < (1 << R); k++) v[(it << R) + k] = gin[base + ((uint32_t)k << s_bits)];
+        }
+    }
+#pragma unroll
+    for (int it = 0; it < ITERS; it++) {
+        const uint32_t u = threadIdx.x + 256 * it;
         const uint32_t b = u & (S - 1);
         const uint32_t base = ((u >> s_bits) << (s_bits + R)) + b;
         L3 x[1 << R];
 #pragma unroll
-        for (int k = 0; k < (1 << R); k++) x[k] = l3_from(sm[NTT_PAD(base + ((uint32_t)k << s_bits))]);
+        for (int k = 0; k < (1 << R); k++)
+            x[k] = l3_from(FROM_GLOBAL ? v[(it << R) + k] : sm[NTT_PAD(base + ((uint32_t)k << s_bits))]);
         l3_dft<R, INV>(x);
         sm[NTT_PAD(base)] = l3_reduce(x[0]);
         if (s_bits) {
@@ -334,28 +350,33 @@ GL_D void ntt_smem_group(u64* sm, uint32_t s_bits, const u64* __restrict__ full1
 }
 
 // Final pass: F DIF stages on contiguous 2^F blocks (F <= 12); a CTA owns 4096 contiguous elements.
+#ifndef NTT_FINAL_MINB
+#define NTT_FINAL_MINB 4
+#endif
 template <bool INV>
-__global__ void __launch_bounds__(256) ntt_final4096_kernel(u64* __restrict__ data, uint32_t F, const u64* __restrict__ full12) {
+__global__ void __launch_bounds__(256, NTT_FINAL_MINB) ntt_final4096_kernel(u64* __restrict__ data, uint32_t F, const u64* __restrict__ full12) {
     __shared__ u64 sm[4096 + 256];
     u64* base = data + ((uint64_t)blockIdx.x << 12);
-    for (uint32_t e = threadIdx.x; e < 4096; e += 256) sm[NTT_PAD(e)] = base[e];
-    __syncthreads();
     uint32_t rem = F;
     const uint32_t r1 = ((F - 1) & 3) + 1;                  // first group takes F mod 4 bits (or 4)
     rem -= r1;
     switch (r1) {
-        case 1: ntt_smem_group<1, INV>(sm, rem, full12); break;
-        case 2: ntt_smem_group<2, INV>(sm, rem, full12); break;
-        case 3: ntt_smem_group<3, INV>(sm, rem, full12); break;
-        default: ntt_smem_group<4, INV>(sm, rem, full12); break;
+        case 1: ntt_smem_group<1, INV, true>(base, sm, rem, full12); break;
+        case 2: ntt_smem_group<2, INV, true>(base, sm, rem, full12); break;
+        case 3: ntt_smem_group<3, INV, true>(base, sm, rem, full12); break;
+        default: ntt_smem_group<4, INV, true>(base, sm, rem, full12); break;
     }
     __syncthreads();
     while (rem) {
         rem -= 4;
-        ntt_smem_group<4, INV>(sm, rem, full12);
+        ntt_smem_group<4, INV, false>(nullptr, sm, rem, full12);
         __syncthreads();
     }
-    for (uint32_t e = threadIdx.x; e < 4096; e += 256) base[e] = gl_canon(sm[NTT_PAD(e)]);
+    u64 o[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) o[k] = sm[NTT_PAD(threadIdx.x + 256 * k)];
+#pragma unroll
+    for (int k = 0; k < 16; k++) base[threadIdx.x + 256 * k] = gl_canon(o[k]);
 }
 
 // transforms are spread over grid.y x grid.z (count must factor as gy * gz with gy <= 65535)

@@ -18,7 +18,7 @@ import numpy as np
 
 from . import gates as gate_lib
 from ._lib import Context, DeviceArray, check, default_context, load, ptr, vp
-from .challenger import Challenger, hash_no_pad_host
+from .challenger import Challenger, hash_no_pad_host, hash_pad_host
 from .plonky2 import PolynomialBatch
 
 P = 0xFFFFFFFF00000001
@@ -48,7 +48,16 @@ class CircuitData:
     def __init__(self, degree_bits, gate_ids, selector_index, groups, constants, sigmas, *, num_wires=135,
                  num_routed_wires=80, rate_bits=3, cap_height=4, num_challenges=2, max_degree=8,
                  quotient_degree_factor=8, num_query_rounds=28, proof_of_work_bits=16, arity_bits=4,
-                 final_poly_bits=5, ctx: Context | None = None, superops: bool = True):
+                 final_poly_bits=5, ctx: Context | None = None, superops: bool = True,
+                 domain_separator=(), domain_separator_digest=None, circuit_digest=None):
+        # plonky2 keeps three independent parameters -- max_quotient_degree_factor (= max_degree here), the circuit's
+        # quotient_degree_factor (chunk size of the permutation argument, number of quotient chunks) and 2^rate_bits (size
+        # of the LDE the quotient is evaluated on).  The device path chunks by max_degree and reshapes the quotient as
+        # 2^rate_bits chunks, which is only the same thing when all three agree (standard_recursion_config: 8 / 8 / 3,
+        # contracts/lib/succinctx/plonky2x/core/src/frontend/builder/mod.rs:69): anything else is rejected, not mis-proved.
+        if not (quotient_degree_factor == max_degree == (1 << rate_bits)):
+            raise ValueError(f"unsupported circuit config: quotient_degree_factor={quotient_degree_factor}, "
+                             f"max_degree={max_degree}, 2^rate_bits={1 << rate_bits} must all be equal")
         self.ctx = ctx or default_context()
         self.degree_bits, self.n = degree_bits, 1 << degree_bits
         self.gate_ids, self.selector_index, self.groups = list(gate_ids), list(selector_index), [tuple(g) for g in groups]
@@ -72,7 +81,15 @@ class CircuitData:
         cs = np.concatenate([self.constants, self.sigmas])
         self.constants_sigmas_commitment = PolynomialBatch.from_values(cs, rate_bits, False, cap_height, ctx=self.ctx)
         cap = self.constants_sigmas_commitment.cap.hashes
-        self.circuit_digest = hash_no_pad_host([int(x) for x in cap.reshape(-1)] + [0, 0, 0, 0] + [degree_bits])
+        # plonky2 `CircuitBuilder::build`: circuit_digest = hash_no_pad(cap.flatten() ++ hash_pad(domain_separator) ++
+        # [degree_bits]); the domain separator is empty unless the builder set one.  A caller that holds the Rust-side
+        # values (CommonCircuitData / VerifierOnlyCircuitData) passes them in and they are used verbatim.
+        if domain_separator_digest is None:
+            domain_separator_digest = hash_pad_host(list(domain_separator))
+        self.domain_separator_digest = [int(x) % P for x in domain_separator_digest]
+        if circuit_digest is None:
+            circuit_digest = hash_no_pad_host([int(x) for x in cap.reshape(-1)] + self.domain_separator_digest + [degree_bits])
+        self.circuit_digest = [int(x) % P for x in circuit_digest]
         self.desc = VxCircuitDesc(degree_bits, rate_bits, num_wires, num_routed_wires, self.num_constants,
                                   self.num_selectors, num_challenges, self.num_partial_products, max_degree,
                                   self.num_gate_constraints, self.k_is.ctypes.data, self.program.ctypes.data,
