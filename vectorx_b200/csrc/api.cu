@@ -63,15 +63,6 @@ extern "C" int32_t vx_ctx_create(int32_t device, vx_ctx** out) {
     if (!ctx) return VX_ENOMEM;
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
-    if (const char* v = getenv("VX_POSEIDON_VARIANT")) ctx->poseidon_variant = atoi(v);
-    if (const char* v = getenv("VX_NTT_LEGACY")) ctx->ntt_legacy = atoi(v);
-    if (const char* v = getenv("VX_TREE_FUSE")) ctx->tree_fuse = atoi(v);
-    if (const char* v = getenv("VX_COOP_MAX_PAIRS")) ctx->coop_max_pairs = atoi(v);
-    if (const char* v = getenv("VX_STREAM_SPONGE")) ctx->stream_sponge = atoi(v);
-    if (const char* v = getenv("VX_SHARD_STREAM")) ctx->shard_stream = atoi(v);
-    if (const char* v = getenv("VX_STREAM_CHUNKS")) { int k = atoi(v); if (k >= 1 && k <= 15) ctx->stream_chunks = (uint32_t)k; }
-    if (const char* v = getenv("VX_H2D_FIRST_GROUPS")) { int k = atoi(v); if (k >= 1 && k <= 64) ctx->h2d_first_groups = (uint32_t)k; }
-    if (const char* v = getenv("VX_H2D_CHUNKS")) { int k = atoi(v); if (k >= 1 && k <= 8) ctx->h2d_chunks = (uint32_t)k; }
     cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete ctx; vx_set_error("stream create: %s", cudaGetErrorString(e)); return VX_ECUDA; }
     // keep freed blocks in the stream-ordered pool: commits allocate GBs per call
@@ -237,7 +228,7 @@ static int32_t commit_run(vx_ctx* ctx, vx_batch* b, const u64* src, bool is_valu
     }
     // streaming sponge: chunk boundaries fall on multiples of the sponge rate and every chunk is absorbed into the per-leaf
     // state right after its LDE, so only the LAST chunk's hashing is left when the last copy lands
-    const bool stream = nchunks > 1 && ctx->stream_sponge && b->hasher == VX_HASHER_POSEIDON && c > 4;
+    const bool stream = nchunks > 1 && b->hasher == VX_HASHER_POSEIDON && c > 4;
     // Chunks grow geometrically (8, 16, 32, ... columns) so that the copy of chunk k+1 is never longer than the work on
     // the chunks before it; the doubling stops once the rest can hide too.  Work per column / copy per column is about
     // 2^rate_bits (hashing is per LDE row, the copy per trace row): ~8 at rate_bits 3 -- 2^16 x 135 goes as 8 / 16 / 111

@@ -51,18 +51,13 @@ enum { VX_EV_START = 0, VX_EV_STAGED, VX_EV_INTT, VX_EV_LDE, VX_EV_LEAF, VX_EV_T
 struct vx_ctx {
     int device = 0;
     int sm_count = 0;
-    int ntt_legacy = 0;                 // VX_NTT_LEGACY=1: radix-2 shared-memory passes only (A/B switch)
-    int coop_max_pairs = 4096;          // Merkle levels with at most this many pairs use 16 lanes per two_to_one (VX_COOP_MAX_PAIRS)
-    int tree_fuse = 1;                  // VX_TREE_FUSE=0: one launch per small Merkle level (A/B switch)
-    uint32_t h2d_chunks = 8;            // VX_H2D_CHUNKS: column chunks of a commit from host memory (copy / transform overlap)
-    uint32_t stream_chunks = 15;        // VX_STREAM_CHUNKS: upper bound on the chunks of the streamed form (sizes double until the rest hides)
-    uint32_t h2d_first_groups = 1;      // VX_H2D_FIRST_GROUPS: size of the first streamed chunk in 8-column groups (then doubling)
-    int stream_sponge = 1;              // VX_STREAM_SPONGE: hash each column chunk as it lands (0 = hash after the last chunk)
-    int poseidon_variant = 0;           // VX_POSEIDON_VARIANT (A/B switch for profiling): 0 = default, 1 = shared-memory state, 2 = 128-register form
+    // commits from host memory travel as column chunks (copy / transform / hash overlap); tuned values, see api.cu
+    static constexpr uint32_t h2d_chunks = 8;         // chunks of the non-streamed form (hashers other than Poseidon)
+    static constexpr uint32_t stream_chunks = 15;     // upper bound on the chunks of the streamed form
+    static constexpr uint32_t h2d_first_groups = 1;   // first streamed chunk in 8-column groups (then doubling)
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr; // host->device staging of commit inputs, overlapped with the transforms
     cudaStream_t aux_stream = nullptr;  // producer side of a streamed sharded commit (iNTT + peer push of the own slice)
-    int shard_stream = 1;               // VX_SHARD_STREAM=0: sharded commit without the column pipeline (A/B switch)
     // streamed leaf hashing: one event pair per leaf_absorb launch of the most recent commit (their sum is the leaf-hash
     // time vx_ctx_phase_ms reports; the launches interleave with the transforms)
     static constexpr int VX_MAX_ABSORB = 64;

@@ -88,12 +88,11 @@ static __constant__ u32 c_gl_eps = 0xFFFFFFFFu;
 //   t = x2*eps + (x1:x0)  (carry C),  t -= x3  (borrow B);  x = t + (C - B)*2^64 = t + (C - B)*eps  (mod p)
 // and t + (C - B)*eps always lands in [0, 2^64): C = 1 needs t <= 2^64 - 2^33 + 1, B = 1 (x3 < 2^32) needs
 // t >= 2^64 - 2^32 + 1, so the single signed fix-up can neither overflow nor underflow.
-// Default: x2*eps + (x1:x0) as ONE accumulating IMAD.WIDE.U32 with carry-out (1 FMA-heavy + 9 ALU instructions).
-// -DGL_REDUCE_ALU: x2*eps = (x2 << 32) - x2 on the ALU pipe (12 ALU instructions, no multiply) -- measured slower:
-// tools/sboxbench.cu gives 31.2 (default) vs 36.5 (ALU form) SMSP cycles per multiplication, leaf hashing 8.64 vs 9.56 ms.
+// x2*eps + (x1:x0) is ONE accumulating IMAD.WIDE.U32 with carry-out (1 FMA-heavy + 9 ALU instructions).  Measured and
+// rejected (profiles/r01*, profiles/r02_poseidon_ab.md): x2*eps = (x2 << 32) - x2 on the ALU pipe (12 ALU instructions, leaf
+// hashing 9.56 vs 8.64 ms), and the two fix-ups as predicated +-eps adds (ptxas materialises the predicates: more code).
 GL_D u64 gl_reduce128_cc(u32 x0, u32 x1, u32 x2, u32 x3) {
     u32 r0, r1;
-#ifndef GL_REDUCE_ALU
     asm("{\n\t"
         ".reg .u32 t0, t1, w2, s;\n\t"
         "mad.lo.cc.u32 t0, %4, %6, %2;\n\t"
@@ -109,25 +108,6 @@ GL_D u64 gl_reduce128_cc(u32 x0, u32 x1, u32 x2, u32 x3) {
         "}"
         : "=r"(r0), "=r"(r1)
         : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(c_gl_eps));
-#else
-    asm("{\n\t"
-        ".reg .u32 e0, e1, t0, t1, w2, s;\n\t"
-        "sub.cc.u32 e0, 0, %4;\n\t"               // e = x2*eps = (x2 << 32) - x2
-        "subc.u32 e1, %4, 0;\n\t"
-        "add.cc.u32 t0, %2, e0;\n\t"              // t = (x1:x0) + e, carry C
-        "addc.cc.u32 t1, %3, e1;\n\t"
-        "addc.u32 w2, 0, 0;\n\t"
-        "sub.cc.u32 t0, t0, %5;\n\t"              // t -= x3, borrow B
-        "subc.cc.u32 t1, t1, 0;\n\t"
-        "subc.u32 w2, w2, 0;\n\t"                 // w2 = C - B in {-1, 0, 1}
-        "shr.s32 s, w2, 31;\n\t"
-        "sub.cc.u32 %0, t0, w2;\n\t"              // t += w2*eps = (w2 << 32) - sext(w2)
-        "subc.u32 t1, t1, s;\n\t"
-        "add.u32 %1, t1, w2;\n\t"
-        "}"
-        : "=r"(r0), "=r"(r1)
-        : "r"(x0), "r"(x1), "r"(x2), "r"(x3));
-#endif
     return pack64(r0, r1);
 }
 
@@ -182,6 +162,8 @@ GL_D u64 gl_mul_add_cc(u64 a, u64 b, u64 c) {
     return gl_reduce128_cc(lo32(p0), r1, r2, r3);
 }
 
+// a^2: three products, the doubled cross term as a second accumulating IMAD.WIDE (FMA pipe) rather than a 64-bit doubling
+// on the ALU pipe (2 ALU instructions fewer per squaring; leaf hashing 8.68 -> 8.59 ms, profiles/r02_poseidon_ab.md)
 GL_D u64 gl_sqr_cc(u64 a) {
     u32 a0 = lo32(a), a1 = hi32(a);
     u32 r0, r1, r2, r3;
@@ -194,8 +176,8 @@ GL_D u64 gl_sqr_cc(u64 a) {
         "mov.b64 {%0, h0}, p0;\n\t"
         "mov.b64 {l1, h1}, p1;\n\t"
         "mov.b64 {l3, h3}, p3;\n\t"
-        "add.cc.u32 m0, l1, l1;\n\t"              // (m2:m1:m0) = 2 * a0*a1
-        "addc.cc.u32 m1, h1, h1;\n\t"
+        "mad.lo.cc.u32 m0, %4, %5, l1;\n\t"       // (m2:m1:m0) = 2 * a0*a1
+        "madc.hi.cc.u32 m1, %4, %5, h1;\n\t"
         "addc.u32 m2, 0, 0;\n\t"
         "add.cc.u32 %1, h0, m0;\n\t"
         "addc.cc.u32 %2, l3, m1;\n\t"
@@ -211,60 +193,6 @@ GL_D u64 gl_pow7_cc(u64 x) {
     u64 x4 = gl_sqr_cc(x2);
     u64 x3 = gl_mul_cc(x2, x);
     return gl_mul_cc(x3, x4);
-}
-
-// ---- "z" forms: every IMAD.WIDE takes a zero-extended 32-bit addend (cannot overflow: (2^32-1)^2 + 2^32-1 < 2^64), so
-// no product carries out and no carry is ever materialised; the price is a dependent chain p0 -> t -> (u, v).
-// 64 x 64 -> 128: 4 IMAD.WIDE + one 64-bit add (A/B against gl_mul128_cc: 4 IMAD.WIDE, one with carry-out, + 4 carry ops)
-GL_D void gl_mul128_z(u64 a, u64 b, u32& r0, u32& r1, u32& r2, u32& r3) {
-    u32 a0 = lo32(a), a1 = hi32(a), b0 = lo32(b), b1 = hi32(b);
-    u64 p0 = mul_wide(a0, b0);
-    u64 t = mad_wide(a0, b1, (u64)hi32(p0));
-    u64 u = mad_wide(a1, b0, (u64)lo32(t));
-    u64 v = mad_wide(a1, b1, (u64)hi32(t));
-    asm("{\n\t"
-        "add.cc.u32 %0, %2, %4;\n\t"
-        "addc.u32 %1, %3, 0;\n\t"
-        "}"
-        : "=r"(r2), "=r"(r3)
-        : "r"(lo32(v)), "r"(hi32(v)), "r"(hi32(u)));
-    r0 = lo32(p0);
-    r1 = lo32(u);
-}
-GL_D u64 gl_mul_z(u64 a, u64 b) {
-    u32 r0, r1, r2, r3;
-    gl_mul128_z(a, b, r0, r1, r2, r3);
-    return gl_reduce128_cc(r0, r1, r2, r3);
-}
-// a * b + c: the addend's halves ride in the first product and in the final carry chain
-GL_D u64 gl_mul_add_z(u64 a, u64 b, u64 c) {
-    u32 a0 = lo32(a), a1 = hi32(a), b0 = lo32(b), b1 = hi32(b);
-    u64 p0 = mad_wide(a0, b0, (u64)lo32(c));
-    u64 t = mad_wide(a0, b1, (u64)hi32(p0));
-    u64 u = mad_wide(a1, b0, (u64)lo32(t));
-    u64 v = mad_wide(a1, b1, (u64)hi32(t));
-    u32 r1, r2, r3;
-    asm("{\n\t"
-        "add.cc.u32 %0, %3, %4;\n\t"
-        "addc.cc.u32 %1, %5, %6;\n\t"
-        "addc.u32 %2, %7, 0;\n\t"
-        "}"
-        : "=r"(r1), "=&r"(r2), "=&r"(r3)
-        : "r"(lo32(u)), "r"(hi32(c)), "r"(lo32(v)), "r"(hi32(u)), "r"(hi32(v)));
-    return gl_reduce128_cc(lo32(p0), r1, r2, r3);
-}
-// S-box variants: SB = 0 the shipped form; 1 = z-form multiplications, carry-chain squarings; 2 = z-form everywhere
-template <int SB>
-GL_D u64 gl_pow7_v(u64 x) {
-    if (SB == 0) return gl_pow7_cc(x);
-    u64 x2 = SB == 2 ? gl_mul_z(x, x) : gl_sqr_cc(x);
-    u64 x4 = SB == 2 ? gl_mul_z(x2, x2) : gl_sqr_cc(x2);
-    u64 x3 = gl_mul_z(x2, x);
-    return gl_mul_z(x3, x4);
-}
-template <int SB>
-GL_D u64 gl_mul_add_v(u64 a, u64 b, u64 c) {
-    return SB ? gl_mul_add_z(a, b, c) : gl_mul_add_cc(a, b, c);
 }
 
 // a + b and a - b for ANY u64 representatives, as pure carry chains (8 ALU instructions, no compare / select):
@@ -330,26 +258,6 @@ GL_D void gl_acc_mad(GlAcc& t, u64 a, u64 b) {
         "}"
         : "+r"(t.l0), "+r"(t.h0), "+r"(t.c0), "+r"(t.l1), "+r"(t.h1), "+r"(t.c1), "+r"(t.l2), "+r"(t.h2), "+r"(t.c2)
         : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
-}
-// Same term with the four products issued as addend-free IMAD.WIDE and the accumulation done by 3-instruction carry
-// chains on the ALU pipe (tools/intpeak2.cu: 5.0 SMSP cycles per partial product against 6.8 for the accumulating
-// IMAD.WIDE with carry-out) -- A/B variant, selected per kernel.
-GL_D void gl_acc_mad_alu(GlAcc& t, u64 a, u64 b) {
-    u32 a0 = lo32(a), a1 = hi32(a), b0 = lo32(b), b1 = hi32(b);
-    u64 p00 = mul_wide(a0, b0), p01 = mul_wide(a0, b1), p10 = mul_wide(a1, b0), p11 = mul_wide(a1, b1);
-    asm("{\n\t"
-        "add.cc.u32 %0, %0, %9;\n\t"   "addc.cc.u32 %1, %1, %10;\n\t"  "addc.u32 %2, %2, 0;\n\t"
-        "add.cc.u32 %3, %3, %11;\n\t"  "addc.cc.u32 %4, %4, %12;\n\t"  "addc.u32 %5, %5, 0;\n\t"
-        "add.cc.u32 %3, %3, %13;\n\t"  "addc.cc.u32 %4, %4, %14;\n\t"  "addc.u32 %5, %5, 0;\n\t"
-        "add.cc.u32 %6, %6, %15;\n\t"  "addc.cc.u32 %7, %7, %16;\n\t"  "addc.u32 %8, %8, 0;\n\t"
-        "}"
-        : "+r"(t.l0), "+r"(t.h0), "+r"(t.c0), "+r"(t.l1), "+r"(t.h1), "+r"(t.c1), "+r"(t.l2), "+r"(t.h2), "+r"(t.c2)
-        : "r"(lo32(p00)), "r"(hi32(p00)), "r"(lo32(p01)), "r"(hi32(p01)), "r"(lo32(p10)), "r"(hi32(p10)),
-          "r"(lo32(p11)), "r"(hi32(p11)));
-}
-template <int ALU>
-GL_D void gl_acc_mad_v(GlAcc& t, u64 a, u64 b) {
-    if (ALU) gl_acc_mad_alu(t, a, b); else gl_acc_mad(t, a, b);
 }
 // small-constant term: a * k, k < 2^32
 GL_D void gl_acc_mad_small(GlAcc& t, u64 a, u32 k) {

@@ -66,9 +66,7 @@ void poseidon_round_constants_host(u64 out[360]) {
     }
 }
 
-static __device__ u64 g_pos_rc[31 * 12];
-static __constant__ unsigned c_leaf_stagger;  // A/B: start delay (cycles) of every second resident block, 0 = off
-static __constant__ unsigned c_leaf_sms = 148;      // global-memory copy of c_pos.rc for kernels that index it per lane
+static __device__ u64 g_pos_rc[31 * 12];      // global-memory copy of c_pos.rc for kernels that index it per lane
 
 int32_t poseidon_module_init(vx_ctx* ctx) {
     u64 rc[360];
@@ -77,18 +75,6 @@ int32_t poseidon_module_init(vx_ctx* ctx) {
     if (!poseidon_derive_tables(rc, &t)) { vx_set_error("poseidon: table derivation failed"); return VX_ECUDA; }
     VX_CUDA(poseidon_upload_constants(t, ctx->stream));
     VX_CUDA(cudaMemcpyToSymbolAsync(g_pos_rc, t.rc, sizeof t.rc, 0, cudaMemcpyHostToDevice, ctx->stream));
-    unsigned stagger = 0, sms = (unsigned)ctx->sm_count;
-    if (const char* v = getenv("VX_LEAF_STAGGER")) stagger = (unsigned)atoi(v);
-    VX_CUDA(cudaMemcpyToSymbolAsync(c_leaf_stagger, &stagger, sizeof stagger, 0, cudaMemcpyHostToDevice, ctx->stream));
-    VX_CUDA(cudaMemcpyToSymbolAsync(c_leaf_sms, &sms, sizeof sms, 0, cudaMemcpyHostToDevice, ctx->stream));
-    int naive = 0;                                           // A/B: hybrid partial rounds of leaf-hash variant 8
-    if (const char* v = getenv("VX_POSEIDON_NAIVE_ROUNDS")) naive = atoi(v);
-    if (naive < 0 || naive > 22) naive = 0;
-    PoseidonTables tk;
-    if (naive < 22 && !poseidon_derive_tables_hybrid(rc, naive, &tk)) { vx_set_error("poseidon: table derivation failed"); return VX_ECUDA; }
-    if (naive == 22) tk = t;
-    VX_CUDA(cudaMemcpyToSymbolAsync(c_posk, &tk, sizeof tk, 0, cudaMemcpyHostToDevice, ctx->stream));
-    VX_CUDA(cudaMemcpyToSymbolAsync(c_posk_naive, &naive, sizeof naive, 0, cudaMemcpyHostToDevice, ctx->stream));
     VX_CUDA(cudaStreamSynchronize(ctx->stream));
     return VX_OK;
 }
@@ -103,58 +89,36 @@ GL_D void store_digest(u64* dst, const u64 s[12]) {
     reinterpret_cast<ulonglong2*>(dst)[1] = b;
 }
 
-// one thread per leaf: hash_or_noop(leaf) -> interleaved slot (or cap when the subtree is 1 leaf)
-// V = 0: state in registers, frequency-domain MDS.  V = 1: state in shared memory, rolled lane loops.
-// V = 2: state in registers, IMAD.WIDE MDS (the round-1a kernel, kept for A/B runs).  V = 3: V 0 with ALU-side accumulation.
-template <bool COL_MAJOR, int V, int MINB>
-__global__ void __launch_bounds__(POSEIDON_BLOCK, MINB) leaf_hash_kernel(const u64* __restrict__ leaves, uint64_t stride,
-                                                        uint64_t N, uint32_t c, uint32_t sub_bits,
-                                                        u64* __restrict__ digests, u64* __restrict__ cap) {
-    __shared__ u64 scratch[12 * POSEIDON_BLOCK];
+// one thread per leaf: hash_or_noop(leaf) -> interleaved slot (or cap when the subtree is 1 leaf); state in registers.
+// LONG: the form for wide leaves on a full GPU -- 256-thread blocks, partial rounds in groups of 4, one barrier per
+// permutation to keep the warps of a block in the same code region (see POSEIDON_GROUP).
+template <bool COL_MAJOR, bool LONG>
+__global__ void __launch_bounds__(LONG ? POSEIDON_BLOCK_LONG : POSEIDON_BLOCK, 1024 / (LONG ? POSEIDON_BLOCK_LONG : POSEIDON_BLOCK))
+leaf_hash_kernel(const u64* __restrict__ leaves, uint64_t stride, uint64_t N, uint32_t c, uint32_t sub_bits,
+                 u64* __restrict__ digests, u64* __restrict__ cap) {
+    constexpr int BLOCK = LONG ? POSEIDON_BLOCK_LONG : POSEIDON_BLOCK;
+    __shared__ u64 scratch[12 * BLOCK];
     uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= N) return;
-    if (c_leaf_stagger) {
-        // A/B (VX_LEAF_STAGGER=cycles): every second resident block of an SM starts late, so that the warps sharing a
-        // sub-partition are not all in the ALU-only MDS layer (or all in the multiplier-heavy S-box layer) together
-        if ((blockIdx.x / c_leaf_sms) & 1) {
-            const long long t0 = clock64();
-            while (clock64() - t0 < (long long)c_leaf_stagger) {}
-        }
-    }
     const u64* src = COL_MAJOR ? leaves + row : leaves + row * c;
     const uint64_t step = COL_MAJOR ? stride : 1;
-    u64* st = scratch + threadIdx.x;
     u64 s[12];
-    if (V != 1) {
 #pragma unroll
-        for (int i = 0; i < 12; i++) s[i] = 0;
-    } else {
-#pragma unroll
-        for (int i = 0; i < 12; i++) PS(i) = 0;
-    }
+    for (int i = 0; i < 12; i++) s[i] = 0;
     if (c <= 4) {                         // hash_or_noop: identity, zero padded
 #pragma unroll
         for (int i = 0; i < 4; i++) s[i] = ((uint32_t)i < c) ? src[i * step] : 0;
     } else {
         for (uint32_t off = 0; off < c; off += POSEIDON_RATE) {
-            if (V != 1) {
 #pragma unroll
-                for (int i = 0; i < POSEIDON_RATE; i++)
-                    if (off + i < c) s[i] = src[(uint64_t)(off + i) * step];   // overwrite-mode absorb
-                if (V == 4) poseidon_permute_hybrid(s, st);
-                else if (V == 5) poseidon_permute<0, 1>(s, st);
-                else if (V == 6) poseidon_permute<0, 2>(s, st);
-                else poseidon_permute<V == 2 ? 1 : (V == 3 ? 2 : 0)>(s, st);
+            for (int i = 0; i < POSEIDON_RATE; i++)
+                if (off + i < c) s[i] = src[(uint64_t)(off + i) * step];   // overwrite-mode absorb
+            if (LONG) {
+                __syncthreads();          // exited threads (row >= N) do not take part
+                poseidon_permute<POSEIDON_GROUP_LONG, BLOCK>(s, scratch + threadIdx.x);
             } else {
-#pragma unroll
-                for (int i = 0; i < POSEIDON_RATE; i++)
-                    if (off + i < c) PS(i) = src[(uint64_t)(off + i) * step];
-                poseidon_s_permute(st);
+                poseidon_permute(s, scratch + threadIdx.x);
             }
-        }
-        if (V == 1) {
-#pragma unroll
-            for (int i = 0; i < 4; i++) s[i] = PS(i);
         }
     }
     u64* dst;
@@ -172,7 +136,7 @@ __global__ void __launch_bounds__(POSEIDON_BLOCK, MINB) leaf_hash_kernel(const u
 // columns are already transformed): absorb columns [col0, col1) of every leaf into the sponge state kept in `state`
 // (12 x N, lane-major so that a warp's accesses are contiguous).  col0 and every col1 < c are multiples of the rate, so a
 // chunk boundary is a permutation boundary of hash_no_pad; the launch with col1 == c writes the digests.
-__global__ void __launch_bounds__(POSEIDON_BLOCK, 8) leaf_absorb_kernel(const u64* __restrict__ lde, uint64_t stride, uint64_t N,
+__global__ void __launch_bounds__(POSEIDON_BLOCK, 1024 / POSEIDON_BLOCK) leaf_absorb_kernel(const u64* __restrict__ lde, uint64_t stride, uint64_t N,
                                                                         uint32_t c, uint32_t col0, uint32_t col1,
                                                                         u64* __restrict__ state, uint32_t sub_bits,
                                                                         u64* __restrict__ digests, u64* __restrict__ cap) {
@@ -187,7 +151,7 @@ __global__ void __launch_bounds__(POSEIDON_BLOCK, 8) leaf_absorb_kernel(const u6
 #pragma unroll
         for (int i = 0; i < POSEIDON_RATE; i++)
             if (off + i < col1) s[i] = src[(uint64_t)(off + i) * stride];
-        poseidon_permute<0>(s, scratch + threadIdx.x);
+        poseidon_permute(s, scratch + threadIdx.x);
     }
     if (col1 < c) {
 #pragma unroll
@@ -230,7 +194,7 @@ __global__ void __launch_bounds__(POSEIDON_BLOCK) level_hash_kernel(u64* __restr
 // permutation per level (~44 us with one thread per permutation).  Here 16 lanes cooperate on one two_to_one: lane i
 // (< 12) owns state element i, the S-box layer runs in parallel and the MDS layer gathers the 12 elements with warp
 // shuffles (spec round structure: add constants, x^7, MDS; partial rounds apply x^7 on lane 0 only).  ~5x lower latency,
-// ~3x more thread-instructions: used only while a level has at most VX_COOP_MAX_PAIRS pairs.
+// ~3x more thread-instructions: used (inside level_hash_fused_kernel) only while a level has at most VX_COOP_MAX_PAIRS pairs.
 #define VX_COOP_MAX_PAIRS 4096
 
 // The cooperative permutation: lane (of a 16-lane group) el < 12 holds state element el; returns the permuted element.
@@ -270,26 +234,6 @@ GL_D u64 poseidon_coop_permute(u64 s, const uint32_t lane, const uint32_t el, co
         s = gl_reduce96(l, hi32(ah) + c);
     }
     return s;
-}
-
-__global__ void __launch_bounds__(256) level_hash_coop_kernel(u64* __restrict__ digests, u64* __restrict__ cap, uint32_t lvl,
-                                                              uint32_t sub_bits, uint64_t total_pairs) {
-    const uint32_t lane = threadIdx.x & 15;
-    const uint64_t t_raw = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
-    const bool live = t_raw < total_pairs;
-    const uint64_t t = live ? t_raw : total_pairs - 1;               // idle groups redo the last pair (no store)
-    const uint32_t pair_bits = sub_bits - lvl - 1;
-    const uint64_t sidx = t >> pair_bits, q = t & ((1ULL << pair_bits) - 1);
-    const uint64_t sub = 1ULL << sub_bits;
-    u64* blk = digests + 4 * sidx * (2 * sub - 2);
-    const u64* src = blk + 4 * pair_pos(q, lvl);
-    const uint32_t el = lane < 12 ? lane : 0;                        // lanes 12..15 shadow lane 0 (results unused)
-    u64 s = lane < 8 ? src[lane] : 0;
-    s = poseidon_coop_permute(s, lane, el, c_pos.rc);
-    if (live && lane < 4) {
-        u64* dst = (pair_bits == 0) ? cap + 4 * sidx : blk + 4 * (pair_pos(q >> 1, lvl + 1) + (q & 1));
-        dst[lane] = gl_canon(s);
-    }
 }
 
 // Several small levels in ONE launch: a CTA owns 2^(nl-1) consecutive sibling pairs of layer lvl0 (all inside one cap
@@ -334,6 +278,19 @@ __global__ void __launch_bounds__(1024) level_hash_fused_kernel(u64* __restrict_
     }
 }
 
+// Launch shape of the leaf kernels.  Few leaves (a shard of a sharded commit, the small oracles): 64- or 32-thread blocks
+// spread the warps evenly over the SMs (512 blocks of 128 on 148 SMs leave some SMs with 16 warps and others with 12).
+// Capping the residency at 28 or 24 warps per SM so that 2^19 leaves become 3.95 whole waves instead of 3.46 was measured
+// and does not pay (8.13 / 8.15 / 8.18 ms at 32 / 28 / 24 warps, profiles/r02_poseidon_ab.md).
+struct LeafPlan { unsigned threads, blocks; };
+static LeafPlan leaf_plan(vx_ctx* ctx, uint64_t N) {
+    LeafPlan p;
+    p.threads = POSEIDON_BLOCK;
+    while (p.threads > 32 && (N + p.threads - 1) / p.threads < 8ULL * (uint64_t)ctx->sm_count) p.threads >>= 1;
+    p.blocks = (unsigned)((N + p.threads - 1) / p.threads);
+    return p;
+}
+
 int32_t merkle_build_device(vx_ctx* ctx, const u64* leaves, bool col_major, uint64_t stride, uint64_t N,
                             uint32_t c, uint32_t cap_height, u64* digests, u64* cap, cudaEvent_t after_leaves) {
     uint32_t log_N = ilog2(N);
@@ -341,31 +298,17 @@ int32_t merkle_build_device(vx_ctx* ctx, const u64* leaves, bool col_major, uint
     VX_REQUIRE(cap_height <= log_N, "merkle: cap_height %u > log2(leaves) %u", cap_height, log_N);
     VX_REQUIRE(c >= 1, "merkle: empty leaves");
     uint32_t sub_bits = log_N - cap_height;
-    // few leaves (a shard of a sharded commit, the small oracles): 64- or 32-thread blocks spread the warps evenly over
-    // the SMs (512 blocks of 128 on 148 SMs leave some SMs with 16 warps and others with 12)
-    unsigned threads = POSEIDON_BLOCK;
-    while (threads > 32 && (N + threads - 1) / threads < 8ULL * (uint64_t)ctx->sm_count) threads >>= 1;
-    unsigned blocks = (unsigned)((N + threads - 1) / threads);
-    const int pv = ctx->poseidon_variant;
-#define LEAF(CM, V, MB) leaf_hash_kernel<CM, V, MB><<<blocks, threads, 0, ctx->stream>>>(leaves, stride, N, c, sub_bits, digests, cap)
-    if (col_major) {
-        switch (pv) {
-            case 1: LEAF(true, 1, 4); break;      // state in shared memory, rolled lane loops
-            case 2: LEAF(true, 2, 8); break;      // round-1a kernel: IMAD.WIDE MDS layer
-            case 3: LEAF(true, 0, 4); break;      // up to 128 registers
-            case 4: LEAF(true, 0, 6); break;      // up to 80 registers
-            case 5: LEAF(true, 0, 10); break;     // 48 registers, 10 blocks per SM
-            case 6: LEAF(true, 0, 9); break;      // 56 registers, 9 blocks per SM
-            case 7: LEAF(true, 3, 8); break;      // lazy dot products accumulated on the ALU pipe
-            case 9: LEAF(true, 5, 8); break;      // z-form multiplications in the S-box and the partial-round axpy
-            case 10: LEAF(true, 6, 8); break;     // z-form multiplications and squarings
-            case 8: LEAF(true, 4, 8); break;      // hybrid partial rounds (VX_POSEIDON_NAIVE_ROUNDS spec-form rounds first)
-            default: LEAF(true, 0, 8); break;     // state in registers, 64 registers / 8 blocks per SM
-        }
-    } else {
-        if (pv % 10 == 1) LEAF(false, 1, 4); else LEAF(false, 0, 4);
-    }
-#undef LEAF
+    const LeafPlan lp = leaf_plan(ctx, N);
+    // the long form needs full 256-thread blocks on every SM and enough permutations per leaf to amortise its cold start
+    const bool long_form = col_major && c >= 64 && lp.threads == POSEIDON_BLOCK &&
+                           N / POSEIDON_BLOCK_LONG >= 8ULL * (uint64_t)ctx->sm_count;
+    if (long_form)
+        leaf_hash_kernel<true, true><<<(unsigned)(N / POSEIDON_BLOCK_LONG), POSEIDON_BLOCK_LONG, 0, ctx->stream>>>(
+            leaves, stride, N, c, sub_bits, digests, cap);
+    else if (col_major)
+        leaf_hash_kernel<true, false><<<lp.blocks, lp.threads, 0, ctx->stream>>>(leaves, stride, N, c, sub_bits, digests, cap);
+    else
+        leaf_hash_kernel<false, false><<<lp.blocks, lp.threads, 0, ctx->stream>>>(leaves, stride, N, c, sub_bits, digests, cap);
     VX_LAUNCH_COUNT(ctx, 1);
     if (after_leaves) VX_CUDA(cudaEventRecord(after_leaves, ctx->stream));
     return merkle_levels_device(ctx, N, cap_height, digests, cap);
@@ -377,11 +320,10 @@ int32_t merkle_absorb_device(vx_ctx* ctx, const u64* lde, uint64_t stride, uint6
     VX_REQUIRE((1ULL << log_N) == N && cap_height <= log_N, "merkle: bad leaf count / cap height");
     VX_REQUIRE(c > 4 && col0 < col1 && col1 <= c && col0 % POSEIDON_RATE == 0 && (col1 == c || col1 % POSEIDON_RATE == 0),
                "merkle: column chunk [%u, %u) of %u is not aligned to the sponge rate", col0, col1, c);
-    unsigned threads = POSEIDON_BLOCK;
-    while (threads > 32 && (N + threads - 1) / threads < 8ULL * (uint64_t)ctx->sm_count) threads >>= 1;
+    const LeafPlan lp = leaf_plan(ctx, N);
     const int slot = ctx->absorb_count < vx_ctx::VX_MAX_ABSORB ? ctx->absorb_count++ : -1;
     if (slot >= 0) VX_CUDA(cudaEventRecord(ctx->absorb_ev[2 * slot], ctx->stream));
-    leaf_absorb_kernel<<<(unsigned)((N + threads - 1) / threads), threads, 0, ctx->stream>>>(
+    leaf_absorb_kernel<<<lp.blocks, lp.threads, 0, ctx->stream>>>(
         lde, stride, N, c, col0, col1, state, log_N - cap_height, digests, cap);
     if (slot >= 0) VX_CUDA(cudaEventRecord(ctx->absorb_ev[2 * slot + 1], ctx->stream));
     VX_LAUNCH_COUNT(ctx, 1);
@@ -394,7 +336,7 @@ int32_t merkle_levels_device(vx_ctx* ctx, uint64_t N, uint32_t cap_height, u64* 
     const uint32_t sub_bits = ilog2(N) - cap_height;
     for (uint32_t lvl = 0; lvl < sub_bits;) {
         uint64_t total_pairs = N >> (lvl + 1);
-        if (total_pairs <= (uint64_t)ctx->coop_max_pairs && !ctx->ntt_legacy && ctx->tree_fuse) {
+        if (total_pairs <= VX_COOP_MAX_PAIRS) {
             // wide layers: short runs (many CTAs, spread over the SMs); the narrow top: one long run per subtree group
             uint32_t nl = sub_bits - lvl;
             const uint32_t cap_nl = total_pairs > 256 ? 5 : VX_FUSE_MAX_LEVELS;
@@ -403,10 +345,6 @@ int32_t merkle_levels_device(vx_ctx* ctx, uint64_t N, uint32_t cap_height, u64* 
             unsigned threads = p0 * 16 < 32 ? 32 : p0 * 16;
             level_hash_fused_kernel<<<(unsigned)(total_pairs / p0), threads, 0, ctx->stream>>>(digests, cap, lvl, nl, sub_bits);
             lvl += nl;
-        } else if (total_pairs <= (uint64_t)ctx->coop_max_pairs && !ctx->ntt_legacy) {
-            unsigned b = (unsigned)((total_pairs * 16 + 255) / 256);
-            level_hash_coop_kernel<<<b, 256, 0, ctx->stream>>>(digests, cap, lvl, sub_bits, total_pairs);
-            lvl++;
         } else {
             unsigned b = (unsigned)((total_pairs + 127) / 128);
             level_hash_kernel<<<b, 128, 0, ctx->stream>>>(digests, cap, lvl, sub_bits, total_pairs);

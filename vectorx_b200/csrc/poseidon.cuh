@@ -19,7 +19,9 @@
 #define POSEIDON_RATE 8
 #define POSEIDON_ROUNDS 30
 #define POSEIDON_PARTIAL_ROUNDS 22
-#define POSEIDON_BLOCK 128          // threads per block of every hashing kernel (shared scratch is sized for it)
+#ifndef POSEIDON_BLOCK
+#define POSEIDON_BLOCK 128
+#endif                              // threads per block of every hashing kernel (shared scratch is sized for it)
 
 #include "poseidon_tables.h"
 
@@ -31,35 +33,6 @@ static inline cudaError_t poseidon_upload_constants(const PoseidonTables& t, cud
     cudaError_t e = cudaMemcpyToSymbolAsync(c_pos, &t, sizeof t, 0, cudaMemcpyHostToDevice, stream);
     if (e != cudaSuccess) return e;
     return cudaStreamSynchronize(stream);
-}
-
-// out = MDS * s + add   (add = 12 canonical constants, warp-uniform pointer into constant memory)
-GL_D void poseidon_mds_add(u64 s[12], const u64* __restrict__ add) {
-    constexpr u32 C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
-    u32 lo[12], hi[12];
-#pragma unroll
-    for (int i = 0; i < 12; i++) {
-        lo[i] = lo32(s[i]);
-        hi[i] = hi32(s[i]);
-    }
-#pragma unroll
-    for (int r = 0; r < 12; r++) {
-        u64 k = add[r];
-        u64 al = (u64)lo32(k), ah = (u64)hi32(k);
-#pragma unroll
-        for (int i = 0; i < 12; i++) {
-            al = mad_wide(lo[(i + r) % 12], C[i], al);
-            ah = mad_wide(hi[(i + r) % 12], C[i], ah);
-        }
-        if (r == 0) {
-            al = mad_wide(lo[0], 8u, al);
-            ah = mad_wide(hi[0], 8u, ah);
-        }
-        // value = al + ah * 2^32, al, ah < 2^42
-        u64 l = al + ((u64)lo32(ah) << 32);
-        u32 c = l < al;
-        s[r] = gl_reduce96(l, hi32(ah) + c);
-    }
 }
 
 // ---- frequency-domain MDS layer --------------------------------------------------------------------------------
@@ -124,7 +97,7 @@ GL_D void poseidon_mds_add_freq(u64 s[12], const u32* __restrict__ kl) {
 // s <- D * s + e with D a dense matrix of full-width constants (the MDS layer of full round 3 merged
 // with the partial rounds' initial matrix).  Rows are produced in a rolled loop (small code) and
 // staged through this thread's shared-memory column: scratch[j * POSEIDON_BLOCK].
-template <int ALU = 0>
+template <int STRIDE = POSEIDON_BLOCK>
 GL_D void poseidon_dense_layer(u64 s[12], u64* __restrict__ scratch, const u64* __restrict__ dense_d = c_pos.dense_d,
                                const u64* __restrict__ dense_e = c_pos.dense_e) {
 #pragma unroll 1
@@ -133,39 +106,63 @@ GL_D void poseidon_dense_layer(u64 s[12], u64* __restrict__ scratch, const u64* 
         GlAcc acc;
         gl_acc_init(acc, dense_e[j]);
 #pragma unroll
-        for (int i = 0; i < 12; i++) gl_acc_mad_v<ALU>(acc, row[i], s[i]);
-        scratch[j * POSEIDON_BLOCK] = gl_acc_reduce(acc);
+        for (int i = 0; i < 12; i++) gl_acc_mad(acc, row[i], s[i]);
+        scratch[j * STRIDE] = gl_acc_reduce(acc);
     }
 #pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = scratch[i * POSEIDON_BLOCK];
+    for (int i = 0; i < 12; i++) s[i] = scratch[i * STRIDE];
 }
 
-// 22 partial rounds in the sparse form (see poseidon_tables.h)
-template <int ALU = 0, int SB = 0>
-GL_D void poseidon_partial_rounds(u64 s[12], const int rounds = POSEIDON_PARTIAL_ROUNDS, const u64* __restrict__ pk = c_pos.pk,
-                                  const u64* __restrict__ pv = c_pos.pv, const u64* __restrict__ pw = c_pos.pw) {
-#pragma unroll 1
-    for (int r = 0; r < rounds; r++) {
-        const u64* v = pv + 11 * r;
-        const u64* w = pw + 11 * r;
-        u64 x0 = gl_add_canon(gl_pow7_v<SB>(s[0]), pk[r]);
-        // d = 25 * x0 + sum_i v_i s_i   (25 = MDS[0][0])
+// 22 partial rounds in the sparse form (see poseidon_tables.h), one round at a time (G = 1 of the grouped form below)
+// The 22 partial rounds in groups of G: lanes 1..11 enter only linearly, so inside a group every first-row dot product is taken
+// against the group's INITIAL lanes plus the cross terms pc[r][q] x_q of the S-box outputs already produced, and the lanes
+// are brought up to date once per group, s_i += sum_q w[q][i] x_q -- a lazy dot product with ONE reduction per lane and group
+// instead of one reduced multiply-add per lane and round.
+template <int G>
+GL_D void poseidon_partial_group(u64 s[12], const int r0, const u64* __restrict__ pk, const u64* __restrict__ pv,
+                                 const u64* __restrict__ pw, const u64* __restrict__ pc) {
+    u64 x[G];
+#pragma unroll
+    for (int j = 0; j < G; j++) {
+        const int r = r0 + j;
+        x[j] = gl_add_canon(gl_pow7_cc(s[0]), pk[r]);
         GlAcc d;
         gl_acc_init(d, 0);
-        gl_acc_mad_small(d, x0, 25u);
+        gl_acc_mad_small(d, x[j], 25u);
 #pragma unroll
-        for (int i = 1; i < 12; i++) gl_acc_mad_v<ALU>(d, v[i - 1], s[i]);
+        for (int i = 1; i < 12; i++) gl_acc_mad(d, pv[11 * r + i - 1], s[i]);
 #pragma unroll
-        for (int i = 1; i < 12; i++) s[i] = gl_mul_add_v<SB>(w[i - 1], x0, s[i]);
+        for (int q = 0; q < j; q++) gl_acc_mad(d, pc[22 * r + r0 + q], x[q]);
         s[0] = gl_acc_reduce(d);
     }
+#pragma unroll
+    for (int i = 1; i < 12; i++) {
+        GlAcc u;
+        gl_acc_init(u, s[i]);
+#pragma unroll
+        for (int j = 0; j < G; j++) gl_acc_mad(u, pw[11 * (r0 + j) + i - 1], x[j]);
+        s[i] = gl_acc_reduce(u);
+    }
+}
+template <int G>
+GL_D void poseidon_partial_rounds_grouped(u64 s[12]) {
+    constexpr int FULL = POSEIDON_PARTIAL_ROUNDS / G, TAIL = POSEIDON_PARTIAL_ROUNDS % G;
+#pragma unroll 1
+    for (int g = 0; g < FULL; g++) poseidon_partial_group<G>(s, g * G, c_pos.pk, c_pos.pv, c_pos.pw, c_pos.pc);
+    if constexpr (TAIL > 0) poseidon_partial_group<TAIL>(s, FULL * G, c_pos.pk, c_pos.pv, c_pos.pw, c_pos.pc);
 }
 
-// scratch: this thread's column of a POSEIDON_BLOCK-wide shared array of 12 rows
-// MV = 0: frequency-domain MDS layer (shifts/adds on 22-bit limb planes); MV = 1: IMAD.WIDE MDS on 32-bit halves (A/B);
-// MV = 2: MV 0 with the lazy dot products accumulated on the ALU pipe (gl_acc_mad_alu, A/B)
-// SB: S-box / multiply-add form (gl_pow7_v): 0 = carry-chain products (shipped), 1 / 2 = zero-extended-addend products (A/B)
-template <int MV = 0, int SB = 0>
+// Rounds per group of the partial rounds (profiles/r02_poseidon_ab.md).  Larger groups execute fewer instructions, but their
+// unrolled bodies have to share the 32 KB instruction cache with the full-round body: with the warps of an SM drifting
+// through different regions G = 1 / 2 / 4 / 6 / 11 hash the config-1 leaves in 8.68 / 8.13 / 9.23 / 10.85 / 10.17 ms.  G = 2 is
+// the default; the long leaf sponge uses G = 4 in 256-thread blocks that re-align their warps with one barrier per
+// permutation (7.99 ms) -- short kernels (one or two permutations per thread) run the big body with a cold cache and lose.
+#define POSEIDON_GROUP 2
+#define POSEIDON_GROUP_LONG 4
+#define POSEIDON_BLOCK_LONG 256
+
+// scratch: this thread's column of a STRIDE-wide shared array of 12 rows
+template <int G = POSEIDON_GROUP, int STRIDE = POSEIDON_BLOCK>
 GL_D void poseidon_permute(u64 s[12], u64* __restrict__ scratch) {
     const u64* rc = c_pos.rc;
 #pragma unroll
@@ -176,166 +173,14 @@ GL_D void poseidon_permute(u64 s[12], u64* __restrict__ scratch) {
 #pragma unroll 1
         for (int r = 0; r < 4; r++) {
 #pragma unroll
-            for (int i = 0; i < 12; i++) s[i] = gl_pow7_v<SB>(s[i]);
-            if (half == 0 && r == 3) poseidon_dense_layer<MV == 2>(s, scratch);
-            else if (MV != 1) poseidon_mds_add_freq(s, c_pos.rc22 + 36 * (first + r));
-            else poseidon_mds_add(s, rc + 12 * (first + r));
+            for (int i = 0; i < 12; i++) s[i] = gl_pow7_cc(s[i]);
+            if (half == 0 && r == 3) poseidon_dense_layer<STRIDE>(s, scratch);
+            else poseidon_mds_add_freq(s, c_pos.rc22 + 36 * (first + r));
         }
         if (half == 0) {
-            poseidon_partial_rounds<MV == 2, SB>(s);
+            poseidon_partial_rounds_grouped<G>(s);
 #pragma unroll
             for (int i = 0; i < 12; i++) s[i] = gl_add_canon(s[i], rc[26 * 12 + i]);
-        }
-    }
-}
-
-// Hybrid partial rounds (A/B): the first c_posk_naive partial rounds in the spec form -- x0^7 then the frequency-domain
-// MDS layer, no IMAD.WIDE in the linear part -- and the remaining ones in the sparse form with tables derived for that
-// suffix (c_posk).  naive = 22 drops the dense layer and the sparse rounds altogether.
-static __constant__ PoseidonTables c_posk;
-static __constant__ int c_posk_naive;
-
-GL_D void poseidon_permute_hybrid(u64 s[12], u64* __restrict__ scratch) {
-    const u64* rc = c_pos.rc;
-    const int K = c_posk_naive;
-#pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = gl_add_canon(s[i], rc[i]);
-#pragma unroll 1
-    for (int r = 0; r < 4; r++) {
-#pragma unroll
-        for (int i = 0; i < 12; i++) s[i] = gl_pow7_cc(s[i]);
-        if (r == 3 && K == 0) poseidon_dense_layer<0>(s, scratch, c_posk.dense_d, c_posk.dense_e);
-        else poseidon_mds_add_freq(s, c_pos.rc22 + 36 * (1 + r));
-    }
-#pragma unroll 1
-    for (int j = 0; j < K; j++) {                            // spec-form partial rounds 4 .. 4 + K - 1
-        s[0] = gl_pow7_cc(s[0]);
-        if (j == K - 1 && K < 22) poseidon_dense_layer<0>(s, scratch, c_posk.dense_d, c_posk.dense_e);
-        else poseidon_mds_add_freq(s, c_pos.rc22 + 36 * (5 + j));
-    }
-    if (K < 22) {
-        poseidon_partial_rounds<0>(s, 22 - K, c_posk.pk, c_posk.pv, c_posk.pw);
-#pragma unroll
-        for (int i = 0; i < 12; i++) s[i] = gl_add_canon(s[i], rc[26 * 12 + i]);
-    }
-#pragma unroll 1
-    for (int r = 0; r < 4; r++) {
-#pragma unroll
-        for (int i = 0; i < 12; i++) s[i] = gl_pow7_cc(s[i]);
-        poseidon_mds_add_freq(s, c_pos.rc22 + 36 * (27 + r));
-    }
-}
-
-// =================================================================================================
-// Variant S ("state in shared memory"): the same permutation with every lane loop rolled, so the
-// whole hot code is a few KB and stays in the instruction cache (ncu showed ~30% of warp time in
-// stall_no_instruction for the fully unrolled form), and so that a thread needs few registers.
-// The state of thread t lives in its column of a 12 x POSEIDON_BLOCK shared array: lane i at
-// st[i * POSEIDON_BLOCK].  The MDS layer works on 22-bit limbs with plain 32-bit IMADs
-// (3 limbs x 12 terms; 22 + 9 bits of growth < 2^31) instead of IMAD.WIDE halves.
-// =================================================================================================
-#define PS(i) st[(i) * POSEIDON_BLOCK]
-
-GL_D void poseidon_s_sbox_all(u64* __restrict__ st) {
-#pragma unroll 1
-    for (int i = 0; i < 12; i += 2) {
-        u64 a = PS(i), b = PS(i + 1);
-        a = gl_pow7_cc(a);
-        b = gl_pow7_cc(b);
-        PS(i) = a;
-        PS(i + 1) = b;
-    }
-}
-
-GL_D u32 imad32(u32 a, u32 b, u32 c) { return a * b + c; }
-
-// st <- MDS * st + k,  k given as 22-bit limbs (kl: 12 x 3 u32, warp-uniform constant pointer)
-GL_D void poseidon_s_mds_add(u64* __restrict__ st, const u32* __restrict__ kl) {
-    constexpr u32 C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
-    u32 l0[12], l1[12], l2[12];
-#pragma unroll
-    for (int i = 0; i < 12; i++) {
-        u64 x = PS(i);
-        u32 lo = lo32(x), hi = hi32(x);
-        l0[i] = lo & 0x3fffffu;
-        l1[i] = __funnelshift_r(lo, hi, 22) & 0x3fffffu;
-        l2[i] = hi >> 12;
-    }
-#pragma unroll
-    for (int r = 0; r < 12; r++) {
-        u32 a0 = kl[3 * r], a1 = kl[3 * r + 1], a2 = kl[3 * r + 2];
-#pragma unroll
-        for (int i = 0; i < 12; i++) {
-            a0 = imad32(l0[(i + r) % 12], C[i], a0);
-            a1 = imad32(l1[(i + r) % 12], C[i], a1);
-            a2 = imad32(l2[(i + r) % 12], C[i], a2);
-        }
-        if (r == 0) {
-            a0 = imad32(l0[0], 8u, a0);
-            a1 = imad32(l1[0], 8u, a1);
-            a2 = imad32(l2[0], 8u, a2);
-        }
-        // value = a0 + a1*2^22 + a2*2^44  (< 2^76)
-        u64 t = mad_wide(a1, 1u << 22, (u64)a0);
-        u64 u = mad_wide(a2, 1u << 12, (u64)hi32(t));
-        PS(r) = gl_reduce96(pack64(lo32(t), lo32(u)), hi32(u));
-    }
-}
-
-GL_D void poseidon_s_dense_layer(u64* __restrict__ st) {
-    u64 s[12];
-#pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = PS(i);
-#pragma unroll 1
-    for (int j = 0; j < 12; j++) {
-        const u64* row = c_pos.dense_d + 12 * j;
-        GlAcc acc;
-        gl_acc_init(acc, c_pos.dense_e[j]);
-#pragma unroll
-        for (int i = 0; i < 12; i++) gl_acc_mad(acc, row[i], s[i]);
-        PS(j) = gl_acc_reduce(acc);
-    }
-}
-
-GL_D void poseidon_s_partial_rounds(u64* __restrict__ st) {
-    u64 s0 = PS(0);
-#pragma unroll 1
-    for (int r = 0; r < POSEIDON_PARTIAL_ROUNDS; r++) {
-        const u64* v = c_pos.pv + 11 * r;
-        const u64* w = c_pos.pw + 11 * r;
-        u64 x0 = gl_add_canon(gl_pow7_cc(s0), c_pos.pk[r]);
-        GlAcc d;
-        gl_acc_init(d, 0);
-        gl_acc_mad_small(d, x0, 25u);
-#pragma unroll 1
-        for (int i = 1; i < 12; i++) {
-            u64 si = PS(i);
-            gl_acc_mad(d, v[i - 1], si);
-            PS(i) = gl_mul_add_cc(w[i - 1], x0, si);
-        }
-        s0 = gl_acc_reduce(d);
-    }
-    PS(0) = s0;
-}
-
-// permutes the state held in this thread's shared-memory column
-GL_D void poseidon_s_permute(u64* __restrict__ st) {
-    const u64* rc = c_pos.rc;
-#pragma unroll 1
-    for (int i = 0; i < 12; i++) PS(i) = gl_add_canon(PS(i), rc[i]);
-#pragma unroll 1
-    for (int half = 0; half < 2; half++) {
-        const u32* next = c_pos.rc22 + 36 * (half ? 27 : 1);
-#pragma unroll 1
-        for (int r = 0; r < 4; r++) {
-            poseidon_s_sbox_all(st);
-            if (half == 0 && r == 3) poseidon_s_dense_layer(st);
-            else poseidon_s_mds_add(st, next + 36 * r);
-        }
-        if (half == 0) {
-            poseidon_s_partial_rounds(st);
-#pragma unroll 1
-            for (int i = 0; i < 12; i++) PS(i) = gl_add_canon(PS(i), rc[26 * 12 + i]);
         }
     }
 }

@@ -113,6 +113,12 @@ bool poseidon_derive_tables_hybrid(const unsigned long long rc360[360], int naiv
         for (int i = 0; i < 11; i++)
             for (int j = 0; j < 11; j++) Mp[i + 1][j + 1] = Ah[i][j];
     }
+    for (int r = 0; r < R; r++)
+        for (int q = 0; q < r; q++) {
+            uint64_t acc = 0;
+            for (int i = 0; i < 11; i++) acc = addm(acc, mulm(t->pv[r * 11 + i], t->pw[q * 11 + i]));
+            t->pc[r * 22 + q] = acc;
+        }
     Mat D = matmul(Mp, M);
     std::vector<uint64_t> e = matvec(Mp, first);
     for (int i = 0; i < 12; i++) {

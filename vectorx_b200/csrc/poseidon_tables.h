@@ -22,6 +22,9 @@ struct PoseidonTables {
     unsigned long long pk[22];             // post-S-box lane-0 constants (last is 0)
     unsigned long long pv[22 * 11];        // first-row entries  (d = 25*x0 + sum v_i x_i)
     unsigned long long pw[22 * 11];        // first-column entries (x_i += w_i x0)
+    // grouped partial rounds: pc[r][q] = sum_i v[r][i] w[q][i] for q < r, the weight of round q's S-box output in round
+    // r's first-row dot product when lanes 1..11 are only brought up to date once per group of rounds
+    unsigned long long pc[22 * 22];
 };
 
 // fills t from the 360 round constants; returns false if a matrix was singular (never happens)

@@ -346,9 +346,8 @@ static int32_t shard_commit_run(vx_shard_group* s, vx_batch* b, const u64* value
     // When does the column pipeline pay?  Values in host memory on 2 ranks: the copy of a 68-column slice hides behind the
     // hashing, 6.58 -> 6.25 ms end to end.  On 4 / 8 ranks the slices are short, a rank hashes only N/4 / N/8 leaves per
     // column and the extra launches cost more than the copy they hide (3.64 -> 3.71 ms, 2.55 -> 2.79 ms); values already
-    // in HBM: whole-slice launches are faster (5.92 against 6.05 ms on 2 ranks).  VX_SHARD_STREAM = 0 / 2 forces off / on.
-    const bool want_stream = ctx->shard_stream == 2 ||
-                             (ctx->shard_stream == 1 && s->world <= 2 && !vx_is_device_ptr(values_local));
+    // in HBM: whole-slice launches are faster (5.92 against 6.05 ms on 2 ranks).
+    const bool want_stream = s->world <= 2 && !vx_is_device_ptr(values_local);
     if (want_stream && s->c > 4) return shard_commit_run_stream(s, b, values_local, cap_all_out);
     ctx->absorb_count = 0;
     const uint64_t n = b->n(), N_loc = b->N_loc();
