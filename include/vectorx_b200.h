@@ -34,7 +34,13 @@ extern "C" {
 #define VX_ENODEV (-4)    /* no usable GPU */
 #define VX_EUNSUPPORTED (-5)
 
-typedef struct vx_ctx vx_ctx;       /* per-device context: streams, twiddles, constants, pools */
+/* Per-device context: twiddle / constant tables and a pool of independent stream sets ("lanes").  Threading contract
+ * (callers are arbitrary Rayon worker threads and a tokio block_in_place thread, several STARK proofs in
+ * flight -- P2X/backend/circuit/build.rs:69-75,127, P2X/frontend/hint/synchronous.rs:41): every entry point is
+ * re-entrant and blocking; a call takes a free lane for its duration, so up to 4 calls on one context run concurrently
+ * on the device and further callers queue.  Handles (vx_batch, vx_tree, vx_fri) may be used from any thread, one call at
+ * a time per handle. */
+typedef struct vx_ctx vx_ctx;
 typedef struct vx_batch vx_batch;   /* device-resident PolynomialBatch (coeffs + LDE + Merkle tree) */
 typedef struct vx_tree vx_tree;     /* device-resident MerkleTree over row-major leaves */
 
@@ -44,6 +50,9 @@ int32_t vx_ctx_create(int32_t device, vx_ctx** out);
  * its proof-level fan-out with it: LocalProver::batch_prove, P2X/backend/prover/local.rs:44-48, proves its independent
  * inputs in a sequential loop; with one context per device they run side by side. */
 int32_t vx_device_count(void);
+/* CUDA ordinals of those devices (a box may mix GPU generations, so they need not be 0..count-1): writes up to `capacity`
+ * ordinals and returns how many there are. */
+int32_t vx_device_list(int32_t* ordinals_out, int32_t capacity);
 void vx_ctx_destroy(vx_ctx* ctx);
 const char* vx_last_error(void);
 int32_t vx_device_sync(vx_ctx* ctx);
@@ -91,6 +100,15 @@ int32_t vx_commit_from_values_keep(vx_ctx* ctx, const uint64_t* cols, uint32_t c
                                    uint32_t cap_height, uint64_t* values_dev_out, vx_batch** out);
 int32_t vx_commit_from_coeffs(vx_ctx* ctx, const uint64_t* coeffs, uint32_t c, uint32_t log_n,
                               uint32_t rate_bits, uint32_t cap_height, vx_batch** out);
+/* The same two with the input exactly as plonky2 holds it -- `values: Vec<PolynomialValues<F>>` /
+ * `polynomials: Vec<PolynomialCoeffs<F>>`, i.e. c SEPARATE heap allocations (fri/oracle.rs from_values / from_coeffs,
+ * reached from P2X/backend/circuit/build.rs:69-75): cols[j] points at the n elements of column j.  No flattening on the
+ * host: the columns feed the copy -> iNTT -> LDE -> leaf-sponge pipeline chunk by chunk.  The memory may be pageable
+ * (a plain Vec), registered with vx_host_register, pinned, or device memory. */
+int32_t vx_commit_from_values_cols(vx_ctx* ctx, const uint64_t* const* cols, uint32_t c, uint32_t log_n,
+                                   uint32_t rate_bits, uint32_t cap_height, vx_batch** out);
+int32_t vx_commit_from_coeffs_cols(vx_ctx* ctx, const uint64_t* const* coeffs, uint32_t c, uint32_t log_n,
+                                   uint32_t rate_bits, uint32_t cap_height, vx_batch** out);
 /* Multi-GPU sharding of one commit (coset partition): shard s of S (S a power of two,
  * S <= 2^rate_bits, S <= 2^cap_height) holds leaves [s*N/S, (s+1)*N/S) -- whole cosets of the LDE
  * and whole cap subtrees -- computed from ALL c coefficient columns with no further communication.

@@ -3,7 +3,7 @@
 Public surface mirrors plonky2 v0.2.0 (`PolynomialBatch`, `MerkleTree`); everything computes in
 libvectorx_b200.so through the C ABI of include/vectorx_b200.h.  No CPU fallback.
 """
-from ._lib import Context, VxError, default_context, device_count, load, pinned_empty, LIB_PATH  # noqa: F401
+from ._lib import Context, VxError, default_context, device_count, device_list, load, pinned_empty, LIB_PATH  # noqa: F401
 from .plonky2 import (MerkleCap, MerkleProof, MerkleTree, PolynomialBatch, hash_n_to_hash_no_pad,  # noqa: F401
                       merkle_tree_digests, ntt, poseidon, poseidon_round_constants, reverse_bits, POSEIDON_HASH,
                       POSEIDON_BN128_HASH, poseidon_bn128, poseidon_bn128_hash, poseidon_bn128_constants)

@@ -23,6 +23,7 @@ c_u64, c_u32, c_i32 = ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int32
 SIGNATURES = {
     "vx_ctx_create": (c_i32, [c_i32, ctypes.POINTER(vp)]),
     "vx_device_count": (c_i32, []),
+    "vx_device_list": (c_i32, [ctypes.POINTER(c_i32), c_i32]),
     "vx_ctx_destroy": (None, [vp]),
     "vx_last_error": (ctypes.c_char_p, []),
     "vx_device_sync": (c_i32, [vp]),
@@ -48,6 +49,8 @@ SIGNATURES = {
     "vx_shard_group_free": (None, [vp]),
     "vx_commit_from_values": (c_i32, [vp, vp, c_u32, c_u32, c_u32, c_u32, ctypes.POINTER(vp)]),
     "vx_commit_from_coeffs": (c_i32, [vp, vp, c_u32, c_u32, c_u32, c_u32, ctypes.POINTER(vp)]),
+    "vx_commit_from_values_cols": (c_i32, [vp, ctypes.POINTER(vp), c_u32, c_u32, c_u32, c_u32, ctypes.POINTER(vp)]),
+    "vx_commit_from_coeffs_cols": (c_i32, [vp, ctypes.POINTER(vp), c_u32, c_u32, c_u32, c_u32, ctypes.POINTER(vp)]),
     "vx_commit_from_values_keep": (c_i32, [vp, vp, c_u32, c_u32, c_u32, c_u32, vp, ctypes.POINTER(vp)]),
     "vx_batch_free": (None, [vp]),
     "vx_batch_shape": (c_i32, [vp, u32p]),
@@ -176,6 +179,16 @@ class Context:
 def device_count() -> int:
     """sm_100-class devices visible to the library (0 without a GPU)."""
     return int(load().vx_device_count())
+
+
+def device_list() -> list:
+    """CUDA ordinals of the devices a Context can be created on (not necessarily 0..count-1 on a mixed box)."""
+    n = device_count()
+    if n == 0:
+        return []
+    buf = (c_i32 * n)()
+    k = int(load().vx_device_list(buf, n))
+    return [int(buf[i]) for i in range(min(k, n))]
 
 
 _default_ctx = {}

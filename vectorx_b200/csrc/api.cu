@@ -41,6 +41,35 @@ void DevBuf::release() {
 }
 
 // ------------------------------------------------------------------------------------------------ context
+// streams and events of one lane
+static int32_t lane_create_streams(vx_ctx* l) {
+    VX_CUDA(cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking));
+    VX_CUDA(cudaStreamCreateWithFlags(&l->copy_stream, cudaStreamNonBlocking));
+    VX_CUDA(cudaStreamCreateWithFlags(&l->aux_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < VX_NUM_PHASE_EVENTS; i++) VX_CUDA(cudaEventCreate(&l->ev[i]));
+    for (auto& e : l->absorb_ev) VX_CUDA(cudaEventCreate(&e));
+    for (auto& e : l->copy_ev) VX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    VX_CUDA(cudaEventCreateWithFlags(&l->copy_free, cudaEventDisableTiming));
+    return VX_OK;
+}
+static void lane_destroy_streams(vx_ctx* l) {
+    for (cudaStream_t st : {l->stream, l->copy_stream, l->aux_stream})
+        if (st) cudaStreamSynchronize(st);
+    for (int i = 0; i < VX_NUM_PHASE_EVENTS; i++) if (l->ev[i]) cudaEventDestroy(l->ev[i]);
+    for (auto& e : l->copy_ev) if (e) cudaEventDestroy(e);
+    for (auto& e : l->absorb_ev) if (e) cudaEventDestroy(e);
+    if (l->copy_free) cudaEventDestroy(l->copy_free);
+    for (cudaStream_t st : {l->stream, l->copy_stream, l->aux_stream})
+        if (st) cudaStreamDestroy(st);
+}
+
+// the one predicate for "this library can run there": the build holds sm_100a code only
+static bool device_usable(int device) {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { cudaGetLastError(); return false; }
+    return prop.major == 10;
+}
+
 extern "C" int32_t vx_ctx_create(int32_t device, vx_ctx** out) {
     if (!out) { vx_set_error("vx_ctx_create: out is NULL"); return VX_EINVAL; }
     *out = nullptr;
@@ -53,7 +82,7 @@ extern "C" int32_t vx_ctx_create(int32_t device, vx_ctx** out) {
     VX_REQUIRE(device >= 0 && device < ndev, "vx_ctx_create: device %d out of range (0..%d)", device, ndev - 1);
     cudaDeviceProp prop;
     VX_CUDA(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10) {
+    if (!device_usable(device)) {
         vx_set_error("vx_ctx_create: device %d is sm_%d%d; this library is built for sm_100a only", device,
                      prop.major, prop.minor);
         return VX_ENODEV;
@@ -63,25 +92,32 @@ extern "C" int32_t vx_ctx_create(int32_t device, vx_ctx** out) {
     if (!ctx) return VX_ENOMEM;
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
-    cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
-    if (e != cudaSuccess) { delete ctx; vx_set_error("stream create: %s", cudaGetErrorString(e)); return VX_ECUDA; }
+    ctx->root = ctx;
+    ctx->lanes.push_back(ctx);
     // keep freed blocks in the stream-ordered pool: commits allocate GBs per call
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
         uint64_t thresh = UINT64_MAX;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh);
     }
-    for (int i = 0; i < VX_NUM_PHASE_EVENTS; i++) cudaEventCreate(&ctx->ev[i]);
-    cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
-    cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking);
-    for (auto& e : ctx->absorb_ev) cudaEventCreate(&e);
-    for (auto& e : ctx->copy_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&ctx->copy_free, cudaEventDisableTiming);
-    int32_t r = poseidon_module_init(ctx);
+    int32_t r = lane_create_streams(ctx);
+    if (r == VX_OK) r = poseidon_module_init(ctx);
     if (r == VX_OK) r = ntt_module_init(ctx);
     if (r == VX_OK) r = fri_module_init(ctx);
     if (r == VX_OK) r = prover_module_init(ctx);
     if (r == VX_OK) r = bn128_module_init(ctx);
+    // the other lanes: own streams and events, the root's tables (read-only after this point)
+    for (int i = 1; r == VX_OK && i < VX_LANES; i++) {
+        vx_ctx* l = new (std::nothrow) vx_ctx();
+        if (!l) { r = VX_ENOMEM; break; }
+        l->device = device; l->sm_count = ctx->sm_count; l->root = ctx; l->lane_index = i;
+        l->w_lo = ctx->w_lo; l->w_hi = ctx->w_hi; l->wi_lo = ctx->wi_lo; l->wi_hi = ctx->wi_hi;
+        l->g_lo = ctx->g_lo; l->g_hi = ctx->g_hi; l->gi_lo = ctx->gi_lo; l->gi_hi = ctx->gi_hi;
+        l->roots12 = ctx->roots12; l->iroots12 = ctx->iroots12; l->roots12f = ctx->roots12f; l->iroots12f = ctx->iroots12f;
+        l->inner_fwd = ctx->inner_fwd; l->inner_inv = ctx->inner_inv;
+        ctx->lanes.push_back(l);
+        r = lane_create_streams(l);
+    }
     if (r != VX_OK) { vx_ctx_destroy(ctx); return r; }
     *out = ctx;
     return VX_OK;
@@ -90,15 +126,9 @@ extern "C" int32_t vx_ctx_create(int32_t device, vx_ctx** out) {
 extern "C" void vx_ctx_destroy(vx_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (vx_ctx* l : ctx->lanes) lane_destroy_streams(l);
     ntt_module_destroy(ctx);
-    for (int i = 0; i < VX_NUM_PHASE_EVENTS; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
-    for (auto& e : ctx->copy_ev) if (e) cudaEventDestroy(e);
-    if (ctx->copy_free) cudaEventDestroy(ctx->copy_free);
-    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
-    if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); }
-    for (auto& e : ctx->absorb_ev) if (e) cudaEventDestroy(e);
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    for (size_t i = 1; i < ctx->lanes.size(); i++) delete ctx->lanes[i];
     delete ctx;
 }
 
@@ -106,20 +136,29 @@ extern "C" int32_t vx_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
     int usable = 0;
-    for (int d = 0; d < n; d++) {
-        cudaDeviceProp prop;
-        if (cudaGetDeviceProperties(&prop, d) == cudaSuccess && prop.major == 10) usable++;
-        else cudaGetLastError();
-    }
+    for (int d = 0; d < n; d++) usable += device_usable(d) ? 1 : 0;
     return usable;
+}
+// CUDA ordinals of the devices vx_ctx_create accepts (a box may mix GPU generations); returns how many were written
+extern "C" int32_t vx_device_list(int32_t* ordinals_out, int32_t capacity) {
+    int n = 0, k = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    for (int d = 0; d < n; d++)
+        if (device_usable(d)) {
+            if (ordinals_out && k < capacity) ordinals_out[k] = d;
+            k++;
+        }
+    return k;
 }
 extern "C" int32_t vx_device_sync(vx_ctx* ctx) {
     VX_REQUIRE(ctx, "vx_device_sync: ctx is NULL");
-    VX_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (vx_ctx* l : ctx->root->lanes)
+        for (cudaStream_t st : {l->stream, l->copy_stream, l->aux_stream}) VX_CUDA(cudaStreamSynchronize(st));
     return VX_OK;
 }
 extern "C" int32_t vx_ctx_phase_ms(vx_ctx* ctx, float out[VX_NUM_PHASE_EVENTS - 1]) {
     VX_REQUIRE(ctx && out, "vx_ctx_phase_ms: NULL argument");
+    ctx = ctx->root->lanes[ctx->root->last_commit_lane.load()];          // the lane of the most recent commit
     std::lock_guard<std::mutex> lk(ctx->mu);
     for (int i = 0; i + 1 < VX_NUM_PHASE_EVENTS; i++) {
         out[i] = 0.f;
@@ -140,12 +179,17 @@ extern "C" int32_t vx_ctx_phase_ms(vx_ctx* ctx, float out[VX_NUM_PHASE_EVENTS - 
     return VX_OK;
 }
 extern "C" void* vx_ctx_stream(vx_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
-extern "C" uint64_t vx_ctx_launch_count(vx_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
+extern "C" uint64_t vx_ctx_launch_count(vx_ctx* ctx) {
+    if (!ctx) return 0;
+    uint64_t n = 0;
+    for (vx_ctx* l : ctx->root->lanes) n += l->launches.load();
+    return n;
+}
 
 extern "C" int32_t vx_dev_alloc(vx_ctx* ctx, size_t bytes, uint64_t** out) {
     VX_REQUIRE(ctx && out, "vx_dev_alloc: NULL argument");
     *out = nullptr;
-    CtxGuard g(ctx);
+    VX_LANE(ctx);
     void* p = nullptr;
     cudaError_t e = cudaMallocAsync(&p, bytes ? bytes : 8, ctx->stream);
     if (e != cudaSuccess) {
@@ -159,13 +203,13 @@ extern "C" int32_t vx_dev_alloc(vx_ctx* ctx, size_t bytes, uint64_t** out) {
 }
 extern "C" void vx_dev_free(vx_ctx* ctx, uint64_t* p) {
     if (!ctx || !p) return;
-    CtxGuard g(ctx);
+    VX_LANE(ctx);
     cudaFreeAsync(p, ctx->stream);
 }
 extern "C" int32_t vx_dev_copy(vx_ctx* ctx, void* dst, const void* src, size_t bytes) {
     VX_REQUIRE(ctx && (bytes == 0 || (dst && src)), "vx_dev_copy: NULL argument");
     if (bytes == 0) return VX_OK;
-    CtxGuard g(ctx);
+    VX_LANE(ctx);
     VX_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, ctx->stream));
     VX_CUDA(cudaStreamSynchronize(ctx->stream));
     return VX_OK;
@@ -201,7 +245,34 @@ extern "C" void vx_host_unregister(void* p) {
 
 #define EV(ctx, i) VX_CUDA(cudaEventRecord((ctx)->ev[i], (ctx)->stream))
 
-static int32_t commit_run(vx_ctx* ctx, vx_batch* b, const u64* src, bool is_values, u64* keep = nullptr) {
+// Where a commit's input lives: ONE contiguous c x n matrix (`flat`), or c separately allocated columns (`cols`, what
+// plonky2 holds: Vec<PolynomialValues<F>>, one heap allocation per column).  Host memory may be pageable, pinned or
+// registered; device memory is accepted too.
+struct ColSource {
+    const u64* flat = nullptr;
+    const u64* const* cols = nullptr;
+    const u64* col(uint32_t j, uint64_t n) const { return cols ? cols[j] : flat + (size_t)j * n; }
+};
+// 0 = device, 1 = pinned / registered host, 2 = pageable host
+static int mem_kind(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return 2; }
+    if (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) return 0;
+    return a.type == cudaMemoryTypeHost ? 1 : 2;
+}
+// copies columns [c0, c1) to dst (contiguous): one transfer for a flat source, one per column otherwise
+static int32_t copy_columns(const ColSource& src, uint32_t c0, uint32_t c1, uint64_t n, u64* dst, cudaMemcpyKind kind,
+                            cudaStream_t st) {
+    if (src.flat) {
+        VX_CUDA(cudaMemcpyAsync(dst, src.flat + (size_t)c0 * n, (size_t)(c1 - c0) * n * sizeof(u64), kind, st));
+        return VX_OK;
+    }
+    for (uint32_t j = c0; j < c1; j++)
+        VX_CUDA(cudaMemcpyAsync(dst + (size_t)(j - c0) * n, src.cols[j], n * sizeof(u64), kind, st));
+    return VX_OK;
+}
+
+static int32_t commit_run(vx_ctx* ctx, vx_batch* b, const ColSource& src, bool is_values, u64* keep = nullptr) {
     const uint32_t c = b->c;
     const uint64_t n = b->n(), N_loc = b->N_loc();
     const size_t coeff_bytes = (size_t)c * n * sizeof(u64);
@@ -212,7 +283,8 @@ static int32_t commit_run(vx_ctx* ctx, vx_batch* b, const u64* src, bool is_valu
     VX_CHECK(b->cap.alloc((size_t)caps_loc * 4 * sizeof(u64), ctx->stream));
     EV(ctx, VX_EV_START);
     ctx->absorb_count = 0;
-    const bool from_host = !vx_is_device_ptr(src);
+    const int kind = mem_kind(src.col(0, n));
+    const bool from_host = kind != 0;
     // column chunks: with a host source the H2D copy of chunk k+1 (copy stream) overlaps the transforms of chunk k
     const uint32_t nchunks = (from_host && c >= 16) ? ctx->h2d_chunks : 1;
     DevBuf stage;
@@ -236,13 +308,18 @@ static int32_t commit_run(vx_ctx* ctx, vx_batch* b, const u64* src, bool is_valu
     const uint32_t groups = (c + 7) / 8;
     uint32_t bound[17] = {0};
     uint32_t nchunks_eff = nchunks;
+    // Pageable memory travels through the driver's staging buffers at roughly a quarter of the pinned rate: the ratio drops
+    // accordingly, chunks grow by it (not by 2) and, where the copy cannot hide at all (ratio < 1), stay equal in size.
     if (stream) {
-        const double ratio = (double)(1u << b->rate_bits) + 0.3;
-        uint32_t k = 0, g = 0, size = ctx->h2d_first_groups;
-        while (k + 1 < ctx->stream_chunks && g + size < groups) {
-            g += size;
+        const double ratio = ((double)(1u << b->rate_bits) + 0.3) * (kind == 2 ? 0.25 : 1.0);
+        const double grow = ratio >= 2.0 ? 2.0 : (ratio > 1.0 ? ratio : 1.0);
+        uint32_t k = 0, g = 0;
+        double size = ctx->h2d_first_groups;
+        if (grow == 1.0 && size * (ctx->stream_chunks - 1) < groups) size = (double)((groups + ctx->stream_chunks - 2) / (ctx->stream_chunks - 1));
+        while (k + 1 < ctx->stream_chunks && g + (uint32_t)size < groups) {
+            g += (uint32_t)size;
             bound[++k] = 8 * g;
-            size *= 2;
+            size *= grow;
             if ((double)(groups - g) <= 0.6 * ratio * (double)g) break;      // the rest hides behind what is queued
         }
         bound[++k] = c;
@@ -260,11 +337,11 @@ static int32_t commit_run(vx_ctx* ctx, vx_batch* b, const u64* src, bool is_valu
         // duplicated into the work buffer on the device (the inverse transform runs in place)
         u64* land = keep ? keep + off : dst;
         if (nchunks > 1) {
-            VX_CUDA(cudaMemcpyAsync(land, src + off, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+            VX_CHECK(copy_columns(src, c0, c1, n, land, cudaMemcpyHostToDevice, ctx->copy_stream));
             VX_CUDA(cudaEventRecord(ctx->copy_ev[k], ctx->copy_stream));
             VX_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[k], 0));
         } else {
-            VX_CUDA(cudaMemcpyAsync(land, src + off, bytes, cudaMemcpyDefault, ctx->stream));
+            VX_CHECK(copy_columns(src, c0, c1, n, land, cudaMemcpyDefault, ctx->stream));
         }
         if (keep) VX_CUDA(cudaMemcpyAsync(dst, land, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
         if (nchunks == 1) EV(ctx, VX_EV_STAGED);
@@ -290,14 +367,18 @@ static int32_t commit_run(vx_ctx* ctx, vx_batch* b, const u64* src, bool is_valu
     return VX_OK;
 }
 
-static int32_t commit_impl(vx_ctx* ctx, const u64* src, bool is_values, uint32_t c, uint32_t log_n,
+static ColSource flat_src(const uint64_t* p) { ColSource s; s.flat = (const u64*)p; return s; }
+
+static int32_t commit_impl(vx_ctx* ctx, const ColSource& src, bool is_values, uint32_t c, uint32_t log_n,
                            uint32_t rate_bits, uint32_t cap_height, uint32_t shard_index, uint32_t shard_count,
                            vx_batch** out, uint32_t hasher = VX_HASHER_POSEIDON, u64* keep = nullptr) {
-    VX_REQUIRE(ctx && src && out, "commit: NULL argument");
+    VX_REQUIRE(ctx && (src.flat || src.cols) && out, "commit: NULL argument");
     *out = nullptr;
+    if (src.cols)
+        for (uint32_t j = 0; j < c; j++) VX_REQUIRE(src.cols[j], "commit: column pointer %u is NULL", j);
     VX_REQUIRE(hasher <= VX_HASHER_POSEIDON_BN128, "commit: unknown hasher %u", hasher);
     VX_REQUIRE(c >= 1 && c < 16384, "commit: column count %u out of range", c);
-    VX_REQUIRE(log_n + rate_bits <= 26, "commit: 2^%u LDE points unsupported", log_n + rate_bits);
+    VX_REQUIRE(log_n <= 26 && log_n + rate_bits <= 30, "commit: 2^%u rows at rate_bits %u unsupported (coset tables cover 2^26 rows)", log_n, rate_bits);
     VX_REQUIRE(cap_height <= log_n + rate_bits, "commit: cap_height %u exceeds tree height %u", cap_height,
                log_n + rate_bits);
     VX_REQUIRE(shard_count >= 1 && (shard_count & (shard_count - 1)) == 0 && shard_index < shard_count,
@@ -306,15 +387,19 @@ static int32_t commit_impl(vx_ctx* ctx, const u64* src, bool is_values, uint32_t
     VX_REQUIRE(sbits <= rate_bits && sbits <= cap_height,
                "commit: %u shards need rate_bits >= %u and cap_height >= %u (whole cosets and whole cap subtrees per shard)",
                shard_count, sbits, sbits);
-    CtxGuard g(ctx);
+    VX_LANE(ctx);
     vx_batch* b = new (std::nothrow) vx_batch();
     if (!b) return VX_ENOMEM;
-    b->ctx = ctx; b->c = c; b->log_n = log_n; b->rate_bits = rate_bits; b->cap_height = cap_height;
+    b->ctx = ctx->root; b->c = c; b->log_n = log_n; b->rate_bits = rate_bits; b->cap_height = cap_height;
     b->hasher = hasher;
     b->blk_count = (1u << rate_bits) >> sbits;
     b->blk_first = shard_index * b->blk_count;
+    ctx->root->last_commit_lane.store(ctx->lane_index);
     int32_t r = commit_run(ctx, b, src, is_values, keep);
     if (r != VX_OK) {
+        // a chunked upload may still be in flight on the copy stream, targeting buffers the batch is about to free
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamSynchronize(ctx->aux_stream);
         cudaStreamSynchronize(ctx->stream);
         delete b;
         return r;
@@ -325,37 +410,50 @@ static int32_t commit_impl(vx_ctx* ctx, const u64* src, bool is_values, uint32_t
 
 extern "C" int32_t vx_commit_from_values(vx_ctx* ctx, const uint64_t* cols, uint32_t c, uint32_t log_n,
                                          uint32_t rate_bits, uint32_t cap_height, vx_batch** out) {
-    return commit_impl(ctx, (const u64*)cols, true, c, log_n, rate_bits, cap_height, 0, 1, out);
+    return commit_impl(ctx, flat_src(cols), true, c, log_n, rate_bits, cap_height, 0, 1, out);
 }
 extern "C" int32_t vx_commit_from_values_keep(vx_ctx* ctx, const uint64_t* cols, uint32_t c, uint32_t log_n,
                                               uint32_t rate_bits, uint32_t cap_height, uint64_t* values_dev_out,
                                               vx_batch** out) {
     VX_REQUIRE(values_dev_out && vx_is_device_ptr(values_dev_out), "vx_commit_from_values_keep: values_dev_out must be device memory");
-    return commit_impl(ctx, (const u64*)cols, true, c, log_n, rate_bits, cap_height, 0, 1, out, VX_HASHER_POSEIDON,
+    return commit_impl(ctx, flat_src(cols), true, c, log_n, rate_bits, cap_height, 0, 1, out, VX_HASHER_POSEIDON,
                        (u64*)values_dev_out);
+}
+// plonky2's own input shape: c separately allocated columns (Vec<PolynomialValues<F>>), no flattening on the host
+extern "C" int32_t vx_commit_from_values_cols(vx_ctx* ctx, const uint64_t* const* cols, uint32_t c, uint32_t log_n,
+                                              uint32_t rate_bits, uint32_t cap_height, vx_batch** out) {
+    ColSource s;
+    s.cols = (const u64* const*)cols;
+    return commit_impl(ctx, s, true, c, log_n, rate_bits, cap_height, 0, 1, out);
+}
+extern "C" int32_t vx_commit_from_coeffs_cols(vx_ctx* ctx, const uint64_t* const* coeffs, uint32_t c, uint32_t log_n,
+                                              uint32_t rate_bits, uint32_t cap_height, vx_batch** out) {
+    ColSource s;
+    s.cols = (const u64* const*)coeffs;
+    return commit_impl(ctx, s, false, c, log_n, rate_bits, cap_height, 0, 1, out);
 }
 extern "C" int32_t vx_commit_from_coeffs(vx_ctx* ctx, const uint64_t* coeffs, uint32_t c, uint32_t log_n,
                                          uint32_t rate_bits, uint32_t cap_height, vx_batch** out) {
-    return commit_impl(ctx, (const u64*)coeffs, false, c, log_n, rate_bits, cap_height, 0, 1, out);
+    return commit_impl(ctx, flat_src(coeffs), false, c, log_n, rate_bits, cap_height, 0, 1, out);
 }
 extern "C" int32_t vx_commit_from_values_hasher(vx_ctx* ctx, uint32_t hasher, const uint64_t* cols, uint32_t c,
                                                 uint32_t log_n, uint32_t rate_bits, uint32_t cap_height, vx_batch** out) {
-    return commit_impl(ctx, (const u64*)cols, true, c, log_n, rate_bits, cap_height, 0, 1, out, hasher);
+    return commit_impl(ctx, flat_src(cols), true, c, log_n, rate_bits, cap_height, 0, 1, out, hasher);
 }
 extern "C" int32_t vx_commit_from_coeffs_hasher(vx_ctx* ctx, uint32_t hasher, const uint64_t* coeffs, uint32_t c,
                                                 uint32_t log_n, uint32_t rate_bits, uint32_t cap_height, vx_batch** out) {
-    return commit_impl(ctx, (const u64*)coeffs, false, c, log_n, rate_bits, cap_height, 0, 1, out, hasher);
+    return commit_impl(ctx, flat_src(coeffs), false, c, log_n, rate_bits, cap_height, 0, 1, out, hasher);
 }
 extern "C" int32_t vx_commit_from_coeffs_shard(vx_ctx* ctx, const uint64_t* coeffs, uint32_t c, uint32_t log_n,
                                                uint32_t rate_bits, uint32_t cap_height, uint32_t shard_index,
                                                uint32_t shard_count, vx_batch** out) {
-    return commit_impl(ctx, (const u64*)coeffs, false, c, log_n, rate_bits, cap_height, shard_index, shard_count, out);
+    return commit_impl(ctx, flat_src(coeffs), false, c, log_n, rate_bits, cap_height, shard_index, shard_count, out);
 }
 
 extern "C" void vx_batch_free(vx_batch* b) {
     if (!b) return;
     {
-        CtxGuard g(b->ctx);
+        LaneGuard g(b->ctx);
         b->coeffs.release(); b->lde.release(); b->digests.release(); b->cap.release();
     }
     delete b;
@@ -375,17 +473,19 @@ extern "C" int32_t vx_batch_shard(const vx_batch* b, uint64_t out[3]) {
 
 extern "C" int32_t vx_batch_cap(vx_batch* b, uint64_t* cap_out) {
     VX_REQUIRE(b && cap_out, "vx_batch_cap: NULL argument");
-    CtxGuard g(b->ctx);
-    VX_CHECK(copy_out(b->ctx, (u64*)cap_out, b->cap.p, b->cap.bytes));
-    VX_CUDA(cudaStreamSynchronize(b->ctx->stream));
+    vx_ctx* ctx = b->ctx;
+    VX_LANE(ctx);
+    VX_CHECK(copy_out(ctx, (u64*)cap_out, b->cap.p, b->cap.bytes));
+    VX_CUDA(cudaStreamSynchronize(ctx->stream));
     return VX_OK;
 }
 
 extern "C" int32_t vx_batch_coeffs(vx_batch* b, uint64_t* coeffs_out) {
     VX_REQUIRE(b && coeffs_out, "vx_batch_coeffs: NULL argument");
-    CtxGuard g(b->ctx);
-    VX_CHECK(copy_out(b->ctx, (u64*)coeffs_out, b->coeffs.p, b->coeffs.bytes));
-    VX_CUDA(cudaStreamSynchronize(b->ctx->stream));
+    vx_ctx* ctx = b->ctx;
+    VX_LANE(ctx);
+    VX_CHECK(copy_out(ctx, (u64*)coeffs_out, b->coeffs.p, b->coeffs.bytes));
+    VX_CUDA(cudaStreamSynchronize(ctx->stream));
     return VX_OK;
 }
 
@@ -427,20 +527,22 @@ static int32_t query_paths(vx_ctx* ctx, const u64* digests, uint64_t N, uint32_t
 
 extern "C" int32_t vx_batch_leaves(vx_batch* b, const uint64_t* idx, uint32_t k, uint64_t* rows_out) {
     VX_REQUIRE(b && (k == 0 || (idx && rows_out)), "vx_batch_leaves: NULL argument");
-    CtxGuard g(b->ctx);
-    return query_rows(b->ctx, b->lde.p, true, b->N_loc(), b->c, b->N_loc(), idx, k, rows_out);
+    vx_ctx* ctx = b->ctx;
+    VX_LANE(ctx);
+    return query_rows(ctx, b->lde.p, true, b->N_loc(), b->c, b->N_loc(), idx, k, rows_out);
 }
 
 extern "C" int32_t vx_batch_merkle_paths(vx_batch* b, const uint64_t* idx, uint32_t k, uint64_t* siblings_out) {
     VX_REQUIRE(b && (k == 0 || (idx && siblings_out)), "vx_batch_merkle_paths: NULL argument");
-    CtxGuard g(b->ctx);
-    return query_paths(b->ctx, b->digests.p, b->N_loc(), b->cap_height_loc(), idx, k, siblings_out);
+    vx_ctx* ctx = b->ctx;
+    VX_LANE(ctx);
+    return query_paths(ctx, b->digests.p, b->N_loc(), b->cap_height_loc(), idx, k, siblings_out);
 }
 
 extern "C" int32_t vx_batch_download(vx_batch* b, uint64_t* leaves_out, uint64_t* digests_out) {
     VX_REQUIRE(b, "vx_batch_download: NULL batch");
-    CtxGuard g(b->ctx);
     vx_ctx* ctx = b->ctx;
+    VX_LANE(ctx);
     if (leaves_out) {
         DevBuf rows;
         VX_CHECK(rows.alloc(b->lde.bytes, ctx->stream));
@@ -476,10 +578,10 @@ extern "C" int32_t vx_merkle_new_hasher(vx_ctx* ctx, uint32_t hasher, const uint
                (unsigned long long)n);
     VX_REQUIRE(w >= 1, "vx_merkle_new: empty leaves");
     VX_REQUIRE(cap_height <= ilog2(n), "vx_merkle_new: cap_height %u exceeds tree height %u", cap_height, ilog2(n));
-    CtxGuard g(ctx);
+    VX_LANE(ctx);
     vx_tree* t = new (std::nothrow) vx_tree();
     if (!t) return VX_ENOMEM;
-    t->ctx = ctx; t->n = n; t->w = w; t->cap_height = cap_height;
+    t->ctx = ctx->root; t->n = n; t->w = w; t->cap_height = cap_height;
     int32_t r = t->leaves.alloc((size_t)n * w * sizeof(u64), ctx->stream);
     if (r == VX_OK) r = t->digests.alloc((size_t)2 * (n - (1ULL << cap_height)) * 4 * sizeof(u64), ctx->stream);
     if (r == VX_OK) r = t->cap.alloc((size_t)(1ULL << cap_height) * 4 * sizeof(u64), ctx->stream);
@@ -507,25 +609,28 @@ extern "C" int32_t vx_merkle_new(vx_ctx* ctx, const uint64_t* leaves, uint64_t n
 
 extern "C" int32_t vx_tree_prove(vx_tree* t, const uint64_t* idx, uint32_t k, uint64_t* siblings_out) {
     VX_REQUIRE(t && (k == 0 || (idx && siblings_out)), "vx_tree_prove: NULL argument");
-    CtxGuard g(t->ctx);
-    return query_paths(t->ctx, t->digests.p, t->n, t->cap_height, idx, k, siblings_out);
+    vx_ctx* ctx = t->ctx;
+    VX_LANE(ctx);
+    return query_paths(ctx, t->digests.p, t->n, t->cap_height, idx, k, siblings_out);
 }
 extern "C" int32_t vx_tree_leaves(vx_tree* t, const uint64_t* idx, uint32_t k, uint64_t* rows_out) {
     VX_REQUIRE(t && (k == 0 || (idx && rows_out)), "vx_tree_leaves: NULL argument");
-    CtxGuard g(t->ctx);
-    return query_rows(t->ctx, t->leaves.p, false, 0, t->w, t->n, idx, k, rows_out);
+    vx_ctx* ctx = t->ctx;
+    VX_LANE(ctx);
+    return query_rows(ctx, t->leaves.p, false, 0, t->w, t->n, idx, k, rows_out);
 }
 extern "C" int32_t vx_tree_cap(vx_tree* t, uint64_t* cap_out) {
     VX_REQUIRE(t && cap_out, "vx_tree_cap: NULL argument");
-    CtxGuard g(t->ctx);
-    VX_CHECK(copy_out(t->ctx, (u64*)cap_out, t->cap.p, t->cap.bytes));
-    VX_CUDA(cudaStreamSynchronize(t->ctx->stream));
+    vx_ctx* ctx = t->ctx;
+    VX_LANE(ctx);
+    VX_CHECK(copy_out(ctx, (u64*)cap_out, t->cap.p, t->cap.bytes));
+    VX_CUDA(cudaStreamSynchronize(ctx->stream));
     return VX_OK;
 }
 extern "C" void vx_tree_free(vx_tree* t) {
     if (!t) return;
     {
-        CtxGuard g(t->ctx);
+        LaneGuard g(t->ctx);
         t->leaves.release(); t->digests.release(); t->cap.release();
     }
     delete t;
@@ -535,7 +640,7 @@ extern "C" void vx_tree_free(vx_tree* t) {
 extern "C" int32_t vx_poseidon_permute(vx_ctx* ctx, const uint64_t* in, uint64_t count, uint64_t* out) {
     VX_REQUIRE(ctx && (count == 0 || (in && out)), "vx_poseidon_permute: NULL argument");
     if (count == 0) return VX_OK;
-    CtxGuard g(ctx);
+    VX_LANE(ctx);
     DevBuf a, b;
     VX_CHECK(a.alloc(count * 12 * sizeof(u64), ctx->stream));
     VX_CHECK(b.alloc(count * 12 * sizeof(u64), ctx->stream));
@@ -550,7 +655,7 @@ extern "C" int32_t vx_hash_no_pad(vx_ctx* ctx, const uint64_t* in, uint64_t coun
     VX_REQUIRE(ctx && (count == 0 || out), "vx_hash_no_pad: NULL argument");
     VX_REQUIRE(len == 0 || in, "vx_hash_no_pad: NULL input");
     if (count == 0) return VX_OK;
-    CtxGuard g(ctx);
+    VX_LANE(ctx);
     DevBuf a, b;
     VX_CHECK(a.alloc((size_t)count * len * sizeof(u64), ctx->stream));
     VX_CHECK(b.alloc(count * 4 * sizeof(u64), ctx->stream));
@@ -574,7 +679,7 @@ extern "C" int32_t vx_bn128_permute(vx_ctx* ctx, const uint64_t* in, uint64_t co
     for (uint64_t i = 0; i < 4 * count; i++)
         VX_REQUIRE(bn128_words_canonical(in + 4 * i), "vx_bn128_permute: scalar %llu is not below the BN254 scalar modulus",
                    (unsigned long long)i);
-    CtxGuard g(ctx);
+    VX_LANE(ctx);
     DevBuf a, b;
     VX_CHECK(a.alloc(count * 16 * sizeof(u64), ctx->stream));
     VX_CHECK(b.alloc(count * 16 * sizeof(u64), ctx->stream));
@@ -589,7 +694,7 @@ extern "C" int32_t vx_bn128_hash(vx_ctx* ctx, const uint64_t* in, uint64_t count
     VX_REQUIRE(ctx && (count == 0 || out), "vx_bn128_hash: NULL argument");
     VX_REQUIRE(len == 0 || in, "vx_bn128_hash: NULL input");
     if (count == 0) return VX_OK;
-    CtxGuard g(ctx);
+    VX_LANE(ctx);
     DevBuf a, b;
     VX_CHECK(a.alloc((size_t)count * len * sizeof(u64), ctx->stream));
     VX_CHECK(b.alloc(count * 4 * sizeof(u64), ctx->stream));
@@ -656,7 +761,7 @@ extern "C" int32_t vx_ntt(vx_ctx* ctx, const uint64_t* in, uint64_t* out, uint32
                           int32_t inverse, uint64_t coset_shift) {
     VX_REQUIRE(ctx && in && out, "vx_ntt: NULL argument");
     VX_REQUIRE(c >= 1 && log_n <= 26, "vx_ntt: shape out of range");
-    CtxGuard g(ctx);
+    VX_LANE(ctx);
     size_t bytes = ((size_t)c << log_n) * sizeof(u64);
     DevBuf a, b;
     VX_CHECK(a.alloc(bytes, ctx->stream));

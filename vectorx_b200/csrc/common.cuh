@@ -65,8 +65,16 @@ struct vx_ctx {
     int absorb_count = 0;
     cudaEvent_t copy_ev[16] = {};       // one per column chunk in flight
     cudaEvent_t copy_free = nullptr;    // staging buffer no longer read by the compute stream
-    std::mutex mu;                      // serialises calls on this context's stream
+    std::mutex mu;                      // serialises calls on this lane's streams
     std::atomic<uint64_t> launches{0};
+    // Lanes: a context is a set of VX_LANES independent stream sets ("lanes") sharing one copy of the tables, so that
+    // concurrent callers (Rayon workers, several STARK proofs in flight: SURVEY.md 8b) run side by side instead of queueing
+    // on one mutex.  lanes[0] is the context itself; every entry point takes a free lane for the duration of the call.
+    vx_ctx* root = nullptr;             // the context the caller holds
+    std::vector<vx_ctx*> lanes;         // root only
+    std::atomic<unsigned> lane_ticket{0};
+    std::atomic<int> last_commit_lane{0};       // lane of the most recent commit (vx_ctx_phase_ms)
+    int lane_index = 0;
     u64 *w_lo = nullptr, *w_hi = nullptr, *wi_lo = nullptr, *wi_hi = nullptr;
     u64 *g_lo = nullptr, *g_hi = nullptr, *gi_lo = nullptr, *gi_hi = nullptr;
     u64 *roots12 = nullptr, *iroots12 = nullptr;
@@ -130,10 +138,29 @@ __host__ __device__ static inline uint64_t bitrev_u64(uint64_t x, unsigned bits)
 #endif
 }
 
-struct CtxGuard {       // one call at a time per context; binds the device to the calling thread
-    std::lock_guard<std::mutex> lk;
+#define VX_LANES 4
+struct CtxGuard {       // one call at a time on THIS lane (used with the primary lane by the sharded commit, whose group
+    std::lock_guard<std::mutex> lk;                                       // state lives on the primary lane's streams)
     explicit CtxGuard(vx_ctx* c) : lk(c->mu) { cudaSetDevice(c->device); }
 };
+struct LaneGuard {      // takes a free lane of the context (or queues on one, round robin); binds the device to the thread
+    vx_ctx* lane = nullptr;
+    explicit LaneGuard(vx_ctx* c) {
+        vx_ctx* root = c->root ? c->root : c;
+        for (vx_ctx* l : root->lanes)
+            if (l->mu.try_lock()) { lane = l; break; }
+        if (!lane) {
+            lane = root->lanes.empty() ? root : root->lanes[root->lane_ticket.fetch_add(1) % root->lanes.size()];
+            lane->mu.lock();
+        }
+        cudaSetDevice(lane->device);
+    }
+    ~LaneGuard() { lane->mu.unlock(); }
+    LaneGuard(const LaneGuard&) = delete;
+    LaneGuard& operator=(const LaneGuard&) = delete;
+};
+// rebinds the local `ctx` to the lane taken for this call
+#define VX_LANE(ctx) LaneGuard _lane_guard(ctx); ctx = _lane_guard.lane
 
 // copy helpers that accept host or device memory on either side
 static inline int32_t copy_in(vx_ctx* ctx, u64* dst_dev, const u64* src, size_t bytes) {

@@ -123,8 +123,7 @@ __global__ void interleave_kernel(const u64* __restrict__ in, uint64_t len, uint
     out[e] = in[(e & 1) * len + (e >> 1)];
 }
 
-static int32_t fri_recompute_values(vx_fri* f) {
-    vx_ctx* ctx = f->ctx;
+static int32_t fri_recompute_values(vx_ctx* ctx, vx_fri* f) {
     uint64_t len = 1ULL << f->log_len;
     VX_CHECK(f->values.alloc(2 * len * 8, ctx->stream));
     VX_CUDA(cudaMemcpyAsync(f->values.p, f->coeffs.p, 2 * len * 8, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -134,7 +133,7 @@ static int32_t fri_recompute_values(vx_fri* f) {
 extern "C" void vx_fri_free(vx_fri* f) {
     if (!f) return;
     {
-        CtxGuard g(f->ctx);
+        LaneGuard g(f->ctx);
         f->coeffs.release(); f->values.release();
         for (FriLayer* l : f->layers) { l->leaves.release(); l->digests.release(); l->cap.release(); delete l; }
     }
@@ -149,11 +148,11 @@ extern "C" int32_t vx_fri_begin(vx_ctx* ctx, vx_batch* const* oracles, uint32_t 
     for (uint32_t o = 0; o < num_oracles; o++)
         VX_REQUIRE(oracles[o] && oracles[o]->log_n == log_n && oracles[o]->rate_bits == rate_bits &&
                    oracles[o]->ctx == ctx, "vx_fri_begin: oracles must share degree, rate and context");
-    CtxGuard g(ctx);
+    VX_LANE(ctx);
     const uint64_t n = 1ULL << log_n, N = n << rate_bits;
     vx_fri* f = new (std::nothrow) vx_fri();
     if (!f) return VX_ENOMEM;
-    f->ctx = ctx; f->log_len = log_n + rate_bits; f->rate_bits = rate_bits; f->shift = GL_GENERATOR;
+    f->ctx = ctx->root; f->log_len = log_n + rate_bits; f->rate_bits = rate_bits; f->shift = GL_GENERATOR;
     auto fail = [&](int32_t r) { cudaStreamSynchronize(ctx->stream); f->coeffs.release(); f->values.release(); delete f; return r; };
     DevBuf fin, comp, dcols;
     int32_t r = fin.alloc(2 * n * 8, ctx->stream);
@@ -204,7 +203,7 @@ extern "C" int32_t vx_fri_begin(vx_ctx* ctx, vx_batch* const* oracles, uint32_t 
     cudaMemsetAsync(f->coeffs.p, 0, 2 * N * 8, ctx->stream);
     cudaMemcpyAsync(f->coeffs.p, fin.p, n * 8, cudaMemcpyDeviceToDevice, ctx->stream);
     cudaMemcpyAsync(f->coeffs.p + N, fin.p + n, n * 8, cudaMemcpyDeviceToDevice, ctx->stream);
-    r = fri_recompute_values(f);
+    r = fri_recompute_values(ctx, f);
     if (r != VX_OK) return fail(r);
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { vx_set_error("vx_fri_begin: sync failed"); return fail(VX_ECUDA); }
     *out = f;
@@ -215,7 +214,7 @@ extern "C" int32_t vx_fri_commit_layer(vx_fri* f, uint32_t arity_bits, uint32_t 
     VX_REQUIRE(f && cap_out && arity_bits >= 1 && arity_bits < f->log_len, "vx_fri_commit_layer: bad argument");
     VX_REQUIRE(f->pending_arity == 0, "vx_fri_commit_layer: fold the previous layer first");
     vx_ctx* ctx = f->ctx;
-    CtxGuard g(ctx);
+    VX_LANE(ctx);
     const uint64_t len = 1ULL << f->log_len, rows = len >> arity_bits;
     VX_REQUIRE(cap_height <= f->log_len - arity_bits, "vx_fri_commit_layer: cap_height too large for this layer");
     FriLayer* L = new (std::nothrow) FriLayer();
@@ -241,7 +240,7 @@ extern "C" int32_t vx_fri_fold(vx_fri* f, const uint64_t beta[2]) {
     VX_REQUIRE(f && beta, "vx_fri_fold: NULL argument");
     VX_REQUIRE(f->pending_arity != 0, "vx_fri_fold: commit the layer first");
     vx_ctx* ctx = f->ctx;
-    CtxGuard g(ctx);
+    VX_LANE(ctx);
     const uint32_t ab = f->pending_arity;
     const uint64_t len = 1ULL << f->log_len, nl = len >> ab;
     DevBuf nc;
@@ -255,7 +254,7 @@ extern "C" int32_t vx_fri_fold(vx_fri* f, const uint64_t beta[2]) {
     f->log_len -= ab;
     f->shift = gl_pow_host(f->shift, 1ULL << ab);
     f->pending_arity = 0;
-    VX_CHECK(fri_recompute_values(f));
+    VX_CHECK(fri_recompute_values(ctx, f));
     VX_CUDA(cudaStreamSynchronize(ctx->stream));
     return VX_OK;
 }
@@ -263,7 +262,7 @@ extern "C" int32_t vx_fri_fold(vx_fri* f, const uint64_t beta[2]) {
 extern "C" int32_t vx_fri_final_poly(vx_fri* f, uint64_t* out, uint32_t* len_out) {
     VX_REQUIRE(f && out && len_out, "vx_fri_final_poly: NULL argument");
     vx_ctx* ctx = f->ctx;
-    CtxGuard g(ctx);
+    VX_LANE(ctx);
     const uint64_t len = 1ULL << f->log_len, keep = len >> f->rate_bits;
     DevBuf d;
     VX_CHECK(d.alloc(2 * keep * 8, ctx->stream));
@@ -281,7 +280,7 @@ extern "C" int32_t vx_fri_query(vx_fri* f, uint32_t layer, const uint64_t* idx, 
     VX_REQUIRE(f && layer < f->layers.size() && (k == 0 || (idx && rows_out && paths_out)), "vx_fri_query: bad argument");
     if (k == 0) return VX_OK;
     vx_ctx* ctx = f->ctx;
-    CtxGuard g(ctx);
+    VX_LANE(ctx);
     FriLayer* L = f->layers[layer];
     for (uint32_t i = 0; i < k; i++)
         VX_REQUIRE(idx[i] < L->leaves_n, "vx_fri_query: leaf index %llu out of range", (unsigned long long)idx[i]);
@@ -327,7 +326,7 @@ int32_t fri_module_init(vx_ctx* ctx) {
 
 extern "C" int32_t vx_pow_grind(vx_ctx* ctx, const uint64_t state[12], uint32_t pos, uint32_t min_zeros, uint64_t* witness_out) {
     VX_REQUIRE(ctx && state && witness_out && pos < 8 && min_zeros >= 1 && min_zeros <= 40, "vx_pow_grind: bad argument");
-    CtxGuard g(ctx);
+    VX_LANE(ctx);
     DevBuf ds, db;
     VX_CHECK(ds.alloc(12 * 8, ctx->stream));
     VX_CHECK(db.alloc(8, ctx->stream));

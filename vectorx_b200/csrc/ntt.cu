@@ -136,11 +136,13 @@ __global__ void scale_table_kernel(u64* __restrict__ tab, uint32_t log_n, uint32
 
 // Callers hold ctx->ntt_cache_mu.  A table is built on the context's main stream and the build is waited for, so any stream
 // of the context may read it afterwards.
-static const u64* cache_find(vx_ctx* ctx, uint64_t key) {
+static const u64* cache_find(vx_ctx* lane, uint64_t key) {
+    vx_ctx* ctx = lane->root;
     for (auto& e : ctx->ntt_cache) if (e.key == key) return e.p;
     return nullptr;
 }
-static int32_t cache_add(vx_ctx* ctx, uint64_t key, size_t bytes, u64** out) {
+static int32_t cache_add(vx_ctx* lane, uint64_t key, size_t bytes, u64** out) {
+    vx_ctx* ctx = lane->root;
     // derived tables are bounded by the number of distinct shapes a process commits; drop everything past 1 GB
     if (ctx->ntt_cache_bytes + bytes > (1ULL << 30)) {
         VX_CUDA(cudaDeviceSynchronize());
@@ -157,7 +159,7 @@ static int32_t outer_table(vx_ctx* ctx, uint32_t log_M, bool inverse, const u64*
     *out = nullptr;
     if (log_M > NTT_OUTER_MAX_LOG) return VX_OK;
     const uint64_t key = (1ULL << 60) | ((uint64_t)inverse << 8) | log_M;
-    std::lock_guard<std::mutex> lk(ctx->ntt_cache_mu);
+    std::lock_guard<std::mutex> lk(ctx->root->ntt_cache_mu);
     if ((*out = cache_find(ctx, key))) return VX_OK;
     u64* p;
     VX_CHECK(cache_add(ctx, key, sizeof(u64) << log_M, &p));
@@ -172,7 +174,7 @@ static int32_t scale_table(vx_ctx* ctx, uint32_t log_n, uint32_t rate_bits, uint
     *out = nullptr;
     if (((uint64_t)blk_count << log_n) > (1ULL << NTT_SCALE_MAX_LOG)) return VX_OK;
     const uint64_t key = (2ULL << 60) | ((uint64_t)blk_count << 32) | ((uint64_t)blk_first << 16) | (rate_bits << 8) | log_n;
-    std::lock_guard<std::mutex> lk(ctx->ntt_cache_mu);
+    std::lock_guard<std::mutex> lk(ctx->root->ntt_cache_mu);
     if ((*out = cache_find(ctx, key))) return VX_OK;
     u64* p;
     VX_CHECK(cache_add(ctx, key, ((size_t)blk_count << log_n) * sizeof(u64), &p));

@@ -279,7 +279,7 @@ extern "C" int32_t vx_quotient(vx_ctx* ctx, const vx_circuit_desc* d, vx_batch* 
                zpp->c == d->num_challenges * (1 + d->num_partial_products), "vx_quotient: batch widths do not match the circuit");
     const uint32_t chunks = (d->num_routed_wires + d->max_degree - 1) / d->max_degree;
     VX_REQUIRE(chunks == d->num_partial_products + 1, "vx_quotient: num_partial_products inconsistent with max_degree");
-    CtxGuard g(ctx);
+    VX_LANE(ctx);
     const uint32_t nch = d->num_challenges;
     const uint32_t perm_terms = nch + nch * chunks;
     const uint32_t num_terms = perm_terms + d->num_gate_constraints;
@@ -484,7 +484,7 @@ extern "C" int32_t vx_zs_partial_products(vx_ctx* ctx, const vx_circuit_desc* d,
                                           const uint64_t* sigmas, const uint64_t* betas, const uint64_t* gammas,
                                           uint64_t* out) {
     VX_REQUIRE(ctx && d && wires && sigmas && betas && gammas && out, "vx_zs_partial_products: NULL argument");
-    CtxGuard g(ctx);
+    VX_LANE(ctx);
     const uint64_t n = 1ULL << d->degree_bits;
     const uint32_t nch = d->num_challenges, R = d->num_routed_wires;
     VX_REQUIRE(nch >= 1 && nch <= 4, "vx_zs_partial_products: num_challenges %u unsupported", nch);
@@ -566,7 +566,7 @@ __global__ void __launch_bounds__(EVAL_BLOCK) eval_ext_kernel(const u64* __restr
 extern "C" int32_t vx_batch_eval_ext(vx_batch* b, const uint64_t point[2], uint64_t* out) {
     VX_REQUIRE(b && point && out, "vx_batch_eval_ext: NULL argument");
     vx_ctx* ctx = b->ctx;
-    CtxGuard g(ctx);
+    VX_LANE(ctx);
     DevBuf d;
     VX_CHECK(d.alloc((size_t)b->c * 2 * 8, ctx->stream));
     eval_ext_kernel<<<b->c, EVAL_BLOCK, 0, ctx->stream>>>(b->coeffs.p, b->log_n, gl2_make(point[0] % GL_P, point[1] % GL_P), d.p);
@@ -601,7 +601,7 @@ extern "C" int32_t vx_field_op(vx_ctx* ctx, uint32_t op, const uint64_t* a, cons
                                uint64_t* out) {
     VX_REQUIRE(ctx && a && out && op <= 8, "vx_field_op: bad argument");
     if (n == 0) return VX_OK;
-    CtxGuard g(ctx);
+    VX_LANE(ctx);
     const uint64_t words = (op >= 7) ? 2 * n : n;
     DevBuf da, db, dc, dout;
     VX_CHECK(da.alloc(words * 8, ctx->stream)); VX_CHECK(db.alloc(words * 8, ctx->stream));

@@ -106,7 +106,7 @@ extern "C" int32_t vx_shard_group_create(vx_ctx* ctx, uint32_t rank, uint32_t wo
     VX_REQUIRE(sbits <= rate_bits && sbits <= cap_height,
                "vx_shard_group_create: %u shards need rate_bits >= %u and cap_height >= %u (whole cosets and whole cap "
                "subtrees per shard)", world, sbits, sbits);
-    VX_REQUIRE(c >= 1 && c < 16384 && log_n >= 1 && log_n + rate_bits <= 26 && cap_height <= log_n + rate_bits,
+    VX_REQUIRE(c >= 1 && c < 16384 && log_n >= 1 && log_n <= 26 && log_n + rate_bits <= 30 && cap_height <= log_n + rate_bits,
                "vx_shard_group_create: shape out of range");
     CtxGuard g(ctx);
     vx_shard_group* s = new (std::nothrow) vx_shard_group();
@@ -414,6 +414,7 @@ extern "C" int32_t vx_shard_commit_from_values(vx_shard_group* s, const uint64_t
     vx_batch* b = new (std::nothrow) vx_batch();
     if (!b) return VX_ENOMEM;
     const uint32_t sbits = ilog2(s->world);
+    s->ctx->last_commit_lane.store(0);
     b->ctx = s->ctx; b->c = s->c; b->log_n = s->log_n; b->rate_bits = s->rate_bits; b->cap_height = s->cap_height;
     b->blk_count = (1u << s->rate_bits) >> sbits;
     b->blk_first = s->rank * b->blk_count;

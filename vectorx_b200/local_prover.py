@@ -14,7 +14,7 @@ import queue
 import threading
 from typing import Callable, Sequence
 
-from ._lib import Context, device_count
+from ._lib import Context, device_list
 from .prover import CircuitData, prove
 
 
@@ -51,10 +51,9 @@ class LocalProver:
     def __init__(self, devices: Sequence[int] | None = None, *, make_ctx: Callable[[int], object] = Context,
                  prove_fn: Callable = prove):
         if devices is None:
-            n = device_count()
-            if n == 0:
+            devices = device_list()           # the usable CUDA ordinals (a box may mix GPU generations)
+            if len(devices) == 0:
                 raise RuntimeError("LocalProver: no sm_100-class GPU is visible (there is no CPU fallback)")
-            devices = list(range(n))
         if len(devices) == 0:
             raise ValueError("LocalProver: empty device list")
         self.devices = list(devices)

@@ -139,7 +139,9 @@ class PolynomialBatch:
     @classmethod
     def from_values(cls, values, rate_bits: int, blinding: bool, cap_height: int, timing=None,
                     fft_root_table=None, ctx: Context | None = None, hasher: int = POSEIDON_HASH) -> "PolynomialBatch":
-        """values: (c, n) uint64 array/tensor, polynomial j = values[j] (evaluations on the subgroup)."""
+        """values: (c, n) uint64 array/tensor, polynomial j = values[j] (evaluations on the subgroup) -- or, as plonky2
+        holds them (`Vec<PolynomialValues<F>>`), a list of c separately allocated length-n arrays / tensors, which go to
+        the device column by column without being flattened on the host."""
         return cls._commit("vx_commit_from_values_hasher", values, rate_bits, blinding, cap_height, ctx, hasher)
 
     @classmethod
@@ -182,6 +184,21 @@ class PolynomialBatch:
         if blinding:
             raise VxError("blinding=true is unsupported (zero_knowledge=false in standard_recursion_config)")
         ctx = ctx or default_context()
+        if isinstance(data, (list, tuple)):
+            # plonky2's own shape: Vec<PolynomialValues<F>> / Vec<PolynomialCoeffs<F>>, one allocation per column
+            if hasher != POSEIDON_HASH:
+                raise VxError("per-column input is bound for the Poseidon hasher only")
+            cols = [np.ascontiguousarray(x, dtype=np.uint64) if isinstance(x, np.ndarray) else x for x in data]
+            c = len(cols)
+            n = int(cols[0].shape[0]) if c else 0
+            log_n = n.bit_length() - 1
+            if c == 0 or (1 << log_n) != n or any(int(x.shape[0]) != n or len(x.shape) != 1 for x in cols):
+                raise VxError("columns must be non-empty 1-D arrays of one power-of-two length")
+            ptrs = (vp * c)(*[ptr(x) for x in cols])
+            name = "vx_commit_from_values_cols" if "values" in fn else "vx_commit_from_coeffs_cols"
+            h = vp()
+            check(getattr(load(), name)(ctx.handle, ptrs, c, log_n, rate_bits, cap_height, ctypes.byref(h)), name)
+            return cls(ctx, h)
         c, n = int(data.shape[0]), int(data.shape[1])
         log_n = n.bit_length() - 1
         if (1 << log_n) != n:
