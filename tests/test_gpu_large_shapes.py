@@ -47,9 +47,9 @@ def _sparse(c, n, seed):
     rng = np.random.default_rng(seed)
     out = []
     for j in range(c):
-        terms = {0: int(rng.integers(1, P)), n - 1: int(rng.integers(1, P))}
+        terms = {0: int(rng.integers(1, P, dtype=np.uint64)), n - 1: int(rng.integers(1, P, dtype=np.uint64))}
         for e in rng.integers(1, n - 1, size=2):
-            terms[int(e)] = int(rng.integers(1, P))
+            terms[int(e)] = int(rng.integers(1, P, dtype=np.uint64))
         out.append(terms)
     return out
 
