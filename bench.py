@@ -181,6 +181,60 @@ def run_reference(a, w, rank):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------ whole proofs
+def run_prove_block(a, vx, ctx, dist, rank, local_rank, G):
+    """Second half of BASELINE's metric ("prove secs at 1/2/4/8 GPU").  The header_range / rotate circuits need the Rust
+    witness generator (not buildable here), so the proof is of a synthetic circuit with the reference's config
+    (standard_recursion_config: 135 wires / 80 routed, rate_bits 3, cap_height 4, 28 queries, 16-bit PoW) and a 9-gate mix,
+    2^prove_bits rows.  Circuit, witness and the verifier come from oracle/ (test infrastructure: input generation and the
+    untimed check only); everything timed goes through the C ABI.
+      ms_per_proof : one prove_with_partition_witness from a pageable witness on one GPU (best of 3, rank 0);
+      proofs_per_s : LocalProver.batch_prove (P2X/backend/prover/local.rs:34-48) -- every rank proves `prove_batch`
+                     independent inputs on its own GPU with two workers sharing one context; all proofs / max time."""
+    import torch
+    from oracle import plonk, synth                      # inputs + untimed verification only
+    from oracle.field import E2
+    from vectorx_b200.local_prover import CircuitSpec, LocalProver
+    bits = a.prove_bits
+    circ, wires, pis = synth.build(bits, seed=11)
+    spec = CircuitSpec(circ.d, [g.id() for g in circ.gates], circ.selector_index, circ.groups, circ.constants, circ.sigmas)
+    lp = LocalProver(devices=[local_rank], workers_per_device=2)
+    lp.batch_prove(spec, [(wires, pis)] * 2)             # warm-up: circuit replica, pools, caches
+    ms_single, verified = None, None
+    if rank == 0:
+        runs = []
+        for _ in range(3):
+            t = time.perf_counter()
+            proof = lp.prove(spec, (wires, pis))
+            runs.append((time.perf_counter() - t) * 1e3)
+        ms_single = min(runs)
+        oproof = dict(proof)
+        oproof["openings"] = {k: [E2(int(e[0]), int(e[1])) for e in v] for k, v in proof["openings"].items()}
+        oproof["final_poly"] = [E2(int(e[0]), int(e[1])) for e in proof["final_poly"]]
+        verified = bool(plonk.verify(circ, oproof))
+        if not verified:
+            raise SystemExit("bench.py: the GPU proof was rejected by the oracle verifier")
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = time.perf_counter()
+    proofs = lp.batch_prove(spec, [(wires, pis)] * a.prove_batch)
+    dt = time.perf_counter() - t
+    ref_w = proofs[0]["pow_witness"]
+    same = all(p["pow_witness"] == ref_w for p in proofs)
+    tt = torch.tensor([dt], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if dist is not None:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    lp.close()
+    if rank != 0:
+        return None
+    return {"circuit": f"synthetic 2^{bits}-row circuit, standard_recursion_config, gates: " + ", ".join(sorted({g.id().split('{')[0].split('(')[0].split(' ')[0] for g in circ.gates})),
+            "witness": "pageable host memory", "ms_per_proof": ms_single, "secs_per_proof": ms_single / 1e3,
+            "proofs_per_s": G * a.prove_batch / float(tt.item()), "proofs_per_batch_per_gpu": a.prove_batch, "n_gpus": G,
+            "workers_per_gpu": 2, "verified_by_oracle_verifier": verified, "batch_identical": same,
+            "note": "BASELINE configs 2-4 (header_range_256/512, rotate) need the Rust witness generator: not measured here"}
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -193,6 +247,9 @@ def main():
     ap.add_argument("--rate-bits", type=int, default=3)
     ap.add_argument("--cap-height", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-prove", action="store_true", help="skip the whole-proof block (second half of BASELINE's metric)")
+    ap.add_argument("--prove-bits", type=int, default=16, help="rows (log2) of the synthetic circuit of the prove block")
+    ap.add_argument("--prove-batch", type=int, default=16, help="proofs per rank in the batch_prove throughput run")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: 'peer' = the library's own kernels over NVLink peer memory, 'nccl' = torch.distributed all-gather (A/B)")
     a = ap.parse_args()
@@ -242,6 +299,12 @@ def main():
         h = torch.from_numpy(mine.view(np.int64)).pin_memory()
         host_sets.append(h)
         dev_sets.append(h.to(f"cuda:{local_rank}"))
+    # the same values as plonky2 holds them: c separately allocated PAGEABLE columns (Vec<PolynomialValues<F>>)
+    page_sets = []
+    if G == 1:
+        for s_ in range(N_INPUT_SETS):
+            full = host_sets[s_].numpy().view(np.uint64)
+            page_sets.append([np.array(full[j], copy=True) for j in range(c)])
     coeff_all = torch.empty((G * cpr, n), dtype=torch.int64, device=f"cuda:{local_rank}")
     coeff_mine = torch.empty((cpr, n), dtype=torch.int64, device=f"cuda:{local_rank}")
     caps_loc = (1 << cap) // G
@@ -288,13 +351,22 @@ def main():
             cap_host.copy_(cap_all, non_blocking=False)
         engine.free(h)
 
+    def one_step_cols(cols):
+        """G == 1: one commit through vx_commit_from_values_cols from c separate pageable allocations; cap -> cap_host."""
+        h = vp()
+        ptrs = (vp * c)(*[x.ctypes.data for x in cols])
+        check(lib.vx_commit_from_values_cols(ctx.handle, ptrs, c, log_n, rate, cap, ctypes.byref(h)),
+              "vx_commit_from_values_cols")
+        check(lib.vx_batch_cap(h, cap_host.data_ptr()), "vx_batch_cap")
+        lib.vx_batch_free(h)
+
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
         ctx.sync()
 
-    def timed(from_host, steps):
+    def timed(from_host, steps, per_column=False):
         sets = host_sets if from_host else dev_sets
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -304,7 +376,10 @@ def main():
         t0 = time.perf_counter()
         e0.record(ev_stream)
         for i in range(steps):
-            one_step(sets[i % N_INPUT_SETS], from_host)
+            if per_column:
+                one_step_cols(page_sets[i % N_INPUT_SETS])
+            else:
+                one_step(sets[i % N_INPUT_SETS], from_host)
         e1.record(ev_stream)
         barrier()
         wall = (time.perf_counter() - t0) * 1e3
@@ -319,25 +394,41 @@ def main():
         one_step(dev_sets[i % N_INPUT_SETS], False)
     for i in range(2):
         one_step(host_sets[i % N_INPUT_SETS], True)
+    shard_parity = None
     if G > 1:
-        # sanity (untimed): the gathered cap of the sharded commit must equal a whole commit of the same values
+        # parity (untimed), on EVERY rank: a whole single-GPU commit of the same values on this rank's own GPU, then
+        #  * this rank's block of Merkle digests (its cosets' leaf digests and interior levels, plonky2 layout) must be
+        #    the matching slice of the whole commit's digests,
+        #  * the gathered cap must equal the whole cap -- for device-resident and for host values (streamed pipeline).
         full0 = gen_values(c, n, seed=0x5EED0001)
-        one_step(dev_sets[0], False)
-        torch.cuda.synchronize()
-        if rank == 0:
-            whole = vx.PolynomialBatch.from_values(full0, rate, False, cap, ctx=ctx)
-            same = np.array_equal(whole.cap.hashes, cap_all.cpu().numpy().view(np.uint64))
-            if not same:
-                raise SystemExit("bench.py: sharded commit cap differs from the single-GPU cap")
-        # the same through the end-to-end path (host values: the streamed column pipeline of csrc/shard.cu)
-        one_step(host_sets[0], True)
-        torch.cuda.synchronize()
-        if rank == 0:
-            same = np.array_equal(whole.cap.hashes, cap_host.numpy().view(np.uint64))
-            whole.close()
-            if not same:
-                raise SystemExit("bench.py: sharded commit cap (host values) differs from the single-GPU cap")
-        del full0
+        whole = vx.PolynomialBatch.from_values(full0, rate, False, cap, ctx=ctx)
+        whole_digests = np.zeros((2 * (N - (1 << cap)), 4), dtype=np.uint64)
+        check(lib.vx_batch_download(whole._h, None, whole_digests.ctypes.data), "vx_batch_download")
+        per_rank = whole_digests.shape[0] // G
+        ok = True
+        for from_host in (False, True):
+            src = host_sets[0] if from_host else dev_sets[0]
+            if use_nccl:
+                h, _ = sharded_commit(src, plan, engine, comm, bufs)
+                got_cap = cap_all.cpu().numpy().view(np.uint64)
+                free = engine.free
+            else:
+                h = group.commit_from_values(src, cap_host if from_host else cap_all)
+                got_cap = (cap_host.numpy() if from_host else cap_all.cpu().numpy()).view(np.uint64)
+                free = group.free_batch
+            torch.cuda.synchronize()
+            mine = np.zeros((per_rank, 4), dtype=np.uint64)
+            check(lib.vx_batch_download(h, None, mine.ctypes.data), "vx_batch_download")
+            ok = ok and np.array_equal(mine, whole_digests[rank * per_rank:(rank + 1) * per_rank])
+            ok = ok and (use_nccl and from_host and rank != 0 or np.array_equal(got_cap, whole.cap.hashes))
+            free(h)
+        whole.close()
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=f"cuda:{local_rank}")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        shard_parity = bool(flag.item())
+        if not shard_parity:
+            raise SystemExit("bench.py: a rank's digests / the gathered cap differ from the single-GPU commit")
+        del full0, whole_digests
     launches0 = ctx.launch_count
     phase_acc.clear()
     sampler = ClockSampler(local_rank)
@@ -347,7 +438,13 @@ def main():
     launches = ctx.launch_count - launches0
     phases = {k: v / a.steps for k, v in phase_acc.items()}
     e2e_ms, _ = timed(True, a.steps)
+    e2e_cols_ms = None
+    if G == 1:
+        for i in range(2):
+            one_step_cols(page_sets[i])
+        e2e_cols_ms, _ = timed(True, a.steps, per_column=True)
     clocks = sampler.stop() if rank == 0 else None
+    prove_block = None if a.no_prove else run_prove_block(a, vx, ctx, dist, rank, local_rank, G)
 
     ms_per_step = total_ms / a.steps
     value = elems / (ms_per_step * 1e-3) / 1e6
@@ -427,7 +524,14 @@ def main():
                        "l2": f"inputs rotate over {N_INPUT_SETS} sets ({N_INPUT_SETS * elems * 8 / 1e6:.0f} MB) and each step streams a {8 * N * c / 1e6:.0f} MB LDE, both > 126 MB L2",
                        "elements": "n*c input trace elements per commit"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": (1 << cap) * 32,
-                    "ms_per_step": e2e_ms / a.steps},
+                    "ms_per_step": e2e_ms / a.steps, "source": "one pinned contiguous host buffer per rank",
+                    # the reference-side shape of the same call: c separately allocated pageable columns, no flatten
+                    "pageable_per_column": None if e2e_cols_ms is None else {
+                        "value": elems / (e2e_cols_ms / a.steps * 1e-3) / 1e6, "unit": UNIT,
+                        "ms_per_step": e2e_cols_ms / a.steps, "entry_point": "vx_commit_from_values_cols",
+                        "source": f"{c} separate pageable numpy allocations (plonky2's Vec<PolynomialValues>)"}},
+            "shard_parity": shard_parity,
+            "prove": prove_block,
             "gpu_launches": launches,
             "wall_ms_per_step": wall_ms / a.steps,
             "roofline": roofline,

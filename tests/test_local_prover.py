@@ -81,6 +81,24 @@ def test_workers_run_concurrently():
     assert sorted(seen) == [0, 1, 2]
 
 
+def test_workers_per_device_share_one_context_and_replica():
+    """workers_per_device = 2: four proofs in flight on two devices, ONE context and ONE bound circuit per device (the
+    context's lanes carry the concurrent calls)."""
+    FakeCtx.made.clear(); FakeSpec.binds.clear()
+    gate, seen = threading.Barrier(4, timeout=5), []
+
+    def rendezvous(circ, wires, pi):                         # completes only if four proofs are in flight at once
+        gate.wait()
+        seen.append(circ[1])
+        return wires
+    lp = LocalProver(devices=[0, 1], make_ctx=FakeCtx, prove_fn=rendezvous, workers_per_device=2)
+    assert lp.batch_prove(FakeSpec(), [(i, []) for i in range(4)]) == [0, 1, 2, 3]
+    assert sorted(seen) == [0, 0, 1, 1]
+    assert sorted(FakeCtx.made) == [0, 1] and sorted(FakeSpec.binds) == [0, 1]
+    with pytest.raises(ValueError):
+        LocalProver(devices=[0], make_ctx=FakeCtx, workers_per_device=0)
+
+
 def test_no_gpu_means_no_prover():
     import torch
     if torch.cuda.is_available():

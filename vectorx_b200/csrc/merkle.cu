@@ -92,8 +92,11 @@ GL_D void store_digest(u64* dst, const u64 s[12]) {
 // one thread per leaf: hash_or_noop(leaf) -> interleaved slot (or cap when the subtree is 1 leaf); state in registers.
 // LONG: the form for wide leaves on a full GPU -- 256-thread blocks, partial rounds in groups of 4, one barrier per
 // permutation to keep the warps of a block in the same code region (see POSEIDON_GROUP).
+#ifndef LEAF_LONG_MINB
+#define LEAF_LONG_MINB 4
+#endif
 template <bool COL_MAJOR, bool LONG>
-__global__ void __launch_bounds__(LONG ? POSEIDON_BLOCK_LONG : POSEIDON_BLOCK, 1024 / (LONG ? POSEIDON_BLOCK_LONG : POSEIDON_BLOCK))
+__global__ void __launch_bounds__(LONG ? POSEIDON_BLOCK_LONG : POSEIDON_BLOCK, LONG ? LEAF_LONG_MINB : 1024 / POSEIDON_BLOCK)
 leaf_hash_kernel(const u64* __restrict__ leaves, uint64_t stride, uint64_t N, uint32_t c, uint32_t sub_bits,
                  u64* __restrict__ digests, u64* __restrict__ cap) {
     constexpr int BLOCK = LONG ? POSEIDON_BLOCK_LONG : POSEIDON_BLOCK;
@@ -136,11 +139,13 @@ leaf_hash_kernel(const u64* __restrict__ leaves, uint64_t stride, uint64_t N, ui
 // columns are already transformed): absorb columns [col0, col1) of every leaf into the sponge state kept in `state`
 // (12 x N, lane-major so that a warp's accesses are contiguous).  col0 and every col1 < c are multiples of the rate, so a
 // chunk boundary is a permutation boundary of hash_no_pad; the launch with col1 == c writes the digests.
-__global__ void __launch_bounds__(POSEIDON_BLOCK, 1024 / POSEIDON_BLOCK) leaf_absorb_kernel(const u64* __restrict__ lde, uint64_t stride, uint64_t N,
-                                                                        uint32_t c, uint32_t col0, uint32_t col1,
-                                                                        u64* __restrict__ state, uint32_t sub_bits,
-                                                                        u64* __restrict__ digests, u64* __restrict__ cap) {
-    __shared__ u64 scratch[12 * POSEIDON_BLOCK];
+// (the long form carries the sponge state across the launch: 64 registers would spill, so it runs 3 blocks per SM)
+template <bool LONG>
+__global__ void __launch_bounds__(LONG ? POSEIDON_BLOCK_LONG : POSEIDON_BLOCK, LONG ? 3 : 1024 / POSEIDON_BLOCK)
+leaf_absorb_kernel(const u64* __restrict__ lde, uint64_t stride, uint64_t N, uint32_t c, uint32_t col0, uint32_t col1,
+                   u64* __restrict__ state, uint32_t sub_bits, u64* __restrict__ digests, u64* __restrict__ cap) {
+    constexpr int BLOCK = LONG ? POSEIDON_BLOCK_LONG : POSEIDON_BLOCK;
+    __shared__ u64 scratch[12 * BLOCK];
     uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= N) return;
     const u64* src = lde + row;
@@ -151,7 +156,12 @@ __global__ void __launch_bounds__(POSEIDON_BLOCK, 1024 / POSEIDON_BLOCK) leaf_ab
 #pragma unroll
         for (int i = 0; i < POSEIDON_RATE; i++)
             if (off + i < col1) s[i] = src[(uint64_t)(off + i) * stride];
-        poseidon_permute(s, scratch + threadIdx.x);
+        if (LONG) {
+            __syncthreads();
+            poseidon_permute<POSEIDON_GROUP_LONG, BLOCK>(s, scratch + threadIdx.x);
+        } else {
+            poseidon_permute(s, scratch + threadIdx.x);
+        }
     }
     if (col1 < c) {
 #pragma unroll
@@ -323,8 +333,13 @@ int32_t merkle_absorb_device(vx_ctx* ctx, const u64* lde, uint64_t stride, uint6
     const LeafPlan lp = leaf_plan(ctx, N);
     const int slot = ctx->absorb_count < vx_ctx::VX_MAX_ABSORB ? ctx->absorb_count++ : -1;
     if (slot >= 0) VX_CUDA(cudaEventRecord(ctx->absorb_ev[2 * slot], ctx->stream));
-    leaf_absorb_kernel<<<lp.blocks, lp.threads, 0, ctx->stream>>>(
-        lde, stride, N, c, col0, col1, state, log_N - cap_height, digests, cap);
+    // chunks of 8+ permutations per leaf on a full GPU: the long form of the sponge (see leaf_hash_kernel)
+    if (col1 - col0 >= 64 && lp.threads == POSEIDON_BLOCK && N / POSEIDON_BLOCK_LONG >= 8ULL * (uint64_t)ctx->sm_count)
+        leaf_absorb_kernel<true><<<(unsigned)(N / POSEIDON_BLOCK_LONG), POSEIDON_BLOCK_LONG, 0, ctx->stream>>>(
+            lde, stride, N, c, col0, col1, state, log_N - cap_height, digests, cap);
+    else
+        leaf_absorb_kernel<false><<<lp.blocks, lp.threads, 0, ctx->stream>>>(
+            lde, stride, N, c, col0, col1, state, log_N - cap_height, digests, cap);
     if (slot >= 0) VX_CUDA(cudaEventRecord(ctx->absorb_ev[2 * slot + 1], ctx->stream));
     VX_LAUNCH_COUNT(ctx, 1);
     VX_CUDA(cudaGetLastError());

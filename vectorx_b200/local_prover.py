@@ -49,13 +49,18 @@ class LocalProver:
     than once: each entry gets its own context (stream), which keeps one GPU busy across the host-side gaps of a proof."""
 
     def __init__(self, devices: Sequence[int] | None = None, *, make_ctx: Callable[[int], object] = Context,
-                 prove_fn: Callable = prove):
+                 prove_fn: Callable = prove, workers_per_device: int = 1):
         if devices is None:
             devices = device_list()           # the usable CUDA ordinals (a box may mix GPU generations)
             if len(devices) == 0:
                 raise RuntimeError("LocalProver: no sm_100-class GPU is visible (there is no CPU fallback)")
         if len(devices) == 0:
             raise ValueError("LocalProver: empty device list")
+        # workers_per_device > 1: that many worker threads share ONE context (and one resident circuit replica) per listed
+        # device -- the context's lanes run their calls side by side, which fills the host-side gaps of a proof
+        if workers_per_device < 1:
+            raise ValueError("LocalProver: workers_per_device must be >= 1")
+        self.workers_per_device = int(workers_per_device)
         self.devices = list(devices)
         self._make_ctx, self._prove_fn = make_ctx, prove_fn
         self._replicas: list[_Replica | None] = [None] * len(self.devices)
@@ -85,9 +90,12 @@ class LocalProver:
         errors: list[tuple[int, BaseException]] = []
         stop = threading.Event()
 
+        bind_lock = threading.Lock()
+
         def worker(slot: int):
             try:
-                circ = self._replica(slot).circuit(circuit)
+                with bind_lock:                          # workers of one device share its replica: bind it once
+                    circ = self._replica(slot).circuit(circuit)
             except BaseException as e:                   # noqa: BLE001 -- reported to the caller below
                 errors.append((-1, e))
                 stop.set()
@@ -106,8 +114,8 @@ class LocalProver:
                     stop.set()
                     return
 
-        n_workers = min(len(self.devices), len(inputs))
-        threads = [threading.Thread(target=worker, args=(s,), name=f"vx-prover-{self.devices[s]}") for s in range(n_workers)]
+        slots = [s for s in range(len(self.devices)) for _ in range(self.workers_per_device)][:len(inputs)]
+        threads = [threading.Thread(target=worker, args=(s,), name=f"vx-prover-{self.devices[s]}") for s in slots]
         for t in threads:
             t.start()
         for t in threads:
