@@ -48,9 +48,12 @@ def workload_name(w):
     return f"plonky2 from_values commit 2^{w['log_n']} rows x {w['cols']} cols, rate_bits={w['rate_bits']}, cap_height={w['cap_height']}"
 
 
-def gen_values(c, n, seed):
-    rng = np.random.default_rng(seed)
-    a = rng.integers(0, P, size=(c, n), dtype=np.uint64)       # uniform canonical field elements
+def gen_values(c, n, seed, col_lo=0, col_hi=None):
+    """uniform canonical field elements; column j depends on (seed, j) only, so a rank can generate just its own slice"""
+    col_hi = c if col_hi is None else col_hi
+    a = np.empty((col_hi - col_lo, n), dtype=np.uint64)
+    for j in range(col_lo, col_hi):
+        a[j - col_lo] = np.random.default_rng([seed, j]).integers(0, P, size=n, dtype=np.uint64)
     return a
 
 
@@ -285,7 +288,7 @@ def main():
     N = n << rate
     elems = n * c
     if G > 1:
-        assert G <= (1 << rate) and G <= (1 << cap), "coset sharding needs G <= 2^rate_bits and 2^cap_height"
+        assert G <= (1 << cap), "sharding needs whole cap subtrees per rank: G <= 2^cap_height"
     cpr = (c + G - 1) // G                     # columns per rank for the iNTT stage (last rank zero-padded)
     col_lo = rank * cpr
     col_hi = min(c, col_lo + cpr)
@@ -293,9 +296,8 @@ def main():
     # ---- inputs: N_INPUT_SETS different value matrices, pinned on the host and resident in HBM
     host_sets, dev_sets = [], []
     for s in range(N_INPUT_SETS):
-        full = gen_values(c, n, seed=0x5EED0001 + s)
         mine = np.zeros((cpr, n), dtype=np.uint64)
-        mine[: col_hi - col_lo] = full[col_lo:col_hi]
+        mine[: col_hi - col_lo] = gen_values(c, n, 0x5EED0001 + s, col_lo, col_hi)
         h = torch.from_numpy(mine.view(np.int64)).pin_memory()
         host_sets.append(h)
         dev_sets.append(h.to(f"cuda:{local_rank}"))

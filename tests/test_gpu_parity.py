@@ -257,10 +257,14 @@ def test_error_behaviour(ctx):
         b.leaves([16])                                      # out of range
 
 
-@pytest.mark.parametrize("shards", [2, 4, 8])
-def test_sharded_commit_matches_whole(ctx, shards):
-    """SURVEY 8e coset partition: the shards' leaves / digests / caps concatenate to the 1-GPU commit."""
-    c, log_n, rate, cap = 21, 9, 3, 4
+@pytest.mark.parametrize("shards,c,log_n,rate", [(2, 21, 9, 3), (4, 21, 9, 3), (8, 21, 9, 3),
+                                                 (16, 21, 9, 3),      # more shards than cosets: halves of a coset block
+                                                 (4, 9, 13, 1), (8, 9, 14, 1), (16, 5, 16, 1),     # STARK rate: folded blocks
+                                                 (8, 7, 10, 0), (4, 40, 12, 2)])
+def test_sharded_commit_matches_whole(ctx, shards, c, log_n, rate):
+    """SURVEY 8e coset partition: the shards' leaves / digests / caps concatenate to the 1-GPU commit -- whole cosets while
+    shards <= 2^rate_bits, parts of one coset's leaf block (transform of the folded coefficients) beyond that."""
+    cap = 4
     coeffs = oracle.random_field((c, 1 << log_n), seed=55)
     want = oracle.commit_from_coeffs(coeffs, rate, cap)
     N = (1 << log_n) << rate

@@ -50,11 +50,16 @@ class OracleEngine:
         rows = np.zeros((plan.leaves, plan.c), dtype=np.uint64)
         bits = plan.log_n
         rev = np.array([int(format(i, f"0{bits}b")[::-1], 2) if bits else 0 for i in range(n)])
+        part = n >> plan.fold_bits                            # fold_bits > 0: one part of ONE coset's leaf block
         for bi, rho in enumerate(plan.cosets):
             shift = G_GEN * pow(w_N, rho, P) % P
             for j in range(plan.c):
                 ev = self.o.fft(co[j], shift=shift)          # evaluations on shift * <w_n>, natural order
-                rows[bi * n: (bi + 1) * n, j] = ev[rev]       # leaf order inside the block
+                blk = ev[rev]                                 # leaf order inside the block
+                if plan.fold_bits:
+                    rows[:, j] = blk[plan.fold_index * part: (plan.fold_index + 1) * part]
+                else:
+                    rows[bi * n: (bi + 1) * n, j] = blk
         cap_loc_h = plan.cap_height - (plan.world.bit_length() - 1)
         digests, cap = self.o.merkle_new(rows, cap_loc_h)
         self._np(cap_out)[:] = cap
@@ -106,7 +111,8 @@ def _worker(rank, world, port, c, log_n, rate, cap_h, q):
         raise
 
 
-@pytest.mark.parametrize("world,c,log_n,rate,cap_h", [(2, 9, 5, 3, 4), (2, 5, 4, 1, 1), (4, 7, 4, 2, 2)])
+@pytest.mark.parametrize("world,c,log_n,rate,cap_h", [(2, 9, 5, 3, 4), (2, 5, 4, 1, 1), (4, 7, 4, 2, 2),
+                                                       (4, 6, 5, 1, 3)])      # more shards than cosets: folded blocks
 def test_sharded_commit_over_gloo(world, c, log_n, rate, cap_h):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -135,6 +141,9 @@ def test_shard_plan_validation():
     assert p.cosets == [6]                      # leaf block 3 = coset bitrev3(3) = 6
     assert ShardPlan(8, 7, 135, 16, 3, 4).col_hi == 135 and ShardPlan(8, 7, 135, 16, 3, 4).col_lo == 119
     assert ShardPlan(2, 1, 20, 10, 3, 4).cosets == [1, 5, 3, 7]
-    for bad in [(3, 0, 8, 4, 3, 4), (16, 0, 8, 4, 3, 4), (4, 0, 8, 4, 3, 1), (2, 2, 8, 4, 3, 4), (2, 0, 0, 4, 3, 4)]:
+    q = ShardPlan(8, 5, 2502, 18, 1, 4)         # rate_bits = 1 STARK trace on 8 GPUs: quarter blocks of the two cosets
+    assert q.fold_bits == 2 and q.fold_index == 1 and q.cosets == [1] and q.leaves == (1 << 19) // 8 and q.caps == 2
+    assert ShardPlan(16, 0, 8, 4, 3, 4).fold_bits == 1
+    for bad in [(3, 0, 8, 4, 3, 4), (32, 0, 8, 4, 3, 4), (4, 0, 8, 4, 3, 1), (2, 2, 8, 4, 3, 4), (2, 0, 0, 4, 3, 4)]:
         with pytest.raises(ValueError):
             ShardPlan(*bad)

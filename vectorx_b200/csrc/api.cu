@@ -349,7 +349,7 @@ static int32_t commit_run(vx_ctx* ctx, vx_batch* b, const ColSource& src, bool i
         if (is_values) VX_CHECK(intt_batch(ctx, work + off, b->coeffs.p + off, c1 - c0, b->log_n));
         if (nchunks == 1) EV(ctx, VX_EV_INTT);
         VX_CHECK(lde_batch(ctx, b->coeffs.p + off, b->lde.p + (size_t)c0 * N_loc, c1 - c0, b->log_n, b->rate_bits,
-                           b->blk_first, b->blk_count));
+                           b->blk_first, b->blk_count, b->fold_bits, b->fold_index));
         if (stream)
             VX_CHECK(merkle_absorb_device(ctx, b->lde.p, N_loc, N_loc, c, c0, c1, sponge.p, b->cap_height_loc(),
                                           b->digests.p, b->cap.p));
@@ -385,16 +385,14 @@ static int32_t commit_impl(vx_ctx* ctx, const ColSource& src, bool is_values, ui
     VX_REQUIRE(shard_count >= 1 && (shard_count & (shard_count - 1)) == 0 && shard_index < shard_count,
                "commit: bad shard %u of %u", shard_index, shard_count);
     uint32_t sbits = ilog2(shard_count);
-    VX_REQUIRE(sbits <= rate_bits && sbits <= cap_height,
-               "commit: %u shards need rate_bits >= %u and cap_height >= %u (whole cosets and whole cap subtrees per shard)",
-               shard_count, sbits, sbits);
+    VX_REQUIRE(sbits <= cap_height && sbits <= rate_bits + log_n,
+               "commit: %u shards need cap_height >= %u (whole cap subtrees per shard)", shard_count, sbits);
     VX_LANE(ctx);
     vx_batch* b = new (std::nothrow) vx_batch();
     if (!b) return VX_ENOMEM;
     b->ctx = ctx->root; b->c = c; b->log_n = log_n; b->rate_bits = rate_bits; b->cap_height = cap_height;
     b->hasher = hasher;
-    b->blk_count = (1u << rate_bits) >> sbits;
-    b->blk_first = shard_index * b->blk_count;
+    b->set_shard(shard_index, sbits);
     ctx->root->last_commit_lane.store(ctx->lane_index);
     int32_t r = commit_run(ctx, b, src, is_values, keep);
     if (r != VX_OK) {

@@ -176,6 +176,9 @@ struct vx_batch {
     vx_ctx* ctx;
     uint32_t c, log_n, rate_bits, cap_height;
     uint32_t blk_first, blk_count;      // leaf blocks (cosets) held: all 2^rate_bits unless sharded
+    // more shards than cosets: the shard holds sub-block fold_index of the 2^fold_bits equal parts of ONE coset's leaf
+    // block (blk_count == 1), computed as a 2^(log_n - fold_bits)-point transform of the folded coefficients (lde_batch)
+    uint32_t fold_bits = 0, fold_index = 0;
     uint32_t hasher = 0;                // VX_HASHER_*
     DevBuf coeffs;    // c x n
     DevBuf lde;       // c x N_loc column-major, leaf order
@@ -183,9 +186,14 @@ struct vx_batch {
     DevBuf cap;       // caps_loc x 4
     uint64_t n() const { return 1ULL << log_n; }
     uint64_t N() const { return 1ULL << (log_n + rate_bits); }
-    uint64_t N_loc() const { return (uint64_t)blk_count << log_n; }
-    uint64_t leaf_first() const { return (uint64_t)blk_first << log_n; }
-    uint32_t shard_bits() const { return rate_bits - ilog2(blk_count); }   // log2(number of shards)
+    uint64_t N_loc() const { return ((uint64_t)blk_count << log_n) >> fold_bits; }
+    uint64_t leaf_first() const { return ((uint64_t)blk_first << log_n) + (uint64_t)fold_index * (n() >> fold_bits); }
+    uint32_t shard_bits() const { return rate_bits - ilog2(blk_count) + fold_bits; }   // log2(number of shards)
+    // shard s of 2^sbits: whole cosets while there are enough of them, then equal parts of one coset
+    void set_shard(uint32_t s, uint32_t sbits) {
+        if (sbits <= rate_bits) { blk_count = (1u << rate_bits) >> sbits; blk_first = s * blk_count; fold_bits = fold_index = 0; }
+        else { fold_bits = sbits - rate_bits; blk_count = 1; blk_first = s >> fold_bits; fold_index = s & ((1u << fold_bits) - 1); }
+    }
     uint32_t cap_height_loc() const { return cap_height - shard_bits(); }
 };
 
@@ -243,9 +251,10 @@ int32_t ntt_dif_inplace(vx_ctx* ctx, u64* data, uint64_t count, uint32_t log_n, 
 int32_t intt_batch(vx_ctx* ctx, u64* work, u64* coeffs_out, uint32_t c, uint32_t log_n);
 // coefficients (c x n natural) -> LDE on coset g*<w_N>, leaf (bit-reversed) order, c x N column-major.
 // Only leaf blocks [blk_first, blk_first + blk_count) of the 2^rate_bits cosets are produced (a block
-// is one coset = n leaves); lde_out is c x (blk_count * n).
+// is one coset = n leaves); lde_out is c x (blk_count * n).  fold_bits > 0 (then blk_count == 1): only part fold_index
+// of the 2^fold_bits equal parts of that block, lde_out is c x (n >> fold_bits).
 int32_t lde_batch(vx_ctx* ctx, const u64* coeffs, u64* lde_out, uint32_t c, uint32_t log_n, uint32_t rate_bits,
-                  uint32_t blk_first, uint32_t blk_count);
+                  uint32_t blk_first, uint32_t blk_count, uint32_t fold_bits = 0, uint32_t fold_index = 0);
 // generic natural-order transform used by vx_ntt (tests, FRI layers)
 int32_t ntt_natural(vx_ctx* ctx, const u64* in, u64* out, uint32_t c, uint32_t log_n, bool inverse,
                     uint64_t coset_shift);

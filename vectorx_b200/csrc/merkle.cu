@@ -309,9 +309,9 @@ int32_t merkle_build_device(vx_ctx* ctx, const u64* leaves, bool col_major, uint
     VX_REQUIRE(c >= 1, "merkle: empty leaves");
     uint32_t sub_bits = log_N - cap_height;
     const LeafPlan lp = leaf_plan(ctx, N);
-    // the long form needs full 256-thread blocks on every SM and enough permutations per leaf to amortise its cold start
+    // the long form needs a full wave of 256-thread blocks and enough permutations per leaf to amortise its cold start
     const bool long_form = col_major && c >= 64 && lp.threads == POSEIDON_BLOCK &&
-                           N / POSEIDON_BLOCK_LONG >= 8ULL * (uint64_t)ctx->sm_count;
+                           N / POSEIDON_BLOCK_LONG >= 4ULL * (uint64_t)ctx->sm_count;
     if (long_form)
         leaf_hash_kernel<true, true><<<(unsigned)(N / POSEIDON_BLOCK_LONG), POSEIDON_BLOCK_LONG, 0, ctx->stream>>>(
             leaves, stride, N, c, sub_bits, digests, cap);
@@ -334,7 +334,7 @@ int32_t merkle_absorb_device(vx_ctx* ctx, const u64* lde, uint64_t stride, uint6
     const int slot = ctx->absorb_count < vx_ctx::VX_MAX_ABSORB ? ctx->absorb_count++ : -1;
     if (slot >= 0) VX_CUDA(cudaEventRecord(ctx->absorb_ev[2 * slot], ctx->stream));
     // chunks of 8+ permutations per leaf on a full GPU: the long form of the sponge (see leaf_hash_kernel)
-    if (col1 - col0 >= 64 && lp.threads == POSEIDON_BLOCK && N / POSEIDON_BLOCK_LONG >= 8ULL * (uint64_t)ctx->sm_count)
+    if (col1 - col0 >= 64 && lp.threads == POSEIDON_BLOCK && N / POSEIDON_BLOCK_LONG >= 3ULL * (uint64_t)ctx->sm_count)
         leaf_absorb_kernel<true><<<(unsigned)(N / POSEIDON_BLOCK_LONG), POSEIDON_BLOCK_LONG, 0, ctx->stream>>>(
             lde, stride, N, c, col0, col1, state, log_N - cap_height, digests, cap);
     else

@@ -481,11 +481,47 @@ __global__ void lde_scale_kernel(const u64* __restrict__ coeffs, u64* __restrict
     }
 }
 
+// Part q of the 2^kb equal parts of a coset's leaf block.  The leaves of a coset are the DIF (bit-reversed) output of the
+// n-point transform of x_m = c_m s^m, s = g w_N^rho: part q holds the outputs k = 2^kb k' + kappa, kappa = bitrev_kb(q), and
+//   X[2^kb k' + kappa] = sum_{m' < n'} ( sum_{j < 2^kb} x_{m' + j n'} w_n^{(m' + j n') kappa} ) w_{n'}^{m' k'},   n' = n / 2^kb,
+// i.e. the n'-point transform of the FOLDED sequence y_{m'} = sum_j c_{m' + j n'} t^{m' + j n'} with t = g w_N^{rho + 2^r kappa}
+// -- the evaluation of the polynomial on the smaller coset t <w_{n'}>.  A shard computes only its own part: 1 / 2^kb of the
+// transform work for one extra read of the coefficients.
+__global__ void lde_fold_kernel(const u64* __restrict__ coeffs, u64* __restrict__ out, uint32_t log_n, uint32_t kb,
+                                uint32_t rho_ext, uint32_t log_N, const u64* __restrict__ g_lo, const u64* __restrict__ g_hi,
+                                TwiddleView tw) {
+    const uint32_t log_np = log_n - kb;
+    const uint64_t mp = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (mp >> log_np) return;
+    const u64* src = coeffs + ((uint64_t)blockIdx.y << log_n);
+    u64 acc = 0;
+    for (uint32_t j = 0; j < (1u << kb); j++) {
+        const uint32_t m = (uint32_t)mp + (j << log_np);
+        u64 f = gl_mul_cc(__ldg(g_hi + (m >> 12)), __ldg(g_lo + (m & 4095)));
+        const u32 E = (m * rho_ext) << (32 - log_N);
+        if (E) f = gl_mul_cc(f, tw_pow_view(tw, E));
+        acc = gl_add_cc(acc, gl_mul_cc(src[m], f));
+    }
+    out[((uint64_t)blockIdx.y << log_np) + mp] = gl_canon(acc);
+}
+
 int32_t lde_batch(vx_ctx* ctx, const u64* coeffs, u64* lde_out, uint32_t c, uint32_t log_n, uint32_t rate_bits,
-                  uint32_t blk_first, uint32_t blk_count) {
+                  uint32_t blk_first, uint32_t blk_count, uint32_t fold_bits, uint32_t fold_index) {
     VX_REQUIRE(log_n <= 26 && log_n + rate_bits <= 32, "lde: 2^%u rows at rate_bits %u exceed the coset tables", log_n, rate_bits);
     VX_REQUIRE(blk_count >= 1 && blk_first + blk_count <= (1u << rate_bits), "lde: coset block range out of bounds");
     uint64_t n = 1ULL << log_n;
+    if (fold_bits) {
+        VX_REQUIRE(blk_count == 1 && fold_bits <= log_n && fold_index < (1u << fold_bits), "lde: bad sub-block %u of 2^%u", fold_index, fold_bits);
+        const uint32_t rho = rate_bits ? (uint32_t)bitrev_u64(blk_first, rate_bits) : 0;
+        const uint32_t kappa = (uint32_t)bitrev_u64(fold_index, fold_bits);
+        const uint32_t log_np = log_n - fold_bits;
+        dim3 grid((unsigned)(((1ULL << log_np) + 255) / 256), c);
+        lde_fold_kernel<<<grid, 256, 0, ctx->stream>>>(coeffs, lde_out, log_n, fold_bits, rho + (kappa << rate_bits),
+                                                       log_n + rate_bits, ctx->g_lo, ctx->g_hi, tw_view(ctx, false));
+        VX_LAUNCH_COUNT(ctx, 1);
+        VX_CUDA(cudaGetLastError());
+        return ntt_dif_inplace(ctx, lde_out, c, log_np, false);
+    }
     if (log_n >= 13) {
         // first pass fused with the coset scaling: reads the coefficients once per coset (L2-resident), writes the LDE
         PassTables tb;

@@ -103,9 +103,8 @@ extern "C" int32_t vx_shard_group_create(vx_ctx* ctx, uint32_t rank, uint32_t wo
     VX_REQUIRE(world >= 1 && world <= VX_MAX_SHARDS && (world & (world - 1)) == 0 && rank < world,
                "vx_shard_group_create: bad rank %u of %u", rank, world);
     const uint32_t sbits = ilog2(world);
-    VX_REQUIRE(sbits <= rate_bits && sbits <= cap_height,
-               "vx_shard_group_create: %u shards need rate_bits >= %u and cap_height >= %u (whole cosets and whole cap "
-               "subtrees per shard)", world, sbits, sbits);
+    VX_REQUIRE(sbits <= cap_height && sbits <= rate_bits + log_n,
+               "vx_shard_group_create: %u shards need cap_height >= %u (whole cap subtrees per shard)", world, sbits);
     VX_REQUIRE(c >= 1 && c < 16384 && log_n >= 1 && log_n <= 26 && log_n + rate_bits <= 30 && cap_height <= log_n + rate_bits,
                "vx_shard_group_create: shape out of range");
     CtxGuard g(ctx);
@@ -312,7 +311,7 @@ static int32_t shard_commit_run_stream(vx_shard_group* s, vx_batch* b, const u64
             VX_CHECK(wait_flags(s, 2 + j, q, 1));                           // also orders the reuse of the gather buffer
             if (c0 >= c1) continue;
             VX_CHECK(lde_batch(ctx, s->base + (size_t)c0 * n, b->lde.p + (size_t)c0 * N_loc, c1 - c0, b->log_n, b->rate_bits,
-                               b->blk_first, b->blk_count));
+                               b->blk_first, b->blk_count, b->fold_bits, b->fold_index));
             const uint32_t upto = c1 == s->c ? s->c : (c1 / 8) * 8;
             if (upto > absorbed) {
                 VX_CHECK(merkle_absorb_device(ctx, b->lde.p, N_loc, N_loc, s->c, absorbed, upto, sponge.p, b->cap_height_loc(),
@@ -381,7 +380,7 @@ static int32_t shard_commit_run(vx_shard_group* s, vx_batch* b, const u64* value
         if (k) VX_CHECK(wait_flags(s, 0, r0, r1 - r0));
         if (c0 >= c1) continue;
         VX_CHECK(lde_batch(ctx, k ? s->base + (size_t)c0 * n : mine.p, b->lde.p + (size_t)c0 * N_loc, c1 - c0, b->log_n,
-                           b->rate_bits, b->blk_first, b->blk_count));
+                           b->rate_bits, b->blk_first, b->blk_count, b->fold_bits, b->fold_index));
     }
     VX_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[0], 0));        // my own block has landed (and `mine` is free)
     VX_CUDA(cudaMemcpyAsync(b->coeffs.p, s->base, b->coeffs.bytes, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -416,8 +415,7 @@ extern "C" int32_t vx_shard_commit_from_values(vx_shard_group* s, const uint64_t
     const uint32_t sbits = ilog2(s->world);
     s->ctx->last_commit_lane.store(0);
     b->ctx = s->ctx; b->c = s->c; b->log_n = s->log_n; b->rate_bits = s->rate_bits; b->cap_height = s->cap_height;
-    b->blk_count = (1u << s->rate_bits) >> sbits;
-    b->blk_first = s->rank * b->blk_count;
+    b->set_shard(s->rank, sbits);
     s->epoch++;
     int32_t r = shard_commit_run(s, b, (const u64*)values_local, (u64*)cap_all_out);
     if (r != VX_OK) {

@@ -1,7 +1,9 @@
 """One commit sharded over G GPUs (coset partition) -- host-side plan and driver.
 
-Rank g of G (G a power of two, G <= 2^rate_bits, G <= 2^cap_height) ends up owning leaf block
-[g N/G, (g+1) N/G): whole LDE cosets and whole cap subtrees, so no interior hashing crosses GPUs.
+Rank g of G (G a power of two, G <= 2^cap_height) ends up owning leaf block [g N/G, (g+1) N/G): whole cap subtrees, so no
+interior hashing crosses GPUs.  While G <= 2^rate_bits the block is a set of whole LDE cosets; beyond that (a rate_bits = 1
+STARK trace on 8 GPUs) it is one of the 2^fold_bits equal parts of ONE coset's leaf block, which is itself the transform of
+the coefficients folded onto a smaller coset (csrc/ntt.cu lde_fold_kernel) -- still no exchange beyond the coefficients.
 
     1. iNTT of this rank's column slice                       (no communication)
     2. all-gather of the coefficients, 8 n c bytes in total    (the ONE exchange step; NCCL over NVLink)
@@ -38,9 +40,8 @@ class ShardPlan:
             raise ValueError(f"world size {g} is not a power of two")
         if not 0 <= self.rank < g:
             raise ValueError(f"rank {self.rank} out of range for world size {g}")
-        if g > (1 << self.rate_bits) or g > (1 << self.cap_height):
-            raise ValueError(f"{g} shards need rate_bits >= {g.bit_length() - 1} and cap_height >= {g.bit_length() - 1} "
-                             "(whole cosets and whole cap subtrees per shard)")
+        if g > (1 << self.cap_height) or g > (1 << (self.rate_bits + self.log_n)):
+            raise ValueError(f"{g} shards need cap_height >= {g.bit_length() - 1} (whole cap subtrees per shard)")
         if self.c < 1:
             raise ValueError("empty batch")
 
@@ -83,8 +84,22 @@ class ShardPlan:
         return self.rank * self.caps
 
     @property
+    def fold_bits(self) -> int:
+        """log2 of the parts one coset's leaf block is split into (0 while every rank owns whole cosets)"""
+        return max(0, (self.world.bit_length() - 1) - self.rate_bits)
+
+    @property
+    def fold_index(self) -> int:
+        """which part of its coset's leaf block this rank owns"""
+        return self.rank & ((1 << self.fold_bits) - 1)
+
+    @property
     def cosets(self):
-        """natural coset indices rho (LDE point i = 2^rate_bits k + rho) of the leaf blocks this rank owns, in leaf order"""
+        """natural coset indices rho (LDE point i = 2^rate_bits k + rho) of the leaf blocks this rank owns (or owns a part
+        of, when fold_bits > 0), in leaf order"""
+        if self.fold_bits:
+            b = self.rank >> self.fold_bits
+            return [int(format(b, f"0{self.rate_bits}b")[::-1], 2) if self.rate_bits else 0]
         per = (1 << self.rate_bits) // self.world
         out = []
         for b in range(self.rank * per, (self.rank + 1) * per):
