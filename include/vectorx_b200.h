@@ -110,8 +110,10 @@ int32_t vx_commit_from_values_cols(vx_ctx* ctx, const uint64_t* const* cols, uin
 int32_t vx_commit_from_coeffs_cols(vx_ctx* ctx, const uint64_t* const* coeffs, uint32_t c, uint32_t log_n,
                                    uint32_t rate_bits, uint32_t cap_height, vx_batch** out);
 /* Multi-GPU sharding of one commit (coset partition): shard s of S (S a power of two,
- * S <= 2^rate_bits, S <= 2^cap_height) holds leaves [s*N/S, (s+1)*N/S) -- whole cosets of the LDE
- * and whole cap subtrees -- computed from ALL c coefficient columns with no further communication.
+ * S <= 2^cap_height) holds leaves [s*N/S, (s+1)*N/S) -- whole cap subtrees; whole cosets of the LDE while
+ * S <= 2^rate_bits, and beyond that (a rate_bits = 1 STARK trace on 8 GPUs) one of the equal parts of ONE coset's leaf
+ * block, which is the transform of the coefficients folded onto a smaller coset -- computed from ALL c coefficient
+ * columns with no further communication.
  * Leaf indices passed to vx_batch_leaves / vx_batch_merkle_paths on a shard are LOCAL (0 .. N/S);
  * vx_batch_cap returns the shard's 2^cap_height/S cap entries. */
 int32_t vx_commit_from_coeffs_shard(vx_ctx* ctx, const uint64_t* coeffs, uint32_t c, uint32_t log_n,
@@ -142,6 +144,9 @@ int32_t vx_shard_commit_from_values(vx_shard_group* g, const uint64_t* values_lo
 const uint64_t* vx_shard_group_coeffs_device(const vx_shard_group* g);
 uint32_t vx_shard_group_cols_per_rank(const vx_shard_group* g);
 void vx_shard_group_free(vx_shard_group* g);
+/* how long (ms) a rank waits for a peer's contribution before vx_shard_commit_from_values fails with VX_ECUDA (default
+ * ~2000; 0 restores the default).  After a timeout the group is unusable -- free it and create a new one. */
+int32_t vx_shard_group_set_timeout(vx_shard_group* g, uint32_t ms);
 /* out[0] = first global leaf held, out[1] = leaves held, out[2] = cap entries held */
 int32_t vx_batch_shard(const vx_batch* b, uint64_t out[3]);
 void vx_batch_free(vx_batch* b);

@@ -47,6 +47,7 @@ SIGNATURES = {
     "vx_shard_group_coeffs_device": (vp, [vp]),
     "vx_shard_group_cols_per_rank": (c_u32, [vp]),
     "vx_shard_group_free": (None, [vp]),
+    "vx_shard_group_set_timeout": (c_i32, [vp, c_u32]),
     "vx_commit_from_values": (c_i32, [vp, vp, c_u32, c_u32, c_u32, c_u32, ctypes.POINTER(vp)]),
     "vx_commit_from_coeffs": (c_i32, [vp, vp, c_u32, c_u32, c_u32, c_u32, ctypes.POINTER(vp)]),
     "vx_commit_from_values_cols": (c_i32, [vp, ctypes.POINTER(vp), c_u32, c_u32, c_u32, c_u32, ctypes.POINTER(vp)]),

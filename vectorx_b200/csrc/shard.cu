@@ -23,7 +23,7 @@
 
 #define VX_MAX_SHARDS 16
 #define VX_FLAG_PHASES 16          // 0: whole coefficient slice, 1: cap entries, 2 + j: sub-block j of a streamed commit
-#define VX_MAX_SUB 4               // sub-blocks per rank slice in the streamed form
+#define VX_MAX_SUB 12              // sub-blocks per rank slice in the streamed form (flag phases 2 .. 2 + VX_MAX_SUB - 1)
 
 struct PeerTable {
     u64* base[VX_MAX_SHARDS];
@@ -40,6 +40,9 @@ struct vx_shard_group {
     bool ipc_opened[VX_MAX_SHARDS] = {};
     bool connected = false;
     uint32_t epoch = 0;
+    cudaEvent_t push_ev[VX_MAX_SUB] = {};      // streamed form: sub-block j of the OWN slice has been pushed (aux stream)
+    long long timeout_cycles = 4000000000LL;   // a peer wait gives up after this many SM cycles (~2 s)
+    bool poisoned = false;             // a wait timed out: flags / epochs of the group are no longer consistent
     uint32_t* counter = nullptr;       // device: CTAs done (last-CTA election of the push kernel)
     int* err_host = nullptr;           // pinned + mapped: set by a wait that timed out
     int* err_dev = nullptr;
@@ -132,9 +135,11 @@ extern "C" int32_t vx_shard_group_create(vx_ctx* ctx, uint32_t rank, uint32_t wo
         *s->err_host = 0;
         ok = cudaHostGetDevicePointer((void**)&s->err_dev, s->err_host, 0) == cudaSuccess;
     }
+    for (auto& e : s->push_ev) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaStreamSynchronize(ctx->stream) == cudaSuccess;
     if (!ok) {
         vx_set_error("vx_shard_group_create: %s", cudaGetErrorString(cudaGetLastError()));
+        for (auto& e : s->push_ev) if (e) cudaEventDestroy(e);
         if (s->counter) cudaFree(s->counter);
         if (s->err_host) cudaFreeHost(s->err_host);
         cudaFree(s->base);
@@ -211,8 +216,16 @@ extern "C" void vx_shard_group_free(vx_shard_group* s) {
         if (s->counter) cudaFree(s->counter);
         if (s->err_host) cudaFreeHost(s->err_host);
         if (s->base) cudaFree(s->base);
+        for (auto& e : s->push_ev) if (e) cudaEventDestroy(e);
     }
     delete s;
+}
+
+/* how long a rank waits for a peer's contribution before the commit fails (default ~2 s); ms == 0 restores the default */
+extern "C" int32_t vx_shard_group_set_timeout(vx_shard_group* s, uint32_t ms) {
+    VX_REQUIRE(s, "vx_shard_group_set_timeout: NULL argument");
+    s->timeout_cycles = ms ? (long long)ms * 2000000LL : 4000000000LL;       // ~2 GHz SM clock
+    return VX_OK;
 }
 
 /* this rank's gather buffer (world * cols_per_rank x n coefficients, valid after a commit) */
@@ -239,13 +252,14 @@ static int32_t push_block(vx_shard_group* s, cudaStream_t stream, const u64* src
 static int32_t wait_flags(vx_shard_group* s, uint32_t phase, uint32_t first, uint32_t count) {
     vx_ctx* ctx = s->ctx;
     const uint32_t* flags = reinterpret_cast<const uint32_t*>(s->base + s->flag_off) + phase * VX_MAX_SHARDS + first;
-    peer_wait_kernel<<<1, count, 0, ctx->stream>>>(flags, s->epoch, 4000000000LL, s->err_dev);
+    peer_wait_kernel<<<1, count, 0, ctx->stream>>>(flags, s->epoch, s->timeout_cycles, s->err_dev);
     VX_LAUNCH_COUNT(ctx, 1);
     VX_CUDA(cudaGetLastError());
     return VX_OK;
 }
 
 #define EV(ctx, i) VX_CUDA(cudaEventRecord((ctx)->ev[i], (ctx)->stream))
+#define VX_STREAM_EXCHANGE_BYTES (256ULL << 20)
 
 // Streamed form (the default): the rank's slice is split into sub-blocks of 8 / 16 / the rest columns.
 //   producer (copy stream + aux stream): copy sub-block j in -> iNTT -> push to every rank's gather buffer, flag (2 + j, rank)
@@ -268,14 +282,21 @@ static int32_t shard_commit_run_stream(vx_shard_group* s, vx_batch* b, const u64
     VX_CHECK(sponge.alloc((size_t)12 * N_loc * sizeof(u64), ctx->stream));
     EV(ctx, VX_EV_START);
     ctx->absorb_count = 0;
-    // sub-block boundaries in local columns.  Only the slice that comes first in sponge order (rank 0's) is needed early:
-    // it travels as 8 / 16 / the rest columns; every other slice is consumed long after it has landed and stays whole
-    // (one transform launch instead of three).
+    // sub-block boundaries in local columns.  Only the slice that comes first in sponge order (rank 0's) is needed early;
+    // every other slice is consumed after it has landed and stays whole (one transform launch).  Small slices (values
+    // from the host, the copy is what hides): rank 0's travels as 8 / 16 / the rest columns.  Big slices (the exchange
+    // itself takes milliseconds -- a STARK trace): rank 0's travels in up to VX_MAX_SUB equal parts, so that every rank's
+    // hashing follows the arrival of the slice instead of waiting for all of it.
+    const bool big = (uint64_t)s->cpr * n * sizeof(u64) * (s->world - 1) >= VX_STREAM_EXCHANGE_BYTES;
     auto sub_edges = [&](uint32_t q, uint32_t* sub) -> uint32_t {
         uint32_t k = 0;
         sub[0] = 0;
-        if (q == 0)
-            for (uint32_t edge = 8, step = 16; k + 1 < VX_MAX_SUB - 1 && edge < s->cpr; edge += step, step *= 2) sub[++k] = edge;
+        if (q == 0 && big) {
+            const uint32_t part = ((s->cpr + VX_MAX_SUB - 1) / VX_MAX_SUB + 7) / 8 * 8;
+            for (uint32_t edge = part; k + 1 < VX_MAX_SUB && edge < s->cpr; edge += part) sub[++k] = edge;
+        } else if (q == 0) {
+            for (uint32_t edge = 8, step = 16; k + 1 < 3 && edge < s->cpr; edge += step, step *= 2) sub[++k] = edge;
+        }
         sub[++k] = s->cpr;
         return k;
     };
@@ -296,6 +317,7 @@ static int32_t shard_commit_run_stream(vx_shard_group* s, vx_batch* b, const u64
         ctx->stream = main_stream;
         VX_CHECK(r);
         VX_CHECK(push_block(s, ctx->aux_stream, mine.p + off, cnt, (uint64_t)s->rank * s->cpr * n + off, 2 + j));
+        VX_CUDA(cudaEventRecord(s->push_ev[j], ctx->aux_stream));
     }
     VX_CUDA(cudaEventRecord(ctx->copy_ev[VX_MAX_SUB], ctx->aux_stream));  // `work` / `mine` free after this
     EV(ctx, VX_EV_STAGED);
@@ -308,7 +330,10 @@ static int32_t shard_commit_run_stream(vx_shard_group* s, vx_batch* b, const u64
         for (uint32_t j = 0; j < nq; j++) {
             const uint32_t g0 = q * s->cpr + qsub[j], g1 = q * s->cpr + qsub[j + 1];
             const uint32_t c0 = g0 < s->c ? g0 : s->c, c1 = g1 < s->c ? g1 : s->c;
-            VX_CHECK(wait_flags(s, 2 + j, q, 1));                           // also orders the reuse of the gather buffer
+            // the own slice is ordered by an event (a spin on a flag raised by another stream of the SAME device would need
+            // the two streams to run concurrently, which serialising tools -- ncu, compute-sanitizer -- do not grant)
+            if (q == s->rank) VX_CUDA(cudaStreamWaitEvent(ctx->stream, s->push_ev[j], 0));
+            else VX_CHECK(wait_flags(s, 2 + j, q, 1));                      // also orders the reuse of the gather buffer
             if (c0 >= c1) continue;
             VX_CHECK(lde_batch(ctx, s->base + (size_t)c0 * n, b->lde.p + (size_t)c0 * N_loc, c1 - c0, b->log_n, b->rate_bits,
                                b->blk_first, b->blk_count, b->fold_bits, b->fold_index));
@@ -333,8 +358,10 @@ static int32_t shard_commit_run_stream(vx_shard_group* s, vx_batch* b, const u64
     VX_CUDA(cudaStreamSynchronize(ctx->stream));
     VX_CUDA(cudaStreamSynchronize(ctx->aux_stream));
     if (*s->err_host) {
-        vx_set_error("vx_shard_commit_from_values: timed out waiting for rank %d (peer missing or failed)", *s->err_host - 1);
+        vx_set_error("vx_shard_commit_from_values: timed out waiting for rank %d (peer missing or failed); the group's flags "
+                     "are no longer consistent: free it and create a new one", *s->err_host - 1);
         *s->err_host = 0;
+        s->poisoned = true;
         return VX_ECUDA;
     }
     return VX_OK;
@@ -346,7 +373,10 @@ static int32_t shard_commit_run(vx_shard_group* s, vx_batch* b, const u64* value
     // hashing, 6.58 -> 6.25 ms end to end.  On 4 / 8 ranks the slices are short, a rank hashes only N/4 / N/8 leaves per
     // column and the extra launches cost more than the copy they hide (3.64 -> 3.71 ms, 2.55 -> 2.79 ms); values already
     // in HBM: whole-slice launches are faster (5.92 against 6.05 ms on 2 ranks).
-    const bool want_stream = s->world <= 2 && !vx_is_device_ptr(values_local);
+    // Big slices (>= VX_STREAM_EXCHANGE_BYTES received per rank, e.g. 4.6 GB for a 2^18 x 2502 trace on 8 ranks): the
+    // exchange takes milliseconds and only the pipeline hides it, whatever the rank count and wherever the values live.
+    const bool big = (uint64_t)s->cpr * b->n() * sizeof(u64) * (s->world - 1) >= VX_STREAM_EXCHANGE_BYTES;
+    const bool want_stream = (s->world <= 2 && !vx_is_device_ptr(values_local)) || (s->world > 1 && big);
     if (want_stream && s->c > 4) return shard_commit_run_stream(s, b, values_local, cap_all_out);
     ctx->absorb_count = 0;
     const uint64_t n = b->n(), N_loc = b->N_loc();
@@ -394,8 +424,10 @@ static int32_t shard_commit_run(vx_shard_group* s, vx_batch* b, const u64* value
         VX_CHECK(copy_out(ctx, cap_all_out, s->base + s->cap_off, ((size_t)4 << s->cap_height) * sizeof(u64)));
     VX_CUDA(cudaStreamSynchronize(ctx->stream));
     if (*s->err_host) {
-        vx_set_error("vx_shard_commit_from_values: timed out waiting for rank %d (peer missing or failed)", *s->err_host - 1);
+        vx_set_error("vx_shard_commit_from_values: timed out waiting for rank %d (peer missing or failed); the group's flags "
+                     "are no longer consistent: free it and create a new one", *s->err_host - 1);
         *s->err_host = 0;
+        s->poisoned = true;
         return VX_ECUDA;
     }
     return VX_OK;
@@ -409,6 +441,7 @@ extern "C" int32_t vx_shard_commit_from_values(vx_shard_group* s, const uint64_t
     VX_REQUIRE(s && values_local && out, "vx_shard_commit_from_values: NULL argument");
     *out = nullptr;
     VX_REQUIRE(s->connected, "vx_shard_commit_from_values: group is not connected to its peers");
+    VX_REQUIRE(!s->poisoned, "vx_shard_commit_from_values: an earlier commit on this group timed out; free it and create a new one");
     CtxGuard g(s->ctx);
     vx_batch* b = new (std::nothrow) vx_batch();
     if (!b) return VX_ENOMEM;
