@@ -293,11 +293,20 @@ def main():
     col_lo = rank * cpr
     col_hi = min(c, col_lo + cpr)
 
+    # ---- which global columns this rank transforms (contiguous slice, or the library's interleaved parts for big slices)
+    col_map = [j if j < c else -1 for j in range(col_lo, col_lo + cpr)]
+    group = None
+    if G > 1 and a.exchange == "peer":
+        from vectorx_b200.sharded import PeerGroup, ShardPlan
+        group = PeerGroup(ctx, ShardPlan(G, rank, c, log_n, rate, cap), dist)
+        col_map = group.column_map()
     # ---- inputs: N_INPUT_SETS different value matrices, pinned on the host and resident in HBM
     host_sets, dev_sets = [], []
     for s in range(N_INPUT_SETS):
         mine = np.zeros((cpr, n), dtype=np.uint64)
-        mine[: col_hi - col_lo] = gen_values(c, n, 0x5EED0001 + s, col_lo, col_hi)
+        for i, gcol in enumerate(col_map):
+            if gcol >= 0:
+                mine[i] = gen_values(c, n, 0x5EED0001 + s, gcol, gcol + 1)[0]
         h = torch.from_numpy(mine.view(np.int64)).pin_memory()
         host_sets.append(h)
         dev_sets.append(h.to(f"cuda:{local_rank}"))
@@ -322,8 +331,6 @@ def main():
         if use_nccl:
             engine, comm = DeviceEngine(ctx), TorchComm(dist)
             bufs = {"coeff_mine": coeff_mine, "coeff_all": coeff_all, "cap_loc": cap_loc, "cap_all": cap_all}
-        else:
-            group = PeerGroup(ctx, plan, dist)
 
     def one_step(src, from_host):
         """One commit. src: this rank's (cpr, n) values (host-pinned or device). Returns nothing; cap -> cap_host."""

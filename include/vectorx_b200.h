@@ -144,6 +144,15 @@ int32_t vx_shard_commit_from_values(vx_shard_group* g, const uint64_t* values_lo
 const uint64_t* vx_shard_group_coeffs_device(const vx_shard_group* g);
 uint32_t vx_shard_group_cols_per_rank(const vx_shard_group* g);
 void vx_shard_group_free(vx_shard_group* g);
+/* Which columns a rank owns in the iNTT / exchange stage.  Small slices: rank r owns the contiguous global columns
+ * [r*cpr, (r+1)*cpr) (cpr = ceil(c / world)).  Big slices (>= 256 MB received per rank, e.g. a 2^18 x 2502 STARK trace on
+ * 8 GPUs): every slice is cut into equal parts and the parts of all ranks ALTERNATE in global column order, so that the
+ * exchange streams behind the leaf hashing instead of every rank waiting for rank 0's slice.  vx_shard_group_column_map
+ * writes, for each of this rank's cpr local columns, the global column the caller must place there (UINT32_MAX =
+ * padding); vx_shard_group_set_layout overrides the choice (0 = by size, 1 = contiguous, 2 = interleaved; same value on
+ * every rank, before the first commit). */
+int32_t vx_shard_group_set_layout(vx_shard_group* g, uint32_t mode);
+int32_t vx_shard_group_column_map(const vx_shard_group* g, uint32_t* global_col_out);
 /* how long (ms) a rank waits for a peer's contribution before vx_shard_commit_from_values fails with VX_ECUDA (default
  * ~2000; 0 restores the default).  After a timeout the group is unusable -- free it and create a new one. */
 int32_t vx_shard_group_set_timeout(vx_shard_group* g, uint32_t ms);

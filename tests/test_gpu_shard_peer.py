@@ -56,17 +56,28 @@ def test_peer_group_world1_shapes(ctx, c, log_n, rate, cap):
     g.close()
 
 
-@pytest.mark.parametrize("world", [2, 4])
-def test_peer_group_same_process(world):
+@pytest.mark.parametrize("world,layout,c,log_n,rate", [(2, 0, 37, 12, 3), (4, 0, 37, 12, 3),
+                                                       (2, 2, 37, 12, 3),      # interleaved parts, whole cosets
+                                                       (2, 2, 300, 13, 1),     # interleaved parts, many of them
+                                                       (4, 2, 100, 13, 1),     # interleaved + folded leaf blocks (4 > 2^1)
+                                                       (8, 2, 135, 13, 3), (8, 0, 70, 13, 1)])
+def test_peer_group_same_process(world, layout, c, log_n, rate):
+    """Ranks as threads of one process (peer access mapped directly).  layout 2 forces the interleaved column ownership
+    that big slices use (the parts of all ranks alternate in sponge order), also together with leaf blocks that are
+    parts of a coset (more ranks than cosets)."""
     if _device_count() < world:
         pytest.skip(f"needs {world} GPUs in one process")
-    c, log_n, rate, cap = 37, 12, 3, 4
+    cap = 4
     cols = oracle.random_field((c, 1 << log_n), seed=5)
     want = oracle.commit_from_values(cols, rate, cap)
     ctxs = [vx.Context(d) for d in range(world)]
     plans = [ShardPlan(world, r, c, log_n, rate, cap) for r in range(world)]
     groups = [PeerGroup(ctxs[r], plans[r]) for r in range(world)]
+    for g in groups:
+        g.set_layout(layout)
     PeerGroup.connect_local(groups)
+    owned = sorted(gc for g in groups for gc in g.column_map() if gc >= 0)
+    assert owned == list(range(c))                        # every column has exactly one owner
     caps = [np.zeros((1 << cap, 4), dtype=np.uint64) for _ in range(world)]
     errs = []
 
@@ -75,9 +86,7 @@ def test_peer_group_same_process(world):
 
     def run(r):
         try:
-            p = plans[r]
-            mine = np.zeros((p.cols_per_rank, 1 << log_n), dtype=np.uint64)
-            mine[: p.col_hi - p.col_lo] = cols[p.col_lo:p.col_hi]
+            mine = groups[r].local_slice(cols)
             for it in range(2):
                 h = groups[r].commit_from_values(mine, caps[r])
                 if it == 0:
@@ -88,7 +97,8 @@ def test_peer_group_same_process(world):
                 lo, hi = r * N // world, (r + 1) * N // world
                 per = want["digests"].shape[0] // world
                 shard_ok[r] = (np.array_equal(leaves, want["leaves"][lo:hi])
-                               and np.array_equal(digests, want["digests"][r * per:(r + 1) * per]))
+                               and np.array_equal(digests, want["digests"][r * per:(r + 1) * per])
+                               and np.array_equal(b.polynomials, want["coeffs"]))
                 b.close()
         except Exception as e:                            # noqa: BLE001
             errs.append(e)

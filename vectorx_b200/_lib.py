@@ -48,6 +48,8 @@ SIGNATURES = {
     "vx_shard_group_cols_per_rank": (c_u32, [vp]),
     "vx_shard_group_free": (None, [vp]),
     "vx_shard_group_set_timeout": (c_i32, [vp, c_u32]),
+    "vx_shard_group_set_layout": (c_i32, [vp, c_u32]),
+    "vx_shard_group_column_map": (c_i32, [vp, u32p]),
     "vx_commit_from_values": (c_i32, [vp, vp, c_u32, c_u32, c_u32, c_u32, ctypes.POINTER(vp)]),
     "vx_commit_from_coeffs": (c_i32, [vp, vp, c_u32, c_u32, c_u32, c_u32, ctypes.POINTER(vp)]),
     "vx_commit_from_values_cols": (c_i32, [vp, ctypes.POINTER(vp), c_u32, c_u32, c_u32, c_u32, ctypes.POINTER(vp)]),

@@ -43,6 +43,7 @@ struct vx_shard_group {
     cudaEvent_t push_ev[VX_MAX_SUB] = {};      // streamed form: sub-block j of the OWN slice has been pushed (aux stream)
     long long timeout_cycles = 4000000000LL;   // a peer wait gives up after this many SM cycles (~2 s)
     bool poisoned = false;             // a wait timed out: flags / epochs of the group are no longer consistent
+    int layout_mode = 0;               // 0 = by size, 1 = contiguous column slices, 2 = interleaved (see group_interleaved)
     uint32_t* counter = nullptr;       // device: CTAs done (last-CTA election of the push kernel)
     int* err_host = nullptr;           // pinned + mapped: set by a wait that timed out
     int* err_dev = nullptr;
@@ -261,6 +262,61 @@ static int32_t wait_flags(vx_shard_group* s, uint32_t phase, uint32_t first, uin
 #define EV(ctx, i) VX_CUDA(cudaEventRecord((ctx)->ev[i], (ctx)->stream))
 #define VX_STREAM_EXCHANGE_BYTES (256ULL << 20)
 
+// ---- which columns a rank transforms and pushes (the iNTT stage) ------------------------------------------------------
+// Contiguous (small slices): rank q owns global columns [q cpr, (q + 1) cpr).  The leaf sponge absorbs columns in global
+// order, so every rank needs rank 0's slice first and rank 0's NVLink egress paces everybody: fine when the exchange is
+// microseconds, not when it is milliseconds (a 2^18 x 2502 trace on 8 ranks: 4.6 GB per rank).
+// Interleaved (big slices): every slice is cut into the same <= VX_MAX_SUB parts and part j of rank q is global columns
+// [G e_j + q w_j, G e_j + (q + 1) w_j) (e_j = first local column of part j, w_j its width).  In global order the parts of
+// all ranks alternate, every link carries what every consumer needs next, and the exchange streams behind the hashing.
+static bool group_big(const vx_shard_group* s) {
+    return (uint64_t)s->cpr * ((uint64_t)1 << s->log_n) * sizeof(u64) * (s->world - 1) >= VX_STREAM_EXCHANGE_BYTES;
+}
+static bool group_interleaved(const vx_shard_group* s) {
+    return s->world > 1 && (s->layout_mode == 2 || (s->layout_mode == 0 && group_big(s)));
+}
+// local column edges of the parts of rank q's slice; returns the number of parts
+static uint32_t group_sub_edges(const vx_shard_group* s, uint32_t q, uint32_t* sub) {
+    uint32_t k = 0;
+    sub[0] = 0;
+    if (group_interleaved(s)) {
+        const uint32_t part = ((s->cpr + VX_MAX_SUB - 1) / VX_MAX_SUB + 7) / 8 * 8;
+        for (uint32_t edge = part; k + 1 < VX_MAX_SUB && edge < s->cpr; edge += part) sub[++k] = edge;
+    } else if (q == 0) {
+        // only the slice that comes first in sponge order is needed early: 8 / 16 / the rest columns
+        for (uint32_t edge = 8, step = 16; k + 1 < 3 && edge < s->cpr; edge += step, step *= 2) sub[++k] = edge;
+    }
+    sub[++k] = s->cpr;
+    return k;
+}
+// first global column of part j of rank q
+static uint32_t group_global_col(const vx_shard_group* s, uint32_t q, const uint32_t* sub, uint32_t j) {
+    return group_interleaved(s) ? s->world * sub[j] + q * (sub[j + 1] - sub[j]) : q * s->cpr + sub[j];
+}
+
+/* 0 = choose by size (default), 1 = contiguous column slices, 2 = interleaved parts; every rank of a group must use the
+ * same value, set before the first commit */
+extern "C" int32_t vx_shard_group_set_layout(vx_shard_group* s, uint32_t mode) {
+    VX_REQUIRE(s && mode <= 2, "vx_shard_group_set_layout: bad argument");
+    s->layout_mode = (int)mode;
+    return VX_OK;
+}
+/* global column index of each of this rank's cols_per_rank local columns (UINT32_MAX: padding beyond c): which columns of
+ * the trace the caller places in `values_local` */
+extern "C" int32_t vx_shard_group_column_map(const vx_shard_group* s, uint32_t* global_col_out) {
+    VX_REQUIRE(s && global_col_out, "vx_shard_group_column_map: NULL argument");
+    uint32_t sub[VX_MAX_SUB + 1];
+    const uint32_t nsub = group_sub_edges(s, s->rank, sub);
+    for (uint32_t j = 0; j < nsub; j++) {
+        const uint32_t g0 = group_global_col(s, s->rank, sub, j);
+        for (uint32_t i = sub[j]; i < sub[j + 1]; i++) {
+            const uint32_t g = g0 + (i - sub[j]);
+            global_col_out[i] = g < s->c ? g : UINT32_MAX;
+        }
+    }
+    return VX_OK;
+}
+
 // Streamed form (the default): the rank's slice is split into sub-blocks of 8 / 16 / the rest columns.
 //   producer (copy stream + aux stream): copy sub-block j in -> iNTT -> push to every rank's gather buffer, flag (2 + j, rank)
 //   consumer (context stream): global columns in sponge order -- for rank q = 0..G-1, sub-block j: wait for its flag,
@@ -282,26 +338,9 @@ static int32_t shard_commit_run_stream(vx_shard_group* s, vx_batch* b, const u64
     VX_CHECK(sponge.alloc((size_t)12 * N_loc * sizeof(u64), ctx->stream));
     EV(ctx, VX_EV_START);
     ctx->absorb_count = 0;
-    // sub-block boundaries in local columns.  Only the slice that comes first in sponge order (rank 0's) is needed early;
-    // every other slice is consumed after it has landed and stays whole (one transform launch).  Small slices (values
-    // from the host, the copy is what hides): rank 0's travels as 8 / 16 / the rest columns.  Big slices (the exchange
-    // itself takes milliseconds -- a STARK trace): rank 0's travels in up to VX_MAX_SUB equal parts, so that every rank's
-    // hashing follows the arrival of the slice instead of waiting for all of it.
-    const bool big = (uint64_t)s->cpr * n * sizeof(u64) * (s->world - 1) >= VX_STREAM_EXCHANGE_BYTES;
-    auto sub_edges = [&](uint32_t q, uint32_t* sub) -> uint32_t {
-        uint32_t k = 0;
-        sub[0] = 0;
-        if (q == 0 && big) {
-            const uint32_t part = ((s->cpr + VX_MAX_SUB - 1) / VX_MAX_SUB + 7) / 8 * 8;
-            for (uint32_t edge = part; k + 1 < VX_MAX_SUB && edge < s->cpr; edge += part) sub[++k] = edge;
-        } else if (q == 0) {
-            for (uint32_t edge = 8, step = 16; k + 1 < 3 && edge < s->cpr; edge += step, step *= 2) sub[++k] = edge;
-        }
-        sub[++k] = s->cpr;
-        return k;
-    };
     uint32_t sub[VX_MAX_SUB + 1];
-    const uint32_t nsub = sub_edges(s->rank, sub);
+    const uint32_t nsub = group_sub_edges(s, s->rank, sub);
+    const bool inter = group_interleaved(s);
     // ---- producer
     VX_CUDA(cudaEventRecord(ctx->copy_free, ctx->stream));                 // allocations above are stream-ordered
     VX_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_free, 0));
@@ -322,21 +361,30 @@ static int32_t shard_commit_run_stream(vx_shard_group* s, vx_batch* b, const u64
     VX_CUDA(cudaEventRecord(ctx->copy_ev[VX_MAX_SUB], ctx->aux_stream));  // `work` / `mine` free after this
     EV(ctx, VX_EV_STAGED);
     EV(ctx, VX_EV_INTT);
-    // ---- consumer
+    // ---- consumer: parts in GLOBAL column order (contiguous: rank-major; interleaved: part-major)
     uint32_t absorbed = 0;
+    uint32_t qsub[VX_MAX_SHARDS][VX_MAX_SUB + 1], nq[VX_MAX_SHARDS], max_parts = 0;
     for (uint32_t q = 0; q < s->world; q++) {
-        uint32_t qsub[VX_MAX_SUB + 1];
-        const uint32_t nq = sub_edges(q, qsub);
-        for (uint32_t j = 0; j < nq; j++) {
-            const uint32_t g0 = q * s->cpr + qsub[j], g1 = q * s->cpr + qsub[j + 1];
+        nq[q] = group_sub_edges(s, q, qsub[q]);
+        if (nq[q] > max_parts) max_parts = nq[q];
+    }
+    const uint32_t outer = inter ? max_parts : s->world, inner = inter ? s->world : max_parts;
+    for (uint32_t a = 0; a < outer; a++) {
+        for (uint32_t bb = 0; bb < inner; bb++) {
+            const uint32_t q = inter ? bb : a, j = inter ? a : bb;
+            if (j >= nq[q]) continue;
+            const uint32_t g0 = group_global_col(s, q, qsub[q], j), g1 = g0 + (qsub[q][j + 1] - qsub[q][j]);
             const uint32_t c0 = g0 < s->c ? g0 : s->c, c1 = g1 < s->c ? g1 : s->c;
             // the own slice is ordered by an event (a spin on a flag raised by another stream of the SAME device would need
             // the two streams to run concurrently, which serialising tools -- ncu, compute-sanitizer -- do not grant)
             if (q == s->rank) VX_CUDA(cudaStreamWaitEvent(ctx->stream, s->push_ev[j], 0));
             else VX_CHECK(wait_flags(s, 2 + j, q, 1));                      // also orders the reuse of the gather buffer
             if (c0 >= c1) continue;
-            VX_CHECK(lde_batch(ctx, s->base + (size_t)c0 * n, b->lde.p + (size_t)c0 * N_loc, c1 - c0, b->log_n, b->rate_bits,
+            const u64* src = s->base + ((size_t)q * s->cpr + qsub[q][j]) * n;
+            VX_CHECK(lde_batch(ctx, src, b->lde.p + (size_t)c0 * N_loc, c1 - c0, b->log_n, b->rate_bits,
                                b->blk_first, b->blk_count, b->fold_bits, b->fold_index));
+            VX_CUDA(cudaMemcpyAsync(b->coeffs.p + (size_t)c0 * n, src, (size_t)(c1 - c0) * n * sizeof(u64),
+                                    cudaMemcpyDeviceToDevice, ctx->stream));
             const uint32_t upto = c1 == s->c ? s->c : (c1 / 8) * 8;
             if (upto > absorbed) {
                 VX_CHECK(merkle_absorb_device(ctx, b->lde.p, N_loc, N_loc, s->c, absorbed, upto, sponge.p, b->cap_height_loc(),
@@ -345,7 +393,6 @@ static int32_t shard_commit_run_stream(vx_shard_group* s, vx_batch* b, const u64
             }
         }
     }
-    VX_CUDA(cudaMemcpyAsync(b->coeffs.p, s->base, b->coeffs.bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     EV(ctx, VX_EV_LDE);
     EV(ctx, VX_EV_LEAF);
     VX_CHECK(merkle_levels_device(ctx, N_loc, b->cap_height_loc(), b->digests.p, b->cap.p));
@@ -375,8 +422,7 @@ static int32_t shard_commit_run(vx_shard_group* s, vx_batch* b, const u64* value
     // in HBM: whole-slice launches are faster (5.92 against 6.05 ms on 2 ranks).
     // Big slices (>= VX_STREAM_EXCHANGE_BYTES received per rank, e.g. 4.6 GB for a 2^18 x 2502 trace on 8 ranks): the
     // exchange takes milliseconds and only the pipeline hides it, whatever the rank count and wherever the values live.
-    const bool big = (uint64_t)s->cpr * b->n() * sizeof(u64) * (s->world - 1) >= VX_STREAM_EXCHANGE_BYTES;
-    const bool want_stream = (s->world <= 2 && !vx_is_device_ptr(values_local)) || (s->world > 1 && big);
+    const bool want_stream = (s->world <= 2 && !vx_is_device_ptr(values_local)) || group_interleaved(s);
     if (want_stream && s->c > 4) return shard_commit_run_stream(s, b, values_local, cap_all_out);
     ctx->absorb_count = 0;
     const uint64_t n = b->n(), N_loc = b->N_loc();

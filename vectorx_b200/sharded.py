@@ -185,6 +185,29 @@ class PeerGroup:
             table = np.frombuffer(b"".join(gathered), dtype=np.uint8).copy()
             check(self.lib.vx_shard_group_connect_ipc(self._h, table.ctypes.data), "vx_shard_group_connect_ipc")
 
+    def set_layout(self, mode: int):
+        """0 = by size (default), 1 = contiguous column slices, 2 = interleaved parts; same on every rank, before the
+        first commit"""
+        self.check(self.lib.vx_shard_group_set_layout(self._h, mode), "vx_shard_group_set_layout")
+
+    def column_map(self):
+        """global column index of each of this rank's cols_per_rank local columns (-1 = padding): the columns of the
+        trace that make up `values_local`"""
+        import numpy as np
+        out = np.zeros(self.plan.cols_per_rank, dtype=np.uint32)
+        self.check(self.lib.vx_shard_group_column_map(self._h, out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32))),
+                   "vx_shard_group_column_map")
+        return [(-1 if int(g) == 0xFFFFFFFF else int(g)) for g in out]
+
+    def local_slice(self, full):
+        """this rank's (cols_per_rank, n) slice of the full (c, n) value matrix, per column_map()"""
+        import numpy as np
+        mine = np.zeros((self.plan.cols_per_rank, full.shape[1]), dtype=np.uint64)
+        for i, g in enumerate(self.column_map()):
+            if g >= 0:
+                mine[i] = full[g]
+        return mine
+
     @staticmethod
     def connect_local(groups):
         """all ranks in this process: map each other's buffers directly (peer access)"""
