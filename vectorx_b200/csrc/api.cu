@@ -43,9 +43,13 @@ void DevBuf::release() {
 // ------------------------------------------------------------------------------------------------ context
 // streams and events of one lane
 static int32_t lane_create_streams(vx_ctx* l) {
-    VX_CUDA(cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking));
-    VX_CUDA(cudaStreamCreateWithFlags(&l->copy_stream, cudaStreamNonBlocking));
-    VX_CUDA(cudaStreamCreateWithFlags(&l->aux_stream, cudaStreamNonBlocking));
+    // the side streams feed the main one (uploads; the producer half of a sharded commit): their kernels go first when
+    // the block scheduler has a choice, otherwise a GPU full of hashing CTAs starves the exchange its peers wait for
+    int prio_lo = 0, prio_hi = 0;
+    VX_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    VX_CUDA(cudaStreamCreateWithPriority(&l->stream, cudaStreamNonBlocking, prio_lo));
+    VX_CUDA(cudaStreamCreateWithPriority(&l->copy_stream, cudaStreamNonBlocking, prio_hi));
+    VX_CUDA(cudaStreamCreateWithPriority(&l->aux_stream, cudaStreamNonBlocking, prio_hi));
     for (int i = 0; i < VX_NUM_PHASE_EVENTS; i++) VX_CUDA(cudaEventCreate(&l->ev[i]));
     for (auto& e : l->absorb_ev) VX_CUDA(cudaEventCreate(&e));
     for (auto& e : l->copy_ev) VX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));

@@ -121,13 +121,15 @@ __global__ void inner_table_kernel(u64* __restrict__ tab, TwiddleView tw) {
     const uint32_t q = threadIdx.x >> 4, r = threadIdx.x & 15;
     tab[threadIdx.x] = gl_canon(tw_pow_view(tw, (r * (__brev(q) >> 28)) << 24));      // w_256^e = W^(e << 24)
 }
-// tab[b][m] = g^m w_N^(rho_b m), rho_b = bitrev_r(blk_first + b)
+// tab[b][m] = g^m w_N^(rho_b m), rho_b = bitrev_r(blk_first + b) -- or rho_b = rho_explicit (one block: the folded cosets of
+// lde_fold_kernel, whose exponent rho + 2^r kappa does not fit r bits)
 __global__ void scale_table_kernel(u64* __restrict__ tab, uint32_t log_n, uint32_t rate_bits, uint32_t blk_first,
-                                   const u64* __restrict__ g_lo, const u64* __restrict__ g_hi, TwiddleView tw) {
+                                   const u64* __restrict__ g_lo, const u64* __restrict__ g_hi, TwiddleView tw,
+                                   uint32_t rho_explicit, bool use_explicit) {
     const uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (m >> log_n) return;
     const uint32_t b = blockIdx.y;
-    const uint32_t rho = rate_bits ? (__brev(blk_first + b) >> (32 - rate_bits)) : 0;
+    const uint32_t rho = use_explicit ? rho_explicit : (rate_bits ? (__brev(blk_first + b) >> (32 - rate_bits)) : 0);
     u64 f = gl_mul_cc(__ldg(g_hi + (m >> 12)), __ldg(g_lo + (m & 4095)));
     const u32 E = ((u32)m * rho) << (32 - (log_n + rate_bits));
     if (E) f = gl_mul_cc(f, tw_pow_view(tw, E));
@@ -169,17 +171,21 @@ static int32_t outer_table(vx_ctx* ctx, uint32_t log_M, bool inverse, const u64*
     *out = p;
     return VX_OK;
 }
+// rho_ext != UINT32_MAX: the one-block table of the folded coset with exponent rho_ext (see lde_fold_kernel)
 static int32_t scale_table(vx_ctx* ctx, uint32_t log_n, uint32_t rate_bits, uint32_t blk_first, uint32_t blk_count,
-                           const u64** out) {
+                           const u64** out, uint32_t rho_ext = UINT32_MAX) {
     *out = nullptr;
     if (((uint64_t)blk_count << log_n) > (1ULL << NTT_SCALE_MAX_LOG)) return VX_OK;
-    const uint64_t key = (2ULL << 60) | ((uint64_t)blk_count << 32) | ((uint64_t)blk_first << 16) | (rate_bits << 8) | log_n;
+    const bool ext = rho_ext != UINT32_MAX;
+    const uint64_t key = ext ? ((3ULL << 60) | ((uint64_t)rho_ext << 16) | (rate_bits << 8) | log_n)
+                             : ((2ULL << 60) | ((uint64_t)blk_count << 32) | ((uint64_t)blk_first << 16) | (rate_bits << 8) | log_n);
     std::lock_guard<std::mutex> lk(ctx->root->ntt_cache_mu);
     if ((*out = cache_find(ctx, key))) return VX_OK;
     u64* p;
     VX_CHECK(cache_add(ctx, key, ((size_t)blk_count << log_n) * sizeof(u64), &p));
     dim3 grid((unsigned)(((1ULL << log_n) + 255) / 256), blk_count);
-    scale_table_kernel<<<grid, 256, 0, ctx->stream>>>(p, log_n, rate_bits, blk_first, ctx->g_lo, ctx->g_hi, tw_view(ctx, false));
+    scale_table_kernel<<<grid, 256, 0, ctx->stream>>>(p, log_n, rate_bits, blk_first, ctx->g_lo, ctx->g_hi, tw_view(ctx, false),
+                                                      ext ? rho_ext : 0u, ext);
     VX_CUDA(cudaGetLastError());
     VX_CUDA(cudaStreamSynchronize(ctx->stream));
     *out = p;
@@ -487,22 +493,30 @@ __global__ void lde_scale_kernel(const u64* __restrict__ coeffs, u64* __restrict
 // i.e. the n'-point transform of the FOLDED sequence y_{m'} = sum_j c_{m' + j n'} t^{m' + j n'} with t = g w_N^{rho + 2^r kappa}
 // -- the evaluation of the polynomial on the smaller coset t <w_{n'}>.  A shard computes only its own part: 1 / 2^kb of the
 // transform work for one extra read of the coefficients.
+// `scale` (t^m, m < n; one coalesced load and one multiplication per coefficient) or, for shapes without a table, the
+// two-level g / W tables.
 __global__ void lde_fold_kernel(const u64* __restrict__ coeffs, u64* __restrict__ out, uint32_t log_n, uint32_t kb,
-                                uint32_t rho_ext, uint32_t log_N, const u64* __restrict__ g_lo, const u64* __restrict__ g_hi,
-                                TwiddleView tw) {
+                                uint32_t rho_ext, uint32_t log_N, const u64* __restrict__ scale,
+                                const u64* __restrict__ g_lo, const u64* __restrict__ g_hi, TwiddleView tw) {
     const uint32_t log_np = log_n - kb;
     const uint64_t mp = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (mp >> log_np) return;
     const u64* src = coeffs + ((uint64_t)blockIdx.y << log_n);
-    u64 acc = 0;
+    GlAcc acc;
+    gl_acc_init(acc, 0);
     for (uint32_t j = 0; j < (1u << kb); j++) {
         const uint32_t m = (uint32_t)mp + (j << log_np);
-        u64 f = gl_mul_cc(__ldg(g_hi + (m >> 12)), __ldg(g_lo + (m & 4095)));
-        const u32 E = (m * rho_ext) << (32 - log_N);
-        if (E) f = gl_mul_cc(f, tw_pow_view(tw, E));
-        acc = gl_add_cc(acc, gl_mul_cc(src[m], f));
+        u64 f;
+        if (scale) {
+            f = __ldg(scale + m);
+        } else {
+            f = gl_mul_cc(__ldg(g_hi + (m >> 12)), __ldg(g_lo + (m & 4095)));
+            const u32 E = (m * rho_ext) << (32 - log_N);
+            if (E) f = gl_mul_cc(f, tw_pow_view(tw, E));
+        }
+        gl_acc_mad(acc, src[m], f);                      // lazy dot product: one reduction per output
     }
-    out[((uint64_t)blockIdx.y << log_np) + mp] = gl_canon(acc);
+    out[((uint64_t)blockIdx.y << log_np) + mp] = gl_canon(gl_acc_reduce(acc));
 }
 
 int32_t lde_batch(vx_ctx* ctx, const u64* coeffs, u64* lde_out, uint32_t c, uint32_t log_n, uint32_t rate_bits,
@@ -515,9 +529,12 @@ int32_t lde_batch(vx_ctx* ctx, const u64* coeffs, u64* lde_out, uint32_t c, uint
         const uint32_t rho = rate_bits ? (uint32_t)bitrev_u64(blk_first, rate_bits) : 0;
         const uint32_t kappa = (uint32_t)bitrev_u64(fold_index, fold_bits);
         const uint32_t log_np = log_n - fold_bits;
+        const uint32_t rho_ext = rho + (kappa << rate_bits);
+        const u64* scale = nullptr;
+        VX_CHECK(scale_table(ctx, log_n, rate_bits, 0, 1, &scale, rho_ext));
         dim3 grid((unsigned)(((1ULL << log_np) + 255) / 256), c);
-        lde_fold_kernel<<<grid, 256, 0, ctx->stream>>>(coeffs, lde_out, log_n, fold_bits, rho + (kappa << rate_bits),
-                                                       log_n + rate_bits, ctx->g_lo, ctx->g_hi, tw_view(ctx, false));
+        lde_fold_kernel<<<grid, 256, 0, ctx->stream>>>(coeffs, lde_out, log_n, fold_bits, rho_ext, log_n + rate_bits, scale,
+                                                       ctx->g_lo, ctx->g_hi, tw_view(ctx, false));
         VX_LAUNCH_COUNT(ctx, 1);
         VX_CUDA(cudaGetLastError());
         return ntt_dif_inplace(ctx, lde_out, c, log_np, false);
