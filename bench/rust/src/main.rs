@@ -4,6 +4,8 @@
 //! the commit: the byte-level pin of the CUDA path against the real prover, and the published CPU number for BASELINE.md.
 //!
 //! usage: refcheck <values.bin> <out.bin> [repeats]
+//!        refcheck --hash-pad                 prints PoseidonHash::hash_pad(&[]) (the domain-separator digest that
+//!                                            CircuitBuilder::build hashes into circuit_digest) as 4 decimal u64
 //! values.bin: u32 c, u32 log_n, u32 rate_bits, u32 cap_height, then c * 2^log_n u64 (column-major, little endian)
 //! out.bin:    2^cap_height * 4 u64 cap, then for each probe index (0, 1, N/2, N-1): the leaf row (c u64) and its
 //!             Merkle path ((log2 N - cap_height) * 4 u64)
@@ -15,6 +17,8 @@ use plonky2::field::goldilocks_field::GoldilocksField as F;
 use plonky2::field::polynomial::PolynomialValues;
 use plonky2::field::types::{Field, PrimeField64};
 use plonky2::fri::oracle::PolynomialBatch;
+use plonky2::hash::poseidon::PoseidonHash;
+use plonky2::plonk::config::Hasher;
 use plonky2::plonk::config::PoseidonGoldilocksConfig as C;
 use plonky2::util::timing::TimingTree;
 
@@ -28,6 +32,12 @@ fn read_u32(f: &mut File) -> anyhow::Result<u32> {
 
 fn main() -> anyhow::Result<()> {
     let args: Vec<String> = std::env::args().collect();
+    if args.len() == 2 && args[1] == "--hash-pad" {
+        let h = <PoseidonHash as Hasher<F>>::hash_pad(&[]);
+        let v: Vec<String> = h.elements.iter().map(|e| e.to_canonical_u64().to_string()).collect();
+        println!("{}", v.join(" "));
+        return Ok(());
+    }
     anyhow::ensure!(args.len() >= 3, "usage: refcheck <values.bin> <out.bin> [repeats]");
     let repeats: usize = args.get(3).map(|s| s.parse()).transpose()?.unwrap_or(3);
     let mut f = File::open(&args[1])?;
