@@ -37,6 +37,7 @@ static void two_level(u64 base, unsigned lo_bits, unsigned hi_count, std::vector
 
 static TwiddleView tw_view(vx_ctx* ctx, bool inverse);
 __global__ void inner_table_kernel(u64* __restrict__ tab, TwiddleView tw);
+static int32_t ntt_kernel_attributes();           // dynamic shared memory limits of the pipelined passes
 
 int32_t ntt_module_init(vx_ctx* ctx) {
     std::vector<u64> lo, hi;
@@ -70,7 +71,7 @@ int32_t ntt_module_init(vx_ctx* ctx) {
     inner_table_kernel<<<1, 256, 0, ctx->stream>>>(ctx->inner_inv, tw_view(ctx, true));
     VX_CUDA(cudaGetLastError());
     VX_CUDA(cudaStreamSynchronize(ctx->stream));
-    return VX_OK;
+    return ntt_kernel_attributes();
 }
 
 void ntt_module_destroy(vx_ctx* ctx) {
@@ -387,6 +388,96 @@ __global__ void __launch_bounds__(256, NTT_FINAL_MINB) ntt_final4096_kernel(u64*
     for (int k = 0; k < 16; k++) base[threadIdx.x + 256 * k] = gl_canon(o[k]);
 }
 
+// ---- the same pass as a persistent, double-buffered pipeline on the bulk-copy engine (TMA) ---------------------------------
+// A CTA walks over chunks blockIdx.x, blockIdx.x + gridDim.x, ...  While it transforms chunk i, the 32 KB of chunk i + 1
+// are already in flight (cp.async.bulk global -> shared, completion on an mbarrier) and the results of chunk i - 1 drain
+// (cp.async.bulk shared -> global, bulk group): loads, stores and their address arithmetic leave the instruction stream and
+// the DRAM latency that the one-shot kernel exposes once per CTA is hidden behind the butterflies.
+GL_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+GL_D void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+GL_D void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+GL_D void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+GL_D void bulk_load(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+GL_D void bulk_store(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+#define NTT_TMA_SMEM (2 * 32768 + (4096 + 256) * 8)
+template <bool INV>
+__global__ void __launch_bounds__(256, 2) ntt_final4096_tma_kernel(u64* __restrict__ data, uint32_t chunks, uint32_t F,
+                                                                   const u64* __restrict__ full12) {
+    extern __shared__ __align__(128) unsigned char ntt_smraw[];
+    u64* tile0 = reinterpret_cast<u64*>(ntt_smraw);                 // linear 4096-element tiles: load target, then store source
+    u64* tile1 = reinterpret_cast<u64*>(ntt_smraw + 32768);
+    u64* sm = reinterpret_cast<u64*>(ntt_smraw + 65536);            // padded working copy
+    __shared__ uint64_t mbar[2];
+    if (threadIdx.x == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const uint32_t r1 = ((F - 1) & 3) + 1;                  // first group takes F mod 4 bits (or 4)
+    uint32_t chunk = blockIdx.x;
+    if (threadIdx.x == 0 && chunk < chunks) {
+        mbar_expect_tx(&mbar[0], 32768);
+        bulk_load(tile0, data + ((uint64_t)chunk << 12), 32768, &mbar[0]);
+    }
+    for (uint32_t it = 0; chunk < chunks; chunk += gridDim.x, it++) {
+        u64* tile = (it & 1) ? tile1 : tile0;
+        u64* other = (it & 1) ? tile0 : tile1;
+        const uint32_t next = chunk + gridDim.x;
+        if (threadIdx.x == 0 && next < chunks) {
+            // `other` is the source of the store issued one iteration ago: it may be overwritten once that store has read it
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            mbar_expect_tx(&mbar[(it & 1) ^ 1], 32768);
+            bulk_load(other, data + ((uint64_t)next << 12), 32768, &mbar[(it & 1) ^ 1]);
+        }
+        mbar_wait(&mbar[it & 1], (it >> 1) & 1);
+        uint32_t rem = F - r1;
+        switch (r1) {
+            case 1: ntt_smem_group<1, INV, true>(tile, sm, rem, full12); break;
+            case 2: ntt_smem_group<2, INV, true>(tile, sm, rem, full12); break;
+            case 3: ntt_smem_group<3, INV, true>(tile, sm, rem, full12); break;
+            default: ntt_smem_group<4, INV, true>(tile, sm, rem, full12); break;
+        }
+        __syncthreads();
+        while (rem) {
+            rem -= 4;
+            ntt_smem_group<4, INV, false>(nullptr, sm, rem, full12);
+            __syncthreads();
+        }
+#pragma unroll
+        for (int k = 0; k < 16; k++) tile[threadIdx.x + 256 * k] = gl_canon(sm[NTT_PAD(threadIdx.x + 256 * k)]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy writes -> visible to the copy engine
+        __syncthreads();
+        if (threadIdx.x == 0) bulk_store(data + ((uint64_t)chunk << 12), tile, 32768);
+    }
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+static int32_t ntt_kernel_attributes() {
+    VX_CUDA(cudaFuncSetAttribute(ntt_final4096_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NTT_TMA_SMEM));
+    VX_CUDA(cudaFuncSetAttribute(ntt_final4096_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NTT_TMA_SMEM));
+    return VX_OK;
+}
+
 // transforms are spread over grid.y x grid.z (count must factor as gy * gz with gy <= 65535)
 static int32_t grid_yz(uint64_t count, uint64_t* gy, uint64_t* gz) {
     *gy = count; *gz = 1;
@@ -424,8 +515,21 @@ int32_t ntt_dif_inplace(vx_ctx* ctx, u64* data, uint64_t count, uint32_t log_n, 
     uint64_t total = count << log_n;
     if ((total & 4095) == 0) {
         VX_REQUIRE((total >> 12) < (1ULL << 31), "ntt: too many blocks");
-        if (inverse) ntt_final4096_kernel<true><<<(unsigned)(total >> 12), 256, 0, ctx->stream>>>(data, rem, tw.full12);
-        else ntt_final4096_kernel<false><<<(unsigned)(total >> 12), 256, 0, ctx->stream>>>(data, rem, tw.full12);
+        const uint64_t chunks = total >> 12;
+        // Measured (profiles/r02_ntt_ab.md): the pipelined form is CORRECT but slower here -- 0.52 against 0.43 ms for the
+        // final pass of the config-1 LDE.  The pass is bound by the ALU pipe (83 % of its issue bound), not by memory
+        // latency, and two 64 KB-staged CTAs per SM (16 warps) feed that pipe worse than four one-shot CTAs (32 warps).
+        // It stays in the tree behind this switch (make EXTRA=-DNTT_FINAL_TMA=1) for shapes / parts where HBM is the bound.
+#ifndef NTT_FINAL_TMA
+#define NTT_FINAL_TMA 0
+#endif
+        if (NTT_FINAL_TMA && chunks >= 4ULL * (uint64_t)ctx->sm_count) {
+            // enough chunks to keep a two-CTA-per-SM persistent grid busy: the pipelined form
+            const unsigned grid = 2u * (unsigned)ctx->sm_count;
+            if (inverse) ntt_final4096_tma_kernel<true><<<grid, 256, NTT_TMA_SMEM, ctx->stream>>>(data, (uint32_t)chunks, rem, tw.full12);
+            else ntt_final4096_tma_kernel<false><<<grid, 256, NTT_TMA_SMEM, ctx->stream>>>(data, (uint32_t)chunks, rem, tw.full12);
+        } else if (inverse) ntt_final4096_kernel<true><<<(unsigned)chunks, 256, 0, ctx->stream>>>(data, rem, tw.full12);
+        else ntt_final4096_kernel<false><<<(unsigned)chunks, 256, 0, ctx->stream>>>(data, rem, tw.full12);
         VX_LAUNCH_COUNT(ctx, 1);
         VX_CUDA(cudaGetLastError());
         return VX_OK;
