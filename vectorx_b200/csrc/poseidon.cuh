@@ -157,7 +157,9 @@ GL_D void poseidon_partial_rounds_grouped(u64 s[12]) {
 // through different regions G = 1 / 2 / 4 / 6 / 11 hash the config-1 leaves in 8.68 / 8.13 / 9.23 / 10.85 / 10.17 ms.  G = 2 is
 // the default; the long leaf sponge uses G = 4 in 256-thread blocks that re-align their warps with one barrier per
 // permutation (7.99 ms) -- short kernels (one or two permutations per thread) run the big body with a cold cache and lose.
+#ifndef POSEIDON_GROUP
 #define POSEIDON_GROUP 2
+#endif
 #define POSEIDON_GROUP_LONG 4
 #define POSEIDON_BLOCK_LONG 256
 
