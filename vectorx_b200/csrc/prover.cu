@@ -76,7 +76,10 @@ GL_D void sts_u64(uint32_t addr, u64 v) { asm volatile("st.shared.u64 [%0], %1;"
 // 12 register numbers from two operand words
 #define QREGS12(w0, w1, k) (((k) < 8 ? (uint32_t)((w0) >> (8 * (k))) : (uint32_t)((w1) >> (8 * ((k) - 8)))) & 0xffu)
 
-__global__ void __launch_bounds__(QBLOCK) quotient_kernel(const QuotParams p) {
+#ifndef QUOT_MINB
+#define QUOT_MINB 5            // 96 registers: 4.97 ms at 2^16 rows; 114 registers (no bound) 5.26 ms, 80 registers 5.02 ms
+#endif
+__global__ void __launch_bounds__(QBLOCK, QUOT_MINB) quotient_kernel(const QuotParams p) {
     extern __shared__ u64 qsmem[];
     u64* prog_s = qsmem;                                   // [QCHUNK]
     u64* scratch = qsmem + QCHUNK + threadIdx.x;           // [12][QBLOCK] column of this thread (dense layer)
@@ -94,8 +97,9 @@ __global__ void __launch_bounds__(QBLOCK) quotient_kernel(const QuotParams p) {
     const u64 l0 = gl_mul_cc(gl_mul_cc(zh, p.n_inv), gl_inv(gl_sub(x, 1)));
     const uint64_t jn = bitrev_u64((i + (1u << p.rate_bits)) & (N - 1), p.bits);   // leaf of g_n * x
 
-    GlAcc2 tot[2];
-    for (uint32_t k = 0; k < p.num_challenges; k++) gl_acc2_init(tot[k], 0);
+    GlAcc2 tot[2];                      // indexed statically everywhere: a run-time index would park both in local memory
+    gl_acc2_init(tot[0], 0);
+    gl_acc2_init(tot[1], 0);
     const uint32_t nch = p.num_challenges;
     const u64* apow0 = p.apow;
     const u64* apow1 = p.apow + p.num_terms;
@@ -110,10 +114,13 @@ __global__ void __launch_bounds__(QBLOCK) quotient_kernel(const QuotParams p) {
     // loaded ONCE and used for all challenges.
     const uint32_t chunks = (p.num_routed + p.max_degree - 1) / p.max_degree;
     u64 prev[2] = {0, 0};
-    for (uint32_t k = 0; k < nch; k++) {
-        const u64 z = p.zpp[(uint64_t)k * N + j];
-        ADD_TERM(k, gl_mul_cc(l0, gl_sub(z, 1)));
-        prev[k] = z;
+#pragma unroll
+    for (uint32_t k = 0; k < 2; k++) {
+        if (k < nch) {
+            const u64 z = p.zpp[(uint64_t)k * N + j];
+            ADD_TERM(k, gl_mul_cc(l0, gl_sub(z, 1)));
+            prev[k] = z;
+        }
     }
     for (uint32_t c = 0; c < chunks; c++) {
         u64 num[2] = {1, 1}, den[2] = {1, 1};
@@ -250,8 +257,10 @@ __global__ void __launch_bounds__(QBLOCK) quotient_kernel(const QuotParams p) {
 #undef RLD
 #undef RST
     const u64 zi = p.zh_inv[coset];
-    if (live)
-        for (uint32_t k = 0; k < nch; k++) p.out[(uint64_t)k * N + j] = gl_canon(gl_mul_cc(gl_acc2_reduce(tot[k]), zi));
+    if (live) {
+        p.out[j] = gl_canon(gl_mul_cc(gl_acc2_reduce(tot[0]), zi));
+        if (nch > 1) p.out[N + j] = gl_canon(gl_mul_cc(gl_acc2_reduce(tot[1]), zi));
+    }
 #undef REG
 #undef ADD_TERM
 }
