@@ -193,7 +193,7 @@ def run_prove_block(a, vx, ctx, dist, rank, local_rank, G):
     untimed check only); everything timed goes through the C ABI.
       ms_per_proof : one prove_with_partition_witness from a pageable witness on one GPU (best of 3, rank 0);
       proofs_per_s : LocalProver.batch_prove (P2X/backend/prover/local.rs:34-48) -- every rank proves `prove_batch`
-                     independent inputs on its own GPU with two workers sharing one context; all proofs / max time."""
+                     independent inputs on its own GPU with four workers sharing one context (one per lane); all proofs / max time."""
     import torch
     from oracle import plonk, synth                      # inputs + untimed verification only
     from oracle.field import E2
@@ -201,7 +201,7 @@ def run_prove_block(a, vx, ctx, dist, rank, local_rank, G):
     bits = a.prove_bits
     circ, wires, pis = synth.build(bits, seed=11)
     spec = CircuitSpec(circ.d, [g.id() for g in circ.gates], circ.selector_index, circ.groups, circ.constants, circ.sigmas)
-    lp = LocalProver(devices=[local_rank], workers_per_device=2)
+    lp = LocalProver(devices=[local_rank], workers_per_device=4)
     lp.batch_prove(spec, [(wires, pis)] * 2)             # warm-up: circuit replica, pools, caches
     ms_single, verified = None, None
     if rank == 0:
@@ -234,7 +234,7 @@ def run_prove_block(a, vx, ctx, dist, rank, local_rank, G):
     return {"circuit": f"synthetic 2^{bits}-row circuit, standard_recursion_config, gates: " + ", ".join(sorted({g.id().split('{')[0].split('(')[0].split(' ')[0] for g in circ.gates})),
             "witness": "pageable host memory", "ms_per_proof": ms_single, "secs_per_proof": ms_single / 1e3,
             "proofs_per_s": G * a.prove_batch / float(tt.item()), "proofs_per_batch_per_gpu": a.prove_batch, "n_gpus": G,
-            "workers_per_gpu": 2, "verified_by_oracle_verifier": verified, "batch_identical": same,
+            "workers_per_gpu": 4, "verified_by_oracle_verifier": verified, "batch_identical": same,
             "note": "BASELINE configs 2-4 (header_range_256/512, rotate) need the Rust witness generator: not measured here"}
 
 
