@@ -107,8 +107,8 @@ GL_D u64 tw_pow(const TwiddleView& tw, u32 E) {
 //   inner(inv)  [q < 16][r < 16]  w_256^(+-r bitrev_4(q))                 between the two radix-16 groups of a pass
 // so that a twiddle costs one coalesced load and one multiplication (the two-level W tables cost two loads and two
 // multiplications per twiddle).  Shapes whose table would be too big fall back to the two-level tables.
-#define NTT_OUTER_MAX_LOG 20          // outer table: 8 * 2^log_M bytes (8 MB at 2^20)
-#define NTT_SCALE_MAX_LOG 23          // scale table: 8 * blk_count * n bytes (64 MB at 2^23 entries)
+#define NTT_OUTER_MAX_LOG 24          // outer table: 8 * 2^log_M bytes (128 MB at 2^24, next to >= 8.6 GB of data)
+#define NTT_SCALE_MAX_LOG 25          // scale table: 8 * blk_count * n bytes (256 MB at 2^25 entries)
 
 __global__ void outer_table_kernel(u64* __restrict__ tab, uint32_t log_M, TwiddleView tw) {
     const uint32_t low = log_M - 8;
@@ -146,8 +146,8 @@ static const u64* cache_find(vx_ctx* lane, uint64_t key) {
 }
 static int32_t cache_add(vx_ctx* lane, uint64_t key, size_t bytes, u64** out) {
     vx_ctx* ctx = lane->root;
-    // derived tables are bounded by the number of distinct shapes a process commits; drop everything past 1 GB
-    if (ctx->ntt_cache_bytes + bytes > (1ULL << 30)) {
+    // derived tables are bounded by the number of distinct shapes a process commits; drop everything past 2 GB
+    if (ctx->ntt_cache_bytes + bytes > (2ULL << 30)) {
         VX_CUDA(cudaDeviceSynchronize());
         for (auto& e : ctx->ntt_cache) cudaFree(e.p);
         ctx->ntt_cache.clear();
@@ -559,13 +559,47 @@ __global__ void bitrev_scale_kernel(const u64* __restrict__ in, u64* __restrict_
     dst[bitrev_u64(p, log_n)] = gl_canon(v);
 }
 
+// The same reorder through 32 x 32 shared-memory tiles (log_n >= 10): an index is (hi | mid | lo) with 5-bit hi and lo, its
+// reversal (rev lo | rev mid | rev hi).  A tile holds all (hi, lo) of one mid: rows are read with lo contiguous and written
+// with rev(hi) contiguous, so both sides move 256-byte runs.  The element-wise scatter above writes one 8-byte word per
+// 32-byte sector and, past a few MB per column, per TLB page: 59 ms of a 2^24 x 64 iNTT went there.
+__global__ void __launch_bounds__(256) bitrev_scale_tiled_kernel(const u64* __restrict__ in, u64* __restrict__ out,
+                                                                 uint32_t log_n, u64 scale) {
+    __shared__ u64 tile[32][33];
+    const uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
+    const uint32_t mid_bits = log_n - 10;
+    const uint32_t mid = blockIdx.x;
+    const uint32_t rmid = mid_bits ? (__brev(mid) >> (32 - mid_bits)) : 0;
+    const u64* src = in + ((uint64_t)blockIdx.y << log_n);
+    u64* dst = out + ((uint64_t)blockIdx.y << log_n);
+#pragma unroll
+    for (uint32_t hi = ty; hi < 32; hi += 8) tile[hi][tx] = src[((uint64_t)hi << (log_n - 5)) | ((uint64_t)mid << 5) | tx];
+    __syncthreads();
+    const uint32_t rb = __brev(tx) >> 27;                                  // hi = rev5(b), b = tx
+#pragma unroll
+    for (uint32_t a = ty; a < 32; a += 8) {
+        u64 v = tile[rb][__brev(a) >> 27];                                 // lo = rev5(a)
+        if (scale != 1) v = gl_mul(v, scale);
+        dst[((uint64_t)a << (log_n - 5)) | ((uint64_t)rmid << 5) | tx] = gl_canon(v);
+    }
+}
+static void launch_bitrev_scale(vx_ctx* ctx, const u64* in, u64* out, uint32_t c, uint32_t log_n, u64 scale) {
+    const uint64_t n = 1ULL << log_n;
+    if (log_n >= 10 && (n >> 10) < (1ULL << 31) && c <= 65535) {
+        dim3 grid((unsigned)(n >> 10), c);
+        bitrev_scale_tiled_kernel<<<grid, 256, 0, ctx->stream>>>(in, out, log_n, scale);
+    } else {
+        dim3 grid((unsigned)((n + 255) / 256), c);
+        bitrev_scale_kernel<<<grid, 256, 0, ctx->stream>>>(in, out, log_n, scale);
+    }
+    VX_LAUNCH_COUNT(ctx, 1);
+}
+
 int32_t intt_batch(vx_ctx* ctx, u64* work, u64* coeffs_out, uint32_t c, uint32_t log_n) {
     VX_CHECK(ntt_dif_inplace(ctx, work, c, log_n, true));
     uint64_t n = 1ULL << log_n;
     u64 ninv = gl_inv_host(n % GL_P);
-    dim3 grid((unsigned)((n + 255) / 256), c);
-    bitrev_scale_kernel<<<grid, 256, 0, ctx->stream>>>(work, coeffs_out, log_n, ninv);
-    VX_LAUNCH_COUNT(ctx, 1);
+    launch_bitrev_scale(ctx, work, coeffs_out, c, log_n, ninv);
     VX_CUDA(cudaGetLastError());
     return VX_OK;
 }
@@ -695,8 +729,7 @@ int32_t ntt_natural(vx_ctx* ctx, const u64* in, u64* out, uint32_t c, uint32_t l
     }
     VX_CHECK(ntt_dif_inplace(ctx, tmp.p, c, log_n, inverse));
     u64 scale = inverse ? gl_inv_host(n % GL_P) : 1;
-    bitrev_scale_kernel<<<grid, 256, 0, ctx->stream>>>(tmp.p, out, log_n, scale);
-    VX_LAUNCH_COUNT(ctx, 1);
+    launch_bitrev_scale(ctx, tmp.p, out, c, log_n, scale);
     if (inverse && coset) {
         coset_scale_kernel<<<grid, 256, 0, ctx->stream>>>(out, log_n, gl_inv_host(coset_shift));
         VX_LAUNCH_COUNT(ctx, 1);
