@@ -486,7 +486,7 @@ def main():
             pass
         pipes = None
         try:
-            with open(os.path.join(ROOT, "profiles", "r01_leaf_hash_pipes.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "r02_leaf_hash_pipes.json")) as f:
                 pipes = json.load(f)
         except Exception:
             pass
