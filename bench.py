@@ -202,7 +202,7 @@ def run_prove_block(a, vx, ctx, dist, rank, local_rank, G):
     circ, wires, pis = synth.build(bits, seed=11)
     spec = CircuitSpec(circ.d, [g.id() for g in circ.gates], circ.selector_index, circ.groups, circ.constants, circ.sigmas)
     lp = LocalProver(devices=[local_rank], workers_per_device=4)
-    lp.batch_prove(spec, [(wires, pis)] * 2)             # warm-up: circuit replica, pools, caches
+    lp.batch_prove(spec, [(wires, pis)] * 8)             # warm-up: circuit replica, every lane's pools and staging buffers
     ms_single, verified = None, None
     if rank == 0:
         runs = []

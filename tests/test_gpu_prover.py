@@ -191,3 +191,32 @@ def test_proof_bytes_match_committed_golden(ctx, gold):
     data = vx.proof_to_bytes(gp)
     assert len(data) == gold["proof_len"]
     assert hashlib.sha256(data).hexdigest() == gold["proof_sha256"]
+
+
+def test_concurrent_proofs_on_one_context_are_identical(ctx):
+    """Four threads prove the same input on ONE context (its four lanes) at the same time, several rounds: every proof must
+    be byte-identical to the single-threaded one.  Guards the stream-ordering rules between lanes: the FRI coefficients
+    re-allocated by a fold used to be freed on the stream they were allocated on (another lane's, idle) while the fold
+    kernel on this call's stream was still reading them -- 2 of 20 concurrent 2^16-row proofs came out with different
+    FRI caps (tools/repro_concurrent_proofs.py)."""
+    import threading
+    circ, wires, pis = synth.build(15, seed=5)      # big enough for the folds' kernels to outlast the host (2^12 hid the bug)
+    pc = vx.CircuitData(circ.d, [g.id() for g in circ.gates], circ.selector_index, circ.groups, circ.constants,
+                        circ.sigmas, ctx=ctx)
+    want = vx.proof_to_bytes(vx.prove(pc, wires, pis))
+    got, errs = [], []
+
+    def worker():
+        try:
+            for _ in range(6):
+                got.append(vx.proof_to_bytes(vx.prove(pc, wires, pis)))
+        except Exception as e:      # noqa: BLE001
+            errs.append(repr(e))
+    ts = [threading.Thread(target=worker) for _ in range(4)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    pc.close()
+    assert not errs, errs
+    assert len(got) == 24 and all(g == want for g in got), f"{sum(g != want for g in got)} of {len(got)} concurrent proofs differ"

@@ -24,7 +24,12 @@ bool vx_is_device_ptr(const void* p) {
 }
 
 int32_t DevBuf::alloc(size_t nbytes, cudaStream_t stream) {
-    release();
+    // Re-allocation of a long-lived buffer (vx_fri's coefficients / values between folds): the old block is freed on the
+    // stream of THIS call, i.e. after the kernels just queued there that still read it.  Freeing it on the stream it was
+    // allocated on -- another lane's, idle since that call returned -- would hand the block back to the pool while those
+    // kernels run (with one stream per context the two were the same stream).
+    if (p) cudaFreeAsync(p, stream);
+    p = nullptr;
     s = stream;
     bytes = nbytes;
     if (nbytes == 0) return VX_OK;
