@@ -252,7 +252,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-prove", action="store_true", help="skip the whole-proof block (second half of BASELINE's metric)")
     ap.add_argument("--prove-bits", type=int, default=16, help="rows (log2) of the synthetic circuit of the prove block")
-    ap.add_argument("--prove-batch", type=int, default=16, help="proofs per rank in the batch_prove throughput run")
+    ap.add_argument("--prove-batch", type=int, default=32, help="proofs per rank in the batch_prove throughput run")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: 'peer' = the library's own kernels over NVLink peer memory, 'nccl' = torch.distributed all-gather (A/B)")
     a = ap.parse_args()
