@@ -2,8 +2,6 @@
 #include "common.cuh"
 #include "poseidon_tables.h"
 
-#include <thread>
-
 // ------------------------------------------------------------------------------------------------ errors
 static thread_local char g_err[512] = "";
 
@@ -70,8 +68,6 @@ static void lane_destroy_streams(vx_ctx* l) {
     for (auto& e : l->copy_ev) if (e) cudaEventDestroy(e);
     for (auto& e : l->absorb_ev) if (e) cudaEventDestroy(e);
     if (l->copy_free) cudaEventDestroy(l->copy_free);
-    for (auto& e : l->stage_ev) if (e) cudaEventDestroy(e);
-    if (l->stage_pinned) cudaFreeHost(l->stage_pinned);
     for (cudaStream_t st : {l->stream, l->copy_stream, l->aux_stream})
         if (st) cudaStreamDestroy(st);
 }
@@ -273,49 +269,6 @@ static int mem_kind(const void* p) {
     if (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) return 0;
     return a.type == cudaMemoryTypeHost ? 1 : 2;
 }
-// Pageable host memory -> device through the lane's own staging ring.  cudaMemcpyAsync from pageable memory is a single
-// thread's memcpy into the driver's bounce buffer (~8 GB/s measured); here VX_STAGE_THREADS host threads each move their
-// share of the pieces (<= 1 MB) into page-locked slots of their own and queue the DMA behind them, so the staging memcpy
-// runs at several threads' bandwidth and overlaps the DMA of earlier pieces.
-static int32_t copy_columns_staged(vx_ctx* ctx, const ColSource& src, uint32_t c0, uint32_t c1, uint64_t n, u64* dst,
-                                   cudaStream_t st) {
-    if (!ctx->stage_pinned) {
-        VX_CUDA(cudaHostAlloc((void**)&ctx->stage_pinned, (size_t)VX_STAGE_THREADS * VX_STAGE_SLOTS * VX_STAGE_SLOT_BYTES,
-                              cudaHostAllocPortable));
-        for (auto& e : ctx->stage_ev) VX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    }
-    const size_t col_bytes = n * sizeof(u64);
-    const size_t pieces_per_col = (col_bytes + VX_STAGE_SLOT_BYTES - 1) / VX_STAGE_SLOT_BYTES;
-    const size_t total = (size_t)(c1 - c0) * pieces_per_col;
-    std::atomic<int> failed{0};
-    auto work = [&](int w) {
-        cudaSetDevice(ctx->device);
-        size_t k = 0;
-        for (size_t t = (size_t)w; t < total; t += VX_STAGE_THREADS, k++) {
-            const uint32_t j = c0 + (uint32_t)(t / pieces_per_col);
-            const size_t off = (t % pieces_per_col) * VX_STAGE_SLOT_BYTES;
-            const size_t bytes = col_bytes - off < VX_STAGE_SLOT_BYTES ? col_bytes - off : VX_STAGE_SLOT_BYTES;
-            const int slot = w * VX_STAGE_SLOTS + (int)(k % VX_STAGE_SLOTS);
-            unsigned char* buf = ctx->stage_pinned + (size_t)slot * VX_STAGE_SLOT_BYTES;
-            if (cudaEventSynchronize(ctx->stage_ev[slot]) != cudaSuccess) { failed = 1; return; }   // the slot's last DMA is done
-            memcpy(buf, (const unsigned char*)src.col(j, n) + off, bytes);
-            if (cudaMemcpyAsync((unsigned char*)(dst + (size_t)(j - c0) * n) + off, buf, bytes, cudaMemcpyHostToDevice, st) != cudaSuccess ||
-                cudaEventRecord(ctx->stage_ev[slot], st) != cudaSuccess) { failed = 1; return; }
-        }
-    };
-    std::thread helpers[VX_STAGE_THREADS - 1];
-    const int nh = total > 1 ? VX_STAGE_THREADS - 1 : 0;
-    for (int w = 0; w < nh; w++) helpers[w] = std::thread(work, w + 1);
-    work(0);
-    for (int w = 0; w < nh; w++) helpers[w].join();
-    if (nh == 0) for (int w = 1; w < VX_STAGE_THREADS; w++) work(w);      // a single piece: nothing to share (w >= total: no-op)
-    if (failed.load()) {
-        vx_set_error("staged host copy: %s", cudaGetErrorString(cudaGetLastError()));
-        return VX_ECUDA;
-    }
-    return VX_OK;
-}
-
 // copies columns [c0, c1) to dst (contiguous): one transfer for a flat source, one per column otherwise
 static int32_t copy_columns(const ColSource& src, uint32_t c0, uint32_t c1, uint64_t n, u64* dst, cudaMemcpyKind kind,
                             cudaStream_t st) {
@@ -364,13 +317,15 @@ static int32_t commit_run(vx_ctx* ctx, vx_batch* b, const ColSource& src, bool i
     const uint32_t groups = (c + 7) / 8;
     uint32_t bound[17] = {0};
     uint32_t nchunks_eff = nchunks;
-    // Pageable memory travels through the lane's staging ring (copy_columns_staged) at a fraction of the pinned rate: the
-    // ratio drops accordingly, chunks grow by it (not by 2) and, where the copy cannot hide at all (ratio < 1), stay equal
-    // in size.  Measured at 2^16 x 135, rate_bits 3 (ms per commit from 135 pageable columns; 9.87 resident, 10.21 pinned):
-    // driver path 10.96; staging ring with slowdown 7 / 3 / 2: 11.38 / 10.87 / 10.80.
+    // Pageable memory travels through the driver's staging buffers at roughly a seventh of the pinned rate (~8 GB/s measured
+    // against ~55): the ratio drops accordingly, chunks grow by it (not by 2) and, where the copy cannot hide at all
+    // (ratio < 1), stay equal in size.  Measured at 2^16 x 135, rate_bits 3: 10.96 ms per commit from 135 pageable columns
+    // (9.87 resident, 10.21 pinned).  A library-side staging ring filled by four host threads was measured too: 10.80 ms,
+    // but it competes with the caller's own threads for cores (batch_prove on two ranks: 76 -> 50 proofs/s) and is gone;
+    // callers that want PCIe rate register their Vecs (vx_host_register).
     if (stream) {
 #ifndef VX_PAGEABLE_SLOWDOWN
-#define VX_PAGEABLE_SLOWDOWN 2.0
+#define VX_PAGEABLE_SLOWDOWN 7.0
 #endif
         const double ratio = ((double)(1u << b->rate_bits) + 0.3) * (kind == 2 ? 1.0 / VX_PAGEABLE_SLOWDOWN : 1.0);
         const double grow = ratio >= 2.0 ? 2.0 : (ratio > 1.0 ? ratio : 1.0);
@@ -398,8 +353,7 @@ static int32_t commit_run(vx_ctx* ctx, vx_batch* b, const ColSource& src, bool i
         // duplicated into the work buffer on the device (the inverse transform runs in place)
         u64* land = keep ? keep + off : dst;
         if (nchunks > 1) {
-            if (kind == 2) VX_CHECK(copy_columns_staged(ctx, src, c0, c1, n, land, ctx->copy_stream));
-            else VX_CHECK(copy_columns(src, c0, c1, n, land, cudaMemcpyHostToDevice, ctx->copy_stream));
+            VX_CHECK(copy_columns(src, c0, c1, n, land, cudaMemcpyHostToDevice, ctx->copy_stream));
             VX_CUDA(cudaEventRecord(ctx->copy_ev[k], ctx->copy_stream));
             VX_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[k], 0));
         } else {

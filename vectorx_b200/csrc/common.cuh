@@ -58,10 +58,6 @@ struct vx_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr; // host->device staging of commit inputs, overlapped with the transforms
     cudaStream_t aux_stream = nullptr;  // producer side of a streamed sharded commit (iNTT + peer push of the own slice)
-    // pageable inputs: the lane's own page-locked staging ring (VX_STAGE_THREADS x VX_STAGE_SLOTS slots), filled by several
-    // host threads at once -- the driver's own pageable path is one thread's memcpy (api.cu copy_columns)
-    unsigned char* stage_pinned = nullptr;
-    cudaEvent_t stage_ev[16] = {};
     // streamed leaf hashing: one event pair per leaf_absorb launch of the most recent commit (their sum is the leaf-hash
     // time vx_ctx_phase_ms reports; the launches interleave with the transforms)
     static constexpr int VX_MAX_ABSORB = 64;
@@ -143,9 +139,6 @@ __host__ __device__ static inline uint64_t bitrev_u64(uint64_t x, unsigned bits)
 }
 
 #define VX_LANES 4
-#define VX_STAGE_THREADS 4
-#define VX_STAGE_SLOTS 4                    // per thread
-#define VX_STAGE_SLOT_BYTES (1u << 20)
 struct CtxGuard {       // one call at a time on THIS lane (used with the primary lane by the sharded commit, whose group
     std::lock_guard<std::mutex> lk;                                       // state lives on the primary lane's streams)
     explicit CtxGuard(vx_ctx* c) : lk(c->mu) { cudaSetDevice(c->device); }
