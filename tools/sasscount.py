@@ -8,7 +8,7 @@ fn = None; counts = collections.OrderedDict()
 for line in out.splitlines():
     m = re.search(r"Function : (\S+)", line)
     if m: fn = m.group(1); counts[fn] = collections.Counter(); continue
-    m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
+    m = re.match(r"\s+/\*[0-9a-f]{4,6}\*/\s+(@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
     if m and fn: counts[fn][m.group(2)] += 1
 for fn, c in counts.items():
     if sel not in fn: continue

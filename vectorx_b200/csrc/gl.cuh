@@ -83,6 +83,9 @@ GL_D u64 gl_reduce96(u64 lo, u32 hi) {
 // eps as an opaque run-time constant: with the literal 0xffffffff ptxas splits x*eps + t into IMAD.HI (4 issue cycles on
 // the FMA-heavy pipe) + IMAD.IADD; from a constant-bank operand it stays ONE IMAD.WIDE.U32 with carry-out.
 static __constant__ u32 c_gl_eps = 0xFFFFFFFFu;
+#ifndef GL_CARRY_MERGE
+#define GL_CARRY_MERGE 1
+#endif
 
 // x = x3*2^96 + x2*2^64 + x1*2^32 + x0  ->  some u64 representative of x mod p.
 //   t = x2*eps + (x1:x0)  (carry C),  t -= x3  (borrow B);  x = t + (C - B)*2^64 = t + (C - B)*eps  (mod p)
@@ -97,10 +100,17 @@ GL_D u64 gl_reduce128_cc(u32 x0, u32 x1, u32 x2, u32 x3) {
         ".reg .u32 t0, t1, w2, s;\n\t"
         "mad.lo.cc.u32 t0, %4, %6, %2;\n\t"
         "madc.hi.cc.u32 t1, %4, %6, %3;\n\t"
+#if GL_CARRY_MERGE
+        "addc.u32 w2, 0xffffffff, 0;\n\t"        // -1 + C
+        "sub.cc.u32 t0, t0, %5;\n\t"
+        "subc.cc.u32 t1, t1, 0;\n\t"
+        "addc.u32 w2, w2, 0;\n\t"                // + (1 - B): CC.CF after a subtraction is the hardware carry = no borrow
+#else
         "addc.u32 w2, 0, 0;\n\t"
         "sub.cc.u32 t0, t0, %5;\n\t"
         "subc.cc.u32 t1, t1, 0;\n\t"
         "subc.u32 w2, w2, 0;\n\t"                 // w2 = C - B in {-1, 0, 1}
+#endif
         "shr.s32 s, w2, 31;\n\t"
         "sub.cc.u32 %0, t0, w2;\n\t"              // t += w2*eps = (w2 << 32) - sext(w2)
         "subc.u32 t1, t1, s;\n\t"
@@ -108,6 +118,41 @@ GL_D u64 gl_reduce128_cc(u32 x0, u32 x1, u32 x2, u32 x3) {
         "}"
         : "=r"(r0), "=r"(r1)
         : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(c_gl_eps));
+    return pack64(r0, r1);
+}
+
+// x = hi*2^64 + (x1:x0), hi*eps + (x1:x0) < 2^65 - 2^33: the carry of the accumulating IMAD.WIDE is the only fix-up and
+// r + eps cannot carry again (r < 2^64 - 2^33 after a wrap).  4 instructions; the compare-and-select form of
+// gl_reduce96 costs 8 (two ISETP, a 64-bit add, two SEL).
+GL_D u64 gl_reduce96_cc(u32 x0, u32 x1, u32 hi) {
+    u32 r0, r1;
+    asm("{\n\t"
+        ".reg .u32 t0, t1, m;\n\t"
+        "mad.lo.cc.u32 t0, %4, %5, %2;\n\t"
+        "madc.hi.cc.u32 t1, %4, %5, %3;\n\t"
+        "addc.u32 m, 0, 0;\n\t"
+        "sub.cc.u32 %0, t0, m;\n\t"             // t += C eps = (C << 32) - C
+        "subc.u32 t1, t1, 0;\n\t"
+        "add.u32 %1, t1, m;\n\t"
+        "}"
+        : "=r"(r0), "=r"(r1)
+        : "r"(x0), "r"(x1), "r"(hi), "r"(c_gl_eps));
+    return pack64(r0, r1);
+}
+// a + b, b canonical (< p), on the carry flag: 5 instructions against 8 for the compare-and-select form
+GL_D u64 gl_add_canon_cc(u64 a, u64 b) {
+    u32 r0, r1;
+    asm("{\n\t"
+        ".reg .u32 s0, s1, m;\n\t"
+        "add.cc.u32 s0, %2, %4;\n\t"
+        "addc.cc.u32 s1, %3, %5;\n\t"
+        "addc.u32 m, 0, 0;\n\t"
+        "sub.cc.u32 %0, s0, m;\n\t"             // s += C eps: s < p - 1 after a wrap, cannot carry again
+        "subc.u32 s1, s1, 0;\n\t"
+        "add.u32 %1, s1, m;\n\t"
+        "}"
+        : "=r"(r0), "=r"(r1)
+        : "r"(lo32(a)), "r"(hi32(a)), "r"(lo32(b)), "r"(hi32(b)));
     return pack64(r0, r1);
 }
 
@@ -125,10 +170,17 @@ GL_D void gl_mul128_cc(u64 a, u64 b, u32& r0, u32& r1, u32& r2, u32& r3) {
         "mov.b64 {l3, h3}, p3;\n\t"
         "mad.lo.cc.u32 m0, %5, %6, l1;\n\t"       // (m2:m1:m0) = a1*b0 + a0*b1
         "madc.hi.cc.u32 m1, %5, %6, h1;\n\t"
+#if GL_CARRY_MERGE
+        "addc.u32 m2, h3, 0;\n\t"               // two addc into one register: ptxas emits ONE IADD3.X with two carry-ins
+        "add.cc.u32 %1, h0, m0;\n\t"
+        "addc.cc.u32 %2, l3, m1;\n\t"
+        "addc.u32 %3, m2, 0;\n\t"
+#else
         "addc.u32 m2, 0, 0;\n\t"
         "add.cc.u32 %1, h0, m0;\n\t"
         "addc.cc.u32 %2, l3, m1;\n\t"
         "addc.u32 %3, h3, m2;\n\t"
+#endif
         "}"
         : "=r"(r0), "=&r"(r1), "=&r"(r2), "=&r"(r3)
         : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
@@ -152,10 +204,17 @@ GL_D u64 gl_mul_add_cc(u64 a, u64 b, u64 c) {
         ".reg .u32 m0, m1, m2;\n\t"
         "mad.lo.cc.u32 m0, %3, %4, %5;\n\t"
         "madc.hi.cc.u32 m1, %3, %4, %6;\n\t"
+#if GL_CARRY_MERGE
+        "addc.u32 m2, %9, 0;\n\t"
+        "add.cc.u32 %0, %7, m0;\n\t"
+        "addc.cc.u32 %1, %8, m1;\n\t"
+        "addc.u32 %2, m2, 0;\n\t"
+#else
         "addc.u32 m2, 0, 0;\n\t"
         "add.cc.u32 %0, %7, m0;\n\t"
         "addc.cc.u32 %1, %8, m1;\n\t"
         "addc.u32 %2, %9, m2;\n\t"
+#endif
         "}"
         : "=&r"(r1), "=&r"(r2), "=&r"(r3)
         : "r"(a1), "r"(b0), "r"(lo32(p1)), "r"(hi32(p1)), "r"(hi32(p0)), "r"(lo32(p3)), "r"(hi32(p3)));
@@ -178,10 +237,17 @@ GL_D u64 gl_sqr_cc(u64 a) {
         "mov.b64 {l3, h3}, p3;\n\t"
         "mad.lo.cc.u32 m0, %4, %5, l1;\n\t"       // (m2:m1:m0) = 2 * a0*a1
         "madc.hi.cc.u32 m1, %4, %5, h1;\n\t"
+#if GL_CARRY_MERGE
+        "addc.u32 m2, h3, 0;\n\t"               // two addc into one register: ptxas emits ONE IADD3.X with two carry-ins
+        "add.cc.u32 %1, h0, m0;\n\t"
+        "addc.cc.u32 %2, l3, m1;\n\t"
+        "addc.u32 %3, m2, 0;\n\t"
+#else
         "addc.u32 m2, 0, 0;\n\t"
         "add.cc.u32 %1, h0, m0;\n\t"
         "addc.cc.u32 %2, l3, m1;\n\t"
         "addc.u32 %3, h3, m2;\n\t"
+#endif
         "}"
         : "=r"(r0), "=&r"(r1), "=&r"(r2), "=&r"(r3)
         : "r"(a0), "r"(a1));
@@ -259,6 +325,24 @@ GL_D void gl_acc_mad(GlAcc& t, u64 a, u64 b) {
         : "+r"(t.l0), "+r"(t.h0), "+r"(t.c0), "+r"(t.l1), "+r"(t.h1), "+r"(t.c1), "+r"(t.l2), "+r"(t.h2), "+r"(t.c2)
         : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
 }
+// First term onto an accumulator that holds only an initial value in its T0 column (gl_acc_init): products onto the empty
+// T1 / T2 columns cannot carry, which ptxas cannot know (it emits a carry-out predicate and a SEL for each).
+GL_D void gl_acc_mad_first(GlAcc& t, u64 a, u64 b) {
+    u32 a0 = lo32(a), a1 = hi32(a), b0 = lo32(b), b1 = hi32(b);
+    asm("{\n\t"
+        ".reg .u64 p1, p2;\n\t"
+        ".reg .u32 q0, q1;\n\t"
+        "mul.wide.u32 p1, %8, %11;\n\t"
+        "mul.wide.u32 p2, %9, %11;\n\t"
+        "mov.b64 {q0, q1}, p1;\n\t"
+        "mov.b64 {%6, %7}, p2;\n\t"
+        "mad.lo.cc.u32 %0, %8, %10, %0;\n\t"  "madc.hi.cc.u32 %1, %8, %10, %1;\n\t"  "addc.u32 %2, 0, 0;\n\t"
+        "mad.lo.cc.u32 %3, %9, %10, q0;\n\t"  "madc.hi.cc.u32 %4, %9, %10, q1;\n\t"  "addc.u32 %5, 0, 0;\n\t"
+        "}"
+        : "+r"(t.l0), "+r"(t.h0), "=r"(t.c0), "=r"(t.l1), "=r"(t.h1), "=r"(t.c1), "=r"(t.l2), "=r"(t.h2)
+        : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+    t.c2 = 0;
+}
 // small-constant term: a * k, k < 2^32
 GL_D void gl_acc_mad_small(GlAcc& t, u64 a, u32 k) {
     u32 a0 = lo32(a), a1 = hi32(a);
@@ -283,10 +367,17 @@ GL_D u64 gl_acc_reduce(const GlAcc& t) {
         "addc.u32 w4, w4, 0;\n\t"
         "mad.lo.cc.u32 t0, w2, %11, %2;\n\t"     // t = w2*eps + (w1:w0), carry C
         "madc.hi.cc.u32 t1, w2, %11, w1;\n\t"
+#if GL_CARRY_MERGE
+        "addc.u32 c, 0xffffffff, 0;\n\t"       // -1 + C
+        "sub.cc.u32 t0, t0, w3;\n\t"            // t -= (w4:w3): hardware carry = 1 - B
+        "subc.cc.u32 t1, t1, w4;\n\t"
+        "addc.u32 c, c, 0;\n\t"                 // c = C - B, both carries taken by ONE IADD3.X
+#else
         "addc.u32 c, 0, 0;\n\t"
         "sub.cc.u32 t0, t0, w3;\n\t"            // t -= (w4:w3), borrow B;  c = C - B
         "subc.cc.u32 t1, t1, w4;\n\t"
         "subc.u32 c, c, 0;\n\t"
+#endif
         "shr.s32 m, c, 31;\n\t"
         "sub.cc.u32 %0, t0, c;\n\t"             // t += c*eps
         "subc.u32 t1, t1, m;\n\t"

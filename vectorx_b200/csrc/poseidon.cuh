@@ -90,7 +90,7 @@ GL_D void poseidon_mds_add_freq(u64 s[12], const u32* __restrict__ kl) {
         // value = y0 + y1 2^22 + y2 2^44 (< 2^76)
         u64 t = mad_wide(y1[r], 1u << 22, (u64)y0[r]);
         u64 u = mad_wide(y2[r], 1u << 12, (u64)hi32(t));
-        s[r] = gl_reduce96(pack64(lo32(t), lo32(u)), hi32(u));
+        s[r] = gl_reduce96_cc(lo32(t), lo32(u), hi32(u));
     }
 }
 
@@ -125,7 +125,7 @@ GL_D void poseidon_partial_group(u64 s[12], const int r0, const u64* __restrict_
 #pragma unroll
     for (int j = 0; j < G; j++) {
         const int r = r0 + j;
-        x[j] = gl_add_canon(gl_pow7_cc(s[0]), pk[r]);
+        x[j] = gl_add_canon_cc(gl_pow7_cc(s[0]), pk[r]);
         GlAcc d;
         gl_acc_init(d, 0);
         gl_acc_mad_small(d, x[j], 25u);
@@ -139,8 +139,9 @@ GL_D void poseidon_partial_group(u64 s[12], const int r0, const u64* __restrict_
     for (int i = 1; i < 12; i++) {
         GlAcc u;
         gl_acc_init(u, s[i]);
+        gl_acc_mad_first(u, pw[11 * r0 + i - 1], x[0]);
 #pragma unroll
-        for (int j = 0; j < G; j++) gl_acc_mad(u, pw[11 * (r0 + j) + i - 1], x[j]);
+        for (int j = 1; j < G; j++) gl_acc_mad(u, pw[11 * (r0 + j) + i - 1], x[j]);
         s[i] = gl_acc_reduce(u);
     }
 }
@@ -168,7 +169,7 @@ template <int G = POSEIDON_GROUP, int STRIDE = POSEIDON_BLOCK>
 GL_D void poseidon_permute(u64 s[12], u64* __restrict__ scratch) {
     const u64* rc = c_pos.rc;
 #pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = gl_add_canon(s[i], rc[i]);
+    for (int i = 0; i < 12; i++) s[i] = gl_add_canon_cc(s[i], rc[i]);
 #pragma unroll 1
     for (int half = 0; half < 2; half++) {
         const int first = half ? 27 : 1;                    // constants of the round after each full round
@@ -182,7 +183,7 @@ GL_D void poseidon_permute(u64 s[12], u64* __restrict__ scratch) {
         if (half == 0) {
             poseidon_partial_rounds_grouped<G>(s);
 #pragma unroll
-            for (int i = 0; i < 12; i++) s[i] = gl_add_canon(s[i], rc[26 * 12 + i]);
+            for (int i = 0; i < 12; i++) s[i] = gl_add_canon_cc(s[i], rc[26 * 12 + i]);
         }
     }
 }
