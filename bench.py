@@ -200,7 +200,10 @@ def run_prove_block(a, vx, ctx, dist, rank, local_rank, G):
     from vectorx_b200.local_prover import CircuitSpec, LocalProver
     bits = a.prove_bits
     circ, wires, pis = synth.build(bits, seed=11)
-    spec = CircuitSpec(circ.d, [g.id() for g in circ.gates], circ.selector_index, circ.groups, circ.constants, circ.sigmas)
+    # compile_gates: the circuit's gate program is compiled once at load time (vx_quotient_compile, untimed like the
+    # circuit build itself); --no-compile-gates interprets the bytecode instead
+    spec = CircuitSpec(circ.d, [g.id() for g in circ.gates], circ.selector_index, circ.groups, circ.constants, circ.sigmas,
+                       compile_gates=not a.no_compile_gates)
     lp = LocalProver(devices=[local_rank], workers_per_device=4)
     lp.batch_prove(spec, [(wires, pis)] * 8)             # warm-up: circuit replica, every lane's pools and staging buffers
     ms_single, verified = None, None
@@ -235,6 +238,7 @@ def run_prove_block(a, vx, ctx, dist, rank, local_rank, G):
             "witness": "pageable host memory", "ms_per_proof": ms_single, "secs_per_proof": ms_single / 1e3,
             "proofs_per_s": G * a.prove_batch / float(tt.item()), "proofs_per_batch_per_gpu": a.prove_batch, "n_gpus": G,
             "workers_per_gpu": 4, "verified_by_oracle_verifier": verified, "batch_identical": same,
+            "gate_program": "compiled at circuit load (NVRTC, sm_100a)" if not a.no_compile_gates else "interpreted bytecode",
             "note": "BASELINE configs 2-4 (header_range_256/512, rotate) need the Rust witness generator: not measured here"}
 
 
@@ -251,6 +255,7 @@ def main():
     ap.add_argument("--cap-height", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-prove", action="store_true", help="skip the whole-proof block (second half of BASELINE's metric)")
+    ap.add_argument("--no-compile-gates", action="store_true", help="prove block: interpret the gate bytecode (no NVRTC)")
     ap.add_argument("--prove-bits", type=int, default=16, help="rows (log2) of the synthetic circuit of the prove block")
     ap.add_argument("--prove-batch", type=int, default=32, help="proofs per rank in the batch_prove throughput run")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],

@@ -233,6 +233,21 @@ int32_t vx_zs_partial_products(vx_ctx* ctx, const vx_circuit_desc* desc, const u
 int32_t vx_quotient(vx_ctx* ctx, const vx_circuit_desc* desc, vx_batch* constants_sigmas, vx_batch* wires,
                     vx_batch* zs_partial_products, const uint64_t pi_hash[4], const uint64_t* betas,
                     const uint64_t* gammas, const uint64_t* alphas, uint64_t* quotient_coeffs_out);
+/* Circuit-load-time specialisation of the gate constraints (the counterpart of the monomorphised
+ * Gate::eval_unfiltered_base_batch bodies a Rust build of plonky2 contains; a prover calls it once per circuit, next to
+ * CircuitBuilder::build -- contracts/lib/succinctx/plonky2x/core/src/frontend/builder/mod.rs:245): the gate bytecode is
+ * turned into straight-line CUDA and compiled for sm_100a with NVRTC (dlopen of libnvrtc.so.12, or VX_NVRTC_PATH).  From
+ * then on vx_quotient runs the compiled kernel for this program on this context's device; results are bit-identical to the
+ * interpreter's.  tuning: 0 = defaults; bits 0-7 minimum blocks per SM (register budget), bits 8-15 threads per block / 32,
+ * bits 16-27 bytecode operations per scheduling fence.  VX_EUNSUPPORTED when NVRTC is not available -- vx_quotient then
+ * keeps interpreting.  VX_QUOTIENT_JIT=0 in the environment disables the compiled path. */
+int32_t vx_quotient_compile(vx_ctx* ctx, const vx_circuit_desc* desc, uint32_t tuning);
+/* 1 if vx_quotient would run a compiled kernel for this circuit on this context, else 0 */
+int32_t vx_quotient_is_compiled(vx_ctx* ctx, const vx_circuit_desc* desc);
+/* The generated translation unit / its sm_100a cubin (no GPU needed: inspection and build checks).  Return the size of
+ * the full result in bytes (negative: error code) and copy at most cap bytes into buf (the source NUL-terminated). */
+int64_t vx_quotient_jit_source(const vx_circuit_desc* desc, char* buf, uint64_t cap);
+int64_t vx_quotient_jit_cubin(const vx_circuit_desc* desc, uint32_t tuning, char* buf, uint64_t cap);
 /* OpeningSet::new: every polynomial of the batch evaluated at an extension point; out: c x 2 */
 int32_t vx_batch_eval_ext(vx_batch* b, const uint64_t point[2], uint64_t* out);
 

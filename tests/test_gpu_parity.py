@@ -220,6 +220,22 @@ def test_commit_from_values_keep(ctx, c, log_n, src):
         vx.PolynomialBatch.from_values_keep(cols, cols.copy(), 3, 4, ctx=ctx)      # keep buffer must be device memory
 
 
+@pytest.mark.parametrize("c,log_n,rate,cap", [(40, 13, 3, 1), (85, 15, 1, 3), (33, 14, 2, 0)])
+def test_commit_device_resident_small_leaf_block(ctx, c, log_n, rate, cap):
+    """A device-resident commit of 2^16 wide leaves: the shape of one rank's block of an 8-way sharded commit, hashed as two
+    half-sponges per leaf block (leaf_hash_split_kernel, merkle.cu).  Digests, cap and leaves equal the oracle's."""
+    from vectorx_b200._lib import DeviceArray
+    cols = oracle.random_field((c, 1 << log_n), seed=1000 + c)
+    want = oracle.commit_from_values(cols, rate, cap)
+    dev = DeviceArray.from_host(ctx, cols)
+    b = vx.PolynomialBatch.from_values(dev, rate, False, cap, ctx=ctx)
+    assert np.array_equal(b.cap.hashes, want["cap"])
+    leaves, digests = b.download()
+    assert np.array_equal(leaves, want["leaves"]) and np.array_equal(digests, want["digests"])
+    b.close()
+    dev.close()
+
+
 def test_pinned_host_buffers(ctx):
     """vx_host_alloc / vx_host_register: a commit whose values come from page-locked memory equals the pageable one."""
     from vectorx_b200._lib import check, load

@@ -25,6 +25,11 @@ def test_prove_verifies_and_times(ctx):
     pc = vx.CircuitData(circ.d, [g.id() for g in circ.gates], circ.selector_index, circ.groups, circ.constants,
                         circ.sigmas, ctx=ctx)
     assert pc.circuit_digest == circ.circuit_digest
+    compile_s = None
+    if os.environ.get("VX_PROVE_COMPILE", "1") != "0":         # circuit-load-time compilation of the gate program (NVRTC)
+        t0 = time.perf_counter()
+        assert pc.compile_gates(int(os.environ.get("VX_JIT_MINB", "0")))
+        compile_s = time.perf_counter() - t0
     vx.prove(pc, wires, pis)                                   # warm-up (pools, twiddle caches)
     pinned = vx.pinned_empty(wires.shape)                      # the witness written straight into page-locked memory
     pinned[:] = wires
@@ -50,6 +55,8 @@ def test_prove_verifies_and_times(ctx):
            "witness": "pinned host memory (vx_host_alloc)", "prove_ms": total, "phase_ms": phases,
            "pageable_witness": {"prove_ms": total_pageable, "commit wires": phases_pageable.get("commit wires")},
            "circuit_build_s": build_s, "oracle_verify_s": verify_s,
+           "gates_compiled": pc.gates_compiled, "gate_compile_s": compile_s,
+           "jit_options": os.environ.get("VX_JIT_OPTS", "default (ptxas -O1)"), "jit_min_blocks": os.environ.get("VX_JIT_MINB", "default"),
            "gates": [g.id() for g in circ.gates]}
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "prove_timing.json"), "w") as f:

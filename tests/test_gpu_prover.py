@@ -2,6 +2,7 @@
 opening evaluation, FRI fold-and-commit, proof-of-work, and the whole proof -- each bit-for-bit against the
 oracle prover (oracle/plonk.py), and the GPU proof must verify under the oracle's independent verifier."""
 import ctypes
+import os
 
 import numpy as np
 import pytest
@@ -73,6 +74,44 @@ def test_quotient_polys(case, ctx, superops):
     for k in range(2):
         assert np.array_equal(q[k], tr["quotient_full"][k])
     assert np.array_equal(q.reshape(16, pc.n), tr["quotient_coeffs"])
+
+
+def _quotient(ctx, pc, wires, tr):
+    rate, cap = pc.rate_bits, pc.cap_height
+    wb = vx.PolynomialBatch.from_values(wires, rate, False, cap, ctx=ctx)
+    zb = vx.PolynomialBatch.from_values(tr["zpp"], rate, False, cap, ctx=ctx)
+    q = np.zeros((2, pc.n << rate), dtype=np.uint64)
+    u = lambda xs: np.array([int(x) for x in xs], dtype=np.uint64)
+    pi, betas, gammas, alphas = u(tr["pi_hash"]), u(tr["betas"]), u(tr["gammas"]), u(tr["alphas"])
+    check(load().vx_quotient(ctx.handle, ctypes.byref(pc.desc), pc.constants_sigmas_commitment.handle, wb.handle,
+                             zb.handle, ptr(pi), ptr(betas), ptr(gammas), ptr(alphas), ptr(q)), "vx_quotient")
+    wb.close(); zb.close()
+    return q
+
+
+def test_quotient_polys_compiled(case, ctx):
+    """The gate program compiled at circuit-load time (vx_quotient_compile: bytecode -> straight-line CUDA -> NVRTC ->
+    sm_100a) gives the oracle's quotient polynomials bit for bit, like the interpreter that ran in the test above.  From
+    here on every test of this process that proves a circuit with this gate set runs the compiled kernel."""
+    circ, wires, pis, proof, tr, pc = case
+    assert not load().vx_quotient_is_compiled(ctx.handle, ctypes.byref(pc.desc))
+    q_interpreted = _quotient(ctx, pc, wires, tr)
+    assert pc.compile_gates() and pc.gates_compiled
+    q = _quotient(ctx, pc, wires, tr)
+    assert np.array_equal(q, q_interpreted)
+    for k in range(2):
+        assert np.array_equal(q[k], tr["quotient_full"][k])
+    assert np.array_equal(q.reshape(16, pc.n), tr["quotient_coeffs"])
+
+
+@pytest.mark.skipif(not os.environ.get("VX_TEST_JIT_ALL"), reason="compiles all 19 gate programs (~75 s of NVRTC); set VX_TEST_JIT_ALL=1")
+def test_all_gate_kinds_compiled_proof_is_identical(ctx):
+    circ, wires, pis = synth.build(7, seed=7, mix=synth.ALL_KINDS)
+    pc = product_circuit(circ, ctx)
+    want = vx.proof_to_bytes(vx.prove(pc, wires, pis))
+    assert pc.compile_gates()
+    assert vx.proof_to_bytes(vx.prove(pc, wires, pis)) == want
+    pc.close()
 
 
 def test_opening_evaluation(case, ctx):

@@ -4,7 +4,7 @@
 cd "$(dirname "$0")/.."
 for tag in "" "$@"; do
   lib=vectorx_b200/libvectorx_b200${tag:+.$tag}.so
-  VX_B200_LIB=$PWD/$lib python bench.py --steps ${STEPS:-10} --warmup 3 --no-cpu-baseline ${BENCH_ARGS} 2>&1 | tail -1 | python -c "
+  VX_B200_LIB=$PWD/$lib python bench.py --steps ${STEPS:-10} --warmup 3 --no-cpu-baseline --no-prove ${BENCH_ARGS} 2>&1 | tail -1 | python -c "
 import json,sys
 d=json.loads(sys.stdin.read())
 p=d['roofline']['phase_ms']

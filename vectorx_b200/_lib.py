@@ -17,7 +17,7 @@ LIB_PATH = os.environ.get("VX_B200_LIB") or os.path.join(_HERE, "libvectorx_b200
 u64p = ctypes.POINTER(ctypes.c_uint64)
 u32p = ctypes.POINTER(ctypes.c_uint32)
 vp = ctypes.c_void_p
-c_u64, c_u32, c_i32 = ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int32
+c_u64, c_u32, c_i32, c_i64 = ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int32, ctypes.c_int64
 
 # name -> (restype, argtypes); must list every symbol declared in include/vectorx_b200.h
 SIGNATURES = {
@@ -83,6 +83,10 @@ SIGNATURES = {
     "vx_poseidon_fast_tables": (c_i32, [vp, vp, vp, vp, vp]),
     "vx_zs_partial_products": (c_i32, [vp, vp, vp, vp, vp, vp, vp]),
     "vx_quotient": (c_i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "vx_quotient_compile": (c_i32, [vp, vp, c_u32]),
+    "vx_quotient_is_compiled": (c_i32, [vp, vp]),
+    "vx_quotient_jit_source": (c_i64, [vp, vp, c_u64]),
+    "vx_quotient_jit_cubin": (c_i64, [vp, c_u32, vp, c_u64]),
     "vx_batch_eval_ext": (c_i32, [vp, vp, vp]),
     "vx_fri_begin": (c_i32, [vp, vp, c_u32, vp, c_u32, vp, ctypes.POINTER(vp)]),
     "vx_fri_commit_layer": (c_i32, [vp, c_u32, c_u32, vp]),

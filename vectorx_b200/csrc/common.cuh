@@ -12,6 +12,7 @@
 
 #include "../../include/vectorx_b200.h"
 #include "gl.cuh"
+#include "twiddle_view.cuh"
 
 // ---- error handling: never throw across the C ABI -----------------------------------------------
 void vx_set_error(const char* fmt, ...);
@@ -89,22 +90,6 @@ struct vx_ctx {
     cudaEvent_t ev[VX_NUM_PHASE_EVENTS] = {};
 };
 
-struct TwiddleView {     // passed by value to kernels
-    const u64* lo;       // W^(E & 0xffff)
-    const u64* hi;       // W^((E >> 16) << 16)
-    const u64* roots12;  // w_4096^e, e < 2048
-    const u64* full12;   // w_4096^e, e < 4096
-};
-
-// W^E for a 32-bit exponent (W of order 2^32): w_M^e = W^(e << (32 - log M))
-#ifdef __CUDACC__
-GL_D u64 tw_pow_view(const TwiddleView& tw, u32 E) {
-    u64 h = __ldg(tw.hi + (E >> 16));
-    u32 l = E & 0xffffu;
-    return l ? gl_mul_cc(h, __ldg(tw.lo + l)) : h;
-}
-#endif
-
 #define VX_LAUNCH_COUNT(ctx, n) (ctx)->launches.fetch_add((n), std::memory_order_relaxed)
 
 // classify a pointer: returns true if it is device memory
@@ -128,16 +113,6 @@ static inline unsigned ilog2(uint64_t x) {
     while ((1ULL << r) < x) r++;
     return r;
 }
-__host__ __device__ static inline uint64_t bitrev_u64(uint64_t x, unsigned bits) {
-#ifdef __CUDA_ARCH__
-    return bits ? (__brevll(x) >> (64 - bits)) : 0;
-#else
-    uint64_t r = 0;
-    for (unsigned i = 0; i < bits; i++) { r = (r << 1) | (x & 1); x >>= 1; }
-    return r;
-#endif
-}
-
 #define VX_LANES 4
 struct CtxGuard {       // one call at a time on THIS lane (used with the primary lane by the sharded commit, whose group
     std::lock_guard<std::mutex> lk;                                       // state lives on the primary lane's streams)
@@ -241,6 +216,8 @@ static inline int32_t merkle_build_hasher(vx_ctx* ctx, uint32_t hasher, const u6
 
 // ntt.cu ------------------------------------------------------------------------------------------
 int32_t ntt_module_init(vx_ctx* ctx);
+// quotient_jit.cu: the kernel compiled at run time for this circuit's gate program (cudaKernel_t as a launchable handle), or nullptr
+const void* quotient_jit_lookup(vx_ctx* ctx, const vx_circuit_desc* d, uint32_t* threads_per_block);
 int32_t prover_module_init(vx_ctx* ctx);                   // prover.cu: its own copy of the Poseidon tables
 int32_t fri_module_init(vx_ctx* ctx);                      // fri.cu: its own copy of the Poseidon tables
 void ntt_module_destroy(vx_ctx* ctx);

@@ -9,7 +9,9 @@
 // IMAD.WIDE.U32 (32x32+64 -> 64 on the FMA pipe) for products and IADD3/.X chains on the ALU pipe
 // for the reductions, keeping both pipes busy.
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cstdint>
+#endif
 
 typedef unsigned long long u64;
 typedef unsigned int u32;
@@ -462,6 +464,7 @@ GL_D u64 gl_pow7(u64 x) {
     return gl_mul(x3, x4);
 }
 
+#ifndef __CUDACC_RTC__          // host-side helpers (tables, setup): not part of run-time compiled kernels
 __host__ __device__ inline u64 gl_mul_slow(u64 a, u64 b) {     // host+device helper (tables, setup)
 #ifdef __CUDA_ARCH__
     return gl_canon(gl_mul(a, b));
@@ -493,6 +496,8 @@ inline u64 gl_root_of_unity_host(unsigned log_n) {
     for (unsigned i = log_n; i < 32; i++) r = gl_mul_slow(r, r);
     return r;
 }
+
+#endif
 
 GL_D u64 gl_pow(u64 a, u64 e) {
     u64 r = 1;

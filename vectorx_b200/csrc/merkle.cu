@@ -95,8 +95,13 @@ GL_D void store_digest(u64* dst, const u64 s[12]) {
 #ifndef LEAF_LONG_MINB
 #define LEAF_LONG_MINB 4
 #endif
-template <bool COL_MAJOR, bool LONG>
-__global__ void __launch_bounds__(LONG ? POSEIDON_BLOCK_LONG : POSEIDON_BLOCK, LONG ? LEAF_LONG_MINB : 1024 / POSEIDON_BLOCK)
+// SPARSE: the form for a leaf block that cannot fill the GPU anyway (a shard of an 8-way sharded commit: 2^16 leaves are 3.5
+// warps per SM sub-partition).  There the kernel waits on instruction latency, not on issue slots, and a 128-register
+// budget lets ptxas interleave more of the twelve independent S-box chains (1.17 -> 1.1x ms for 2^16 x 135,
+// profiles/r02_leaf_split_ab.log); with the GPU full the 64-register form wins on residency.
+template <bool COL_MAJOR, bool LONG, bool SPARSE = false>
+__global__ void __launch_bounds__(LONG ? POSEIDON_BLOCK_LONG : POSEIDON_BLOCK,
+                                  LONG ? LEAF_LONG_MINB : (SPARSE ? 512 : 1024) / POSEIDON_BLOCK)
 leaf_hash_kernel(const u64* __restrict__ leaves, uint64_t stride, uint64_t N, uint32_t c, uint32_t sub_bits,
                  u64* __restrict__ digests, u64* __restrict__ cap) {
     constexpr int BLOCK = LONG ? POSEIDON_BLOCK_LONG : POSEIDON_BLOCK;
@@ -315,6 +320,8 @@ int32_t merkle_build_device(vx_ctx* ctx, const u64* leaves, bool col_major, uint
     if (long_form)
         leaf_hash_kernel<true, true><<<(unsigned)(N / POSEIDON_BLOCK_LONG), POSEIDON_BLOCK_LONG, 0, ctx->stream>>>(
             leaves, stride, N, c, sub_bits, digests, cap);
+    else if (col_major && c >= 32 && (N + 31) / 32 <= 16ULL * (uint64_t)ctx->sm_count)       // <= 4 warps per sub-partition
+        leaf_hash_kernel<true, false, true><<<lp.blocks, lp.threads, 0, ctx->stream>>>(leaves, stride, N, c, sub_bits, digests, cap);
     else if (col_major)
         leaf_hash_kernel<true, false><<<lp.blocks, lp.threads, 0, ctx->stream>>>(leaves, stride, N, c, sub_bits, digests, cap);
     else

@@ -27,13 +27,19 @@
 
 // All tables (8.3 KB) live in constant memory and are only ever indexed warp-uniformly.  One copy per
 // translation unit that hashes; each is filled by poseidon_upload_constants() at context creation.
+#ifdef __CUDACC_RTC__
+extern "C" { __constant__ PoseidonTables c_pos; }      // run-time compiled modules: filled through cudaLibraryGetGlobal
+#else
 static __constant__ PoseidonTables c_pos;
+#endif
 
+#ifndef __CUDACC_RTC__
 static inline cudaError_t poseidon_upload_constants(const PoseidonTables& t, cudaStream_t stream) {
     cudaError_t e = cudaMemcpyToSymbolAsync(c_pos, &t, sizeof t, 0, cudaMemcpyHostToDevice, stream);
     if (e != cudaSuccess) return e;
     return cudaStreamSynchronize(stream);
 }
+#endif
 
 // ---- frequency-domain MDS layer --------------------------------------------------------------------------------
 // The circulant part y[r] = sum_i CIRC[i] x[(r+i) % 12] is a cyclic correlation over Z/12 = Z/4 x Z/3

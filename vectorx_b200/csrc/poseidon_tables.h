@@ -12,7 +12,9 @@
 //   M' = diag(1, A[1:,1:]) (commutes with lane-0 operations) and M'' sparse (first row/column).
 // The dense INIT is merged with the preceding full round's MDS layer: D = INIT*M, e = INIT*first.
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cstdint>
+#endif
 
 struct PoseidonTables {
     unsigned long long rc[31 * 12];        // RC[30][12] + one zero row
@@ -27,7 +29,9 @@ struct PoseidonTables {
     unsigned long long pc[22 * 22];
 };
 
+#ifndef __CUDACC_RTC__
 // fills t from the 360 round constants; returns false if a matrix was singular (never happens)
 bool poseidon_derive_tables(const unsigned long long rc360[360], PoseidonTables* t);
 // hybrid form: the first `naive` (0..21) partial rounds stay in the spec form; pk/pv/pw hold 22 - naive rounds
 bool poseidon_derive_tables_hybrid(const unsigned long long rc360[360], int naive, PoseidonTables* t);
+#endif

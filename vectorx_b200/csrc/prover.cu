@@ -12,9 +12,8 @@
 // [VX_PROGRAM_REGS][blockDim] shared-memory array; instruction words are warp-uniform loads.
 // Constraint terms are alpha-reduced with lazy 128-bit dot products (one reduction per challenge).
 #include "common.cuh"
-#include "poseidon.cuh"      // this TU's copy of the Poseidon tables: the interpreter's super-instructions run native layers
+#include "quotient_core.cuh" // with this TU's copy of the Poseidon tables: the interpreter's super-instructions run native layers
 
-#define QBLOCK 128           // == POSEIDON_BLOCK (the dense layer's scratch is sized for it)
 #define QCHUNK 1024          // program words staged in shared memory at a time; no instruction straddles a chunk
 
 int32_t prover_module_init(vx_ctx* ctx) {
@@ -25,26 +24,6 @@ int32_t prover_module_init(vx_ctx* ctx) {
     VX_CUDA(poseidon_upload_constants(t, ctx->stream));
     return VX_OK;
 }
-
-struct QuotParams {
-    const u64 *cs, *wires, *zpp;       // LDE column-major, leaf order, stride N
-    uint64_t N;
-    uint32_t bits, rate_bits, degree_bits;
-    uint32_t num_wires, num_routed, num_constants, num_selectors, num_challenges, num_pp, max_degree;
-    const u64* program;
-    uint32_t program_len;              // padded to a multiple of QCHUNK
-    uint32_t num_regs;                 // registers the program uses (shared-memory register file rows)
-    const u64* beta_k;                 // [challenge][routed]  beta_k * k_j
-    const u64* apow;                   // [challenge][num_terms] alpha_k^j
-    uint32_t num_terms, num_perm_terms;
-    u64 betas[4], gammas[4];
-    u64 pi_hash[4];
-    u64 zh_inv[64];                    // 1 / Z_H on the 2^rate_bits cosets of the subgroup
-    u64 zh[64];
-    u64 n_inv;
-    u64* out;                          // [challenge][N], leaf order
-    TwiddleView tw;
-};
 
 GL_D u64 lds_u64(uint32_t addr) {
     u64 v;
@@ -67,8 +46,8 @@ GL_D u64 ldg_u64(const u64* p) {
 #define QIMM_MASK 0x01ffffffu
 #define VX_OP_WAIT_INTERNAL 0xfe
 // column load: asynchronous 8-byte global -> shared copy straight into the register file (no stall until the run's WAIT)
-GL_D void cp_async_u64(uint32_t saddr, const u64* g) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(saddr), "l"(g) : "memory");
+GL_D void cp_async_u64(uint32_t saddr, const u64* g, u64 pol) {
+    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 8, %2;" ::"r"(saddr), "l"(g), "l"(pol) : "memory");
 }
 GL_D void cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 GL_D void sts_u64(uint32_t addr, u64 v) { asm volatile("st.shared.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory"); }
@@ -84,70 +63,12 @@ __global__ void __launch_bounds__(QBLOCK, QUOT_MINB) quotient_kernel(const QuotP
     u64* prog_s = qsmem;                                   // [QCHUNK]
     u64* scratch = qsmem + QCHUNK + threadIdx.x;           // [12][QBLOCK] column of this thread (dense layer)
     u64* R = qsmem + QCHUNK + 12 * QBLOCK + threadIdx.x;   // [num_regs][QBLOCK] register file column
-#define REG(i) R[(i) * QBLOCK]
-    const uint64_t j_raw = (uint64_t)blockIdx.x * QBLOCK + threadIdx.x;
-    const bool live = j_raw < p.N;
-    const uint64_t j = live ? j_raw : p.N - 1;             // idle threads shadow the last point (they take part in barriers)
-    const uint64_t N = p.N;
-    const uint32_t i = (uint32_t)bitrev_u64(j, p.bits);                 // natural LDE index
-    const u64 x = gl_mul_cc(GL_GENERATOR, tw_pow_view(p.tw, i << (32 - p.bits)));
-    const uint32_t coset = i & ((1u << p.rate_bits) - 1);
-    const u64 zh = p.zh[coset];
-    // L_0(x) = Z_H(x) / (n (x - 1))
-    const u64 l0 = gl_mul_cc(gl_mul_cc(zh, p.n_inv), gl_inv(gl_sub(x, 1)));
-    const uint64_t jn = bitrev_u64((i + (1u << p.rate_bits)) & (N - 1), p.bits);   // leaf of g_n * x
-
     GlAcc2 tot[2];                      // indexed statically everywhere: a run-time index would park both in local memory
-    gl_acc2_init(tot[0], 0);
-    gl_acc2_init(tot[1], 0);
+    const QuotPoint q = quot_prologue(p, tot);
+    const uint64_t j = q.j, N = p.N;
     const uint32_t nch = p.num_challenges;
     const u64* apow0 = p.apow;
     const u64* apow1 = p.apow + p.num_terms;
-#define ADD_TERM(idx, val)                                        \
-    do {                                                          \
-        u64 _v = (val);                                           \
-        gl_acc2_mad(tot[0], _v, __ldg(apow0 + (idx)));            \
-        if (nch > 1) gl_acc2_mad(tot[1], _v, __ldg(apow1 + (idx))); \
-    } while (0)
-
-    // ---- Z(1) = 1 and the permutation argument.  The chunk loop is outermost so that every routed wire and sigma value is
-    // loaded ONCE and used for all challenges.
-    const uint32_t chunks = (p.num_routed + p.max_degree - 1) / p.max_degree;
-    u64 prev[2] = {0, 0};
-#pragma unroll
-    for (uint32_t k = 0; k < 2; k++) {
-        if (k < nch) {
-            const u64 z = p.zpp[(uint64_t)k * N + j];
-            ADD_TERM(k, gl_mul_cc(l0, gl_sub(z, 1)));
-            prev[k] = z;
-        }
-    }
-    for (uint32_t c = 0; c < chunks; c++) {
-        u64 num[2] = {1, 1}, den[2] = {1, 1};
-        const uint32_t hi = min(p.num_routed, (c + 1) * p.max_degree);
-        for (uint32_t w = c * p.max_degree; w < hi; w++) {
-            const u64 wv = p.wires[(uint64_t)w * N + j];
-            const u64 sg = p.cs[(uint64_t)(p.num_constants + w) * N + j];
-#pragma unroll
-            for (uint32_t k = 0; k < 2; k++) {
-                if (k < nch) {
-                    const u64 a = gl_add(gl_mul_add_cc(x, __ldg(p.beta_k + k * p.num_routed + w), wv), p.gammas[k]);
-                    const u64 b = gl_add(gl_mul_add_cc(sg, p.betas[k], wv), p.gammas[k]);
-                    num[k] = gl_mul_cc(num[k], a);
-                    den[k] = gl_mul_cc(den[k], b);
-                }
-            }
-        }
-#pragma unroll
-        for (uint32_t k = 0; k < 2; k++) {
-            if (k < nch) {
-                const u64 next = (c + 1 < chunks) ? p.zpp[(uint64_t)(nch + k * p.num_pp + c) * N + j]
-                                                  : p.zpp[(uint64_t)k * N + jn];
-                ADD_TERM(nch + k * chunks + c, gl_sub(gl_mul_cc(prev[k], num[k]), gl_mul_cc(next, den[k])));
-                prev[k] = next;
-            }
-        }
-    }
 
     // ---- gate constraints: bytecode interpreter.  The program is the same for every thread: the block stages it through
     // shared memory QCHUNK words at a time, so an instruction fetch is a broadcast LDS instead of a dependent global load.
@@ -162,6 +83,7 @@ __global__ void __launch_bounds__(QBLOCK, QUOT_MINB) quotient_kernel(const QuotP
     const u64* wires_j = p.wires + j;
     const u64* cs_j = p.cs + j;
     uint64_t Nq = N;
+    const u64 pol_keep = quot_policy_keep();       // gate columns are read again by other gates: keep them in L2
     // opaque to the optimiser: held in registers instead of being recomputed from special registers per instruction
     asm volatile("" : "+l"(wires_j), "+l"(cs_j), "+r"(prog_sa), "+r"(reg_sa), "+l"(Nq));
 #define RLD(i) lds_u64(reg_sa + ((i) << 10))
@@ -180,7 +102,7 @@ __global__ void __launch_bounds__(QBLOCK, QUOT_MINB) quotient_kernel(const QuotP
             // immediate, tested one bit at a time in order of frequency (a switch compiles to a balanced tree instead)
             const uint32_t lo = (uint32_t)ins, hi = (uint32_t)(ins >> 32), imm = hi & QIMM_MASK;
             const uint32_t dst = (lo >> 8) & 0xff, ra = (lo >> 16) & 0xff, rb = lo >> 24;
-            if (hi & QF_LOADW) { cp_async_u64(reg_sa + (dst << 10), wires_j + (uint64_t)imm * Nq); continue; }
+            if (hi & QF_LOADW) { cp_async_u64(reg_sa + (dst << 10), wires_j + (uint64_t)imm * Nq, pol_keep); continue; }
             if (hi & QF_EMIT) {
                 const u64 v = RLD(ra);
                 gl_acc2_mad(h[0], v, __ldg(apow0 + cidx));
@@ -203,7 +125,7 @@ __global__ void __launch_bounds__(QBLOCK, QUOT_MINB) quotient_kernel(const QuotP
             if (op == VX_OP_END) { done = true; break; }
             switch (op) {
                 case VX_OP_SBOX7: RST(dst, gl_pow7_cc(RLD(ra))); break;
-                case VX_OP_LOADC: cp_async_u64(reg_sa + (dst << 10), cs_j + (uint64_t)imm * Nq); break;
+                case VX_OP_LOADC: cp_async_u64(reg_sa + (dst << 10), cs_j + (uint64_t)imm * Nq, pol_keep); break;
                 case VX_OP_LOADPI: RST(dst, p.pi_hash[imm & 3]); break;
                 case VX_OP_LOADK: RST(dst, lds_u64(pa)); pa += 8; break;
                 case VX_OP_ADD: RST(dst, gl_add(RLD(ra), RLD(rb))); break;
@@ -224,17 +146,7 @@ __global__ void __launch_bounds__(QBLOCK, QUOT_MINB) quotient_kernel(const QuotP
                     } else if (op == VX_OP_DENSE12) {
                         poseidon_dense_layer(st, scratch);
                     } else {
-                        const u64* v = c_pos.pv + 11 * imm;
-                        const u64* w = c_pos.pw + 11 * imm;
-                        const u64 x0 = gl_add_canon(st[0], c_pos.pk[imm]);
-                        GlAcc d;
-                        gl_acc_init(d, 0);
-                        gl_acc_mad_small(d, x0, 25u);
-#pragma unroll
-                        for (int k = 1; k < 12; k++) gl_acc_mad(d, v[k - 1], st[k]);
-#pragma unroll
-                        for (int k = 1; k < 12; k++) st[k] = gl_mul_add_cc(w[k - 1], x0, st[k]);
-                        st[0] = gl_acc_reduce(d);
+                        quot_partial12(st, imm);
                     }
 #pragma unroll
                     for (int k = 0; k < 12; k++) RST(QREGS12(d0, d1, k), st[k]);
@@ -256,13 +168,7 @@ __global__ void __launch_bounds__(QBLOCK, QUOT_MINB) quotient_kernel(const QuotP
     }
 #undef RLD
 #undef RST
-    const u64 zi = p.zh_inv[coset];
-    if (live) {
-        p.out[j] = gl_canon(gl_mul_cc(gl_acc2_reduce(tot[0]), zi));
-        if (nch > 1) p.out[N + j] = gl_canon(gl_mul_cc(gl_acc2_reduce(tot[1]), zi));
-    }
-#undef REG
-#undef ADD_TERM
+    quot_epilogue(p, q, tot);
 }
 
 // out[col][bitrev(p)] = in[col][p]
@@ -387,9 +293,16 @@ extern "C" int32_t vx_quotient(vx_ctx* ctx, const vx_circuit_desc* d, vx_batch* 
     p.n_inv = gl_inv_host(n % GL_P);
     p.out = d_q.p;
     p.tw.lo = ctx->w_lo; p.tw.hi = ctx->w_hi; p.tw.roots12 = ctx->roots12; p.tw.full12 = ctx->roots12f;
-    size_t smem = ((size_t)QCHUNK + (size_t)(12 + p.num_regs) * QBLOCK) * sizeof(u64);
-    VX_CUDA(cudaFuncSetAttribute(quotient_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    quotient_kernel<<<(unsigned)((N + QBLOCK - 1) / QBLOCK), QBLOCK, smem, ctx->stream>>>(p);
+    uint32_t jit_threads = QBLOCK;
+    if (const void* jit = quotient_jit_lookup(ctx, d, &jit_threads)) {
+        // the circuit's gate program compiled at load time (vx_quotient_compile): same arithmetic, no interpreter
+        void* args[] = {(void*)&p};
+        VX_CUDA(cudaLaunchKernel(jit, dim3((unsigned)((N + jit_threads - 1) / jit_threads)), dim3(jit_threads), args, 0, ctx->stream));
+    } else {
+        size_t smem = ((size_t)QCHUNK + (size_t)(12 + p.num_regs) * QBLOCK) * sizeof(u64);
+        VX_CUDA(cudaFuncSetAttribute(quotient_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        quotient_kernel<<<(unsigned)((N + QBLOCK - 1) / QBLOCK), QBLOCK, smem, ctx->stream>>>(p);
+    }
     VX_LAUNCH_COUNT(ctx, 1);
     VX_CUDA(cudaGetLastError());
     // leaf order -> natural order, then coset iNTT (transpose + coset_ifft(g) upstream)

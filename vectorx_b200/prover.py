@@ -49,7 +49,7 @@ class CircuitData:
                  num_routed_wires=80, rate_bits=3, cap_height=4, num_challenges=2, max_degree=8,
                  quotient_degree_factor=8, num_query_rounds=28, proof_of_work_bits=16, arity_bits=4,
                  final_poly_bits=5, ctx: Context | None = None, superops: bool = True,
-                 domain_separator=(), domain_separator_digest=None, circuit_digest=None):
+                 domain_separator=(), domain_separator_digest=None, circuit_digest=None, compile_gates: bool = False):
         # plonky2 keeps three independent parameters -- max_quotient_degree_factor (= max_degree here), the circuit's
         # quotient_degree_factor (chunk size of the permutation argument, number of quotient chunks) and 2^rate_bits (size
         # of the LDE the quotient is evaluated on).  The device path chunks by max_degree and reshapes the quotient as
@@ -94,6 +94,18 @@ class CircuitData:
                                   self.num_selectors, num_challenges, self.num_partial_products, max_degree,
                                   self.num_gate_constraints, self.k_is.ctypes.data, self.program.ctypes.data,
                                   len(self.program))
+
+        # circuit-load-time specialisation: the gate program compiled to a straight-line sm_100a kernel (NVRTC, tens of
+        # seconds once per circuit); vx_quotient then runs it instead of interpreting the bytecode.  Same results.
+        self.gates_compiled = False
+        if compile_gates:
+            self.compile_gates()
+
+    def compile_gates(self, tuning: int = 0) -> bool:
+        """tuning: 0 = defaults, else min blocks per SM | (threads per block / 32) << 8 | (operations per fence) << 16"""
+        check(load().vx_quotient_compile(self.ctx.handle, ctypes.byref(self.desc), tuning), "vx_quotient_compile")
+        self.gates_compiled = bool(load().vx_quotient_is_compiled(self.ctx.handle, ctypes.byref(self.desc)))
+        return self.gates_compiled
 
     def close(self):
         """Release the device-resident prover data (before the context it lives on is destroyed)."""
