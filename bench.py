@@ -491,7 +491,7 @@ def main():
             pass
         pipes = None
         try:
-            with open(os.path.join(ROOT, "profiles", "r02_leaf_hash_pipes.json")) as f:
+            with open(sorted(glob.glob(os.path.join(ROOT, "profiles", "r0*_leaf_hash_pipes.json")))[-1]) as f:
                 pipes = json.load(f)
         except Exception:
             pass

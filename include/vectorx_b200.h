@@ -242,6 +242,8 @@ int32_t vx_quotient(vx_ctx* ctx, const vx_circuit_desc* desc, vx_batch* constant
  * bits 16-27 bytecode operations per scheduling fence.  VX_EUNSUPPORTED when NVRTC is not available -- vx_quotient then
  * keeps interpreting.  VX_QUOTIENT_JIT=0 in the environment disables the compiled path. */
 int32_t vx_quotient_compile(vx_ctx* ctx, const vx_circuit_desc* desc, uint32_t tuning);
+/* forget the compiled kernel of this circuit on this context's device: vx_quotient interprets again */
+int32_t vx_quotient_discard(vx_ctx* ctx, const vx_circuit_desc* desc);
 /* 1 if vx_quotient would run a compiled kernel for this circuit on this context, else 0 */
 int32_t vx_quotient_is_compiled(vx_ctx* ctx, const vx_circuit_desc* desc);
 /* The generated translation unit / its sm_100a cubin (no GPU needed: inspection and build checks).  Return the size of

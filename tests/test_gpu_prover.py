@@ -58,6 +58,7 @@ def test_quotient_polys(case, ctx, superops):
     """compute_quotient_polys bit-for-bit, with the gate program in both forms: native Poseidon / RANGE4 / MADK
     super-instructions (default) and scalar field operations only."""
     circ, wires, pis, proof, tr, pc = case
+    check(load().vx_quotient_discard(ctx.handle, ctypes.byref(pc.desc)), "discard")     # this test is about the interpreter
     if not superops:
         pc = vx.CircuitData(circ.d, [g.id() for g in circ.gates], circ.selector_index, circ.groups, circ.constants,
                             circ.sigmas, ctx=ctx, superops=False)
@@ -94,6 +95,7 @@ def test_quotient_polys_compiled(case, ctx):
     sm_100a) gives the oracle's quotient polynomials bit for bit, like the interpreter that ran in the test above.  From
     here on every test of this process that proves a circuit with this gate set runs the compiled kernel."""
     circ, wires, pis, proof, tr, pc = case
+    check(load().vx_quotient_discard(ctx.handle, ctypes.byref(pc.desc)), "discard")     # an earlier test file may have compiled it
     assert not load().vx_quotient_is_compiled(ctx.handle, ctypes.byref(pc.desc))
     q_interpreted = _quotient(ctx, pc, wires, tr)
     assert pc.compile_gates() and pc.gates_compiled

@@ -19,7 +19,7 @@ for f in ("gpurun_out/${tag}_bench.json", "gpurun_out/${tag}_bench_reference.jso
         print(f, "FAILED", e, open(f).read()[-800:])
 PY
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${tag}_launches.csv \
-    python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/${tag}_ncu_list.log 2>&1
+    python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-prove > gpurun_out/${tag}_ncu_list.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:leaf_hash_kernel -s 4 -c 1 -o gpurun_out/${tag}_leaf -f \
-    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_ncu_full.log 2>&1
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-prove > gpurun_out/${tag}_ncu_full.log 2>&1
 ls -la gpurun_out | tail -12

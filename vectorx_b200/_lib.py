@@ -85,6 +85,7 @@ SIGNATURES = {
     "vx_quotient": (c_i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "vx_quotient_compile": (c_i32, [vp, vp, c_u32]),
     "vx_quotient_is_compiled": (c_i32, [vp, vp]),
+    "vx_quotient_discard": (c_i32, [vp, vp]),
     "vx_quotient_jit_source": (c_i64, [vp, vp, c_u64]),
     "vx_quotient_jit_cubin": (c_i64, [vp, c_u32, vp, c_u64]),
     "vx_batch_eval_ext": (c_i32, [vp, vp, vp]),

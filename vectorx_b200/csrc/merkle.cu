@@ -95,13 +95,8 @@ GL_D void store_digest(u64* dst, const u64 s[12]) {
 #ifndef LEAF_LONG_MINB
 #define LEAF_LONG_MINB 4
 #endif
-// SPARSE: the form for a leaf block that cannot fill the GPU anyway (a shard of an 8-way sharded commit: 2^16 leaves are 3.5
-// warps per SM sub-partition).  There the kernel waits on instruction latency, not on issue slots, and a 128-register
-// budget lets ptxas interleave more of the twelve independent S-box chains (1.17 -> 1.1x ms for 2^16 x 135,
-// profiles/r02_leaf_split_ab.log); with the GPU full the 64-register form wins on residency.
-template <bool COL_MAJOR, bool LONG, bool SPARSE = false>
-__global__ void __launch_bounds__(LONG ? POSEIDON_BLOCK_LONG : POSEIDON_BLOCK,
-                                  LONG ? LEAF_LONG_MINB : (SPARSE ? 512 : 1024) / POSEIDON_BLOCK)
+template <bool COL_MAJOR, bool LONG>
+__global__ void __launch_bounds__(LONG ? POSEIDON_BLOCK_LONG : POSEIDON_BLOCK, LONG ? LEAF_LONG_MINB : 1024 / POSEIDON_BLOCK)
 leaf_hash_kernel(const u64* __restrict__ leaves, uint64_t stride, uint64_t N, uint32_t c, uint32_t sub_bits,
                  u64* __restrict__ digests, u64* __restrict__ cap) {
     constexpr int BLOCK = LONG ? POSEIDON_BLOCK_LONG : POSEIDON_BLOCK;
@@ -296,7 +291,9 @@ __global__ void __launch_bounds__(1024) level_hash_fused_kernel(u64* __restrict_
 // Launch shape of the leaf kernels.  Few leaves (a shard of a sharded commit, the small oracles): 64- or 32-thread blocks
 // spread the warps evenly over the SMs (512 blocks of 128 on 148 SMs leave some SMs with 16 warps and others with 12).
 // Capping the residency at 28 or 24 warps per SM so that 2^19 leaves become 3.95 whole waves instead of 3.46 was measured
-// and does not pay (8.13 / 8.15 / 8.18 ms at 32 / 28 / 24 warps, profiles/r02_poseidon_ab.md).
+// and does not pay (8.13 / 8.15 / 8.18 ms at 32 / 28 / 24 warps, profiles/r02_poseidon_ab.md).  Neither do, for a shard's 2^16
+// leaves (3.5 warps per sub-partition), two half-sponges per leaf block drawn from a ticket counter (1.28 against 1.17 ms) or a
+// 128-register build of the kernel (1.17 ms either way): profiles/r02_leaf_split_ab.log.
 struct LeafPlan { unsigned threads, blocks; };
 static LeafPlan leaf_plan(vx_ctx* ctx, uint64_t N) {
     LeafPlan p;
@@ -320,8 +317,6 @@ int32_t merkle_build_device(vx_ctx* ctx, const u64* leaves, bool col_major, uint
     if (long_form)
         leaf_hash_kernel<true, true><<<(unsigned)(N / POSEIDON_BLOCK_LONG), POSEIDON_BLOCK_LONG, 0, ctx->stream>>>(
             leaves, stride, N, c, sub_bits, digests, cap);
-    else if (col_major && c >= 32 && (N + 31) / 32 <= 16ULL * (uint64_t)ctx->sm_count)       // <= 4 warps per sub-partition
-        leaf_hash_kernel<true, false, true><<<lp.blocks, lp.threads, 0, ctx->stream>>>(leaves, stride, N, c, sub_bits, digests, cap);
     else if (col_major)
         leaf_hash_kernel<true, false><<<lp.blocks, lp.threads, 0, ctx->stream>>>(leaves, stride, N, c, sub_bits, digests, cap);
     else

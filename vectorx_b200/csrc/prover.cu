@@ -212,6 +212,9 @@ extern "C" int32_t vx_quotient(vx_ctx* ctx, const vx_circuit_desc* d, vx_batch* 
     VX_CHECK(d_qnat.alloc((size_t)nch * N * 8, ctx->stream));
     VX_CUDA(cudaMemcpyAsync(d_apow.p, h_apow.data(), h_apow.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
     VX_CUDA(cudaMemcpyAsync(d_betak.p, h_betak.data(), h_betak.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    // the circuit's gate program compiled at load time (vx_quotient_compile), if there is one: nothing to stage then
+    uint32_t jit_threads = QBLOCK;
+    const void* jit = quotient_jit_lookup(ctx, d, &jit_threads);
     // re-lay the program so that no instruction straddles a QCHUNK boundary (pad with NOPs), find the register count
     std::vector<u64> prog;
     prog.reserve(d->program_len + 2 * QCHUNK);
@@ -224,7 +227,7 @@ extern "C" int32_t vx_quotient(vx_ctx* ctx, const vx_circuit_desc* d, vx_batch* 
             default: return 1;
         }
     };
-    for (uint64_t pc = 0; pc < d->program_len;) {
+    for (uint64_t pc = 0; pc < d->program_len && !jit;) {
         const u64 ins = d->program[pc];
         const uint32_t op = (uint32_t)ins & 0xff, len = oplen(op);
         VX_REQUIRE(op <= VX_OP_MADK && pc + len <= d->program_len, "vx_quotient: malformed program at word %llu",
@@ -265,8 +268,10 @@ extern "C" int32_t vx_quotient(vx_ctx* ctx, const vx_circuit_desc* d, vx_batch* 
     VX_REQUIRE(max_reg < VX_PROGRAM_REGS, "vx_quotient: program uses register %u (limit %d)", max_reg, VX_PROGRAM_REGS);
     prog.push_back(VX_OP_END);
     while (prog.size() % QCHUNK) prog.push_back(VX_OP_END);
-    VX_CHECK(d_prog.alloc(prog.size() * 8, ctx->stream));
-    VX_CUDA(cudaMemcpyAsync(d_prog.p, prog.data(), prog.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (!jit) {
+        VX_CHECK(d_prog.alloc(prog.size() * 8, ctx->stream));
+        VX_CUDA(cudaMemcpyAsync(d_prog.p, prog.data(), prog.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    }
 
     QuotParams p;
     memset(&p, 0, sizeof p);
@@ -293,9 +298,8 @@ extern "C" int32_t vx_quotient(vx_ctx* ctx, const vx_circuit_desc* d, vx_batch* 
     p.n_inv = gl_inv_host(n % GL_P);
     p.out = d_q.p;
     p.tw.lo = ctx->w_lo; p.tw.hi = ctx->w_hi; p.tw.roots12 = ctx->roots12; p.tw.full12 = ctx->roots12f;
-    uint32_t jit_threads = QBLOCK;
-    if (const void* jit = quotient_jit_lookup(ctx, d, &jit_threads)) {
-        // the circuit's gate program compiled at load time (vx_quotient_compile): same arithmetic, no interpreter
+    if (jit) {
+        // same arithmetic as the interpreter below, no decode
         void* args[] = {(void*)&p};
         VX_CUDA(cudaLaunchKernel(jit, dim3((unsigned)((N + jit_threads - 1) / jit_threads)), dim3(jit_threads), args, 0, ctx->stream));
     } else {
