@@ -206,6 +206,9 @@ def run_prove_block(a, vx, ctx, dist, rank, local_rank, G):
                        compile_gates=not a.no_compile_gates)
     lp = LocalProver(devices=[local_rank], workers_per_device=4)
     lp.batch_prove(spec, [(wires, pis)] * 8)             # warm-up: circuit replica, every lane's pools and staging buffers
+    bound = [c for r in lp._replicas if r is not None for c in r.bound.values()]
+    compiled = bool(bound) and all(getattr(c, "gates_compiled", False) for c in bound)
+    compile_err = next((c.gates_compile_error for c in bound if getattr(c, "gates_compile_error", None)), None)
     ms_single, verified = None, None
     if rank == 0:
         runs = []
@@ -238,7 +241,8 @@ def run_prove_block(a, vx, ctx, dist, rank, local_rank, G):
             "witness": "pageable host memory", "ms_per_proof": ms_single, "secs_per_proof": ms_single / 1e3,
             "proofs_per_s": G * a.prove_batch / float(tt.item()), "proofs_per_batch_per_gpu": a.prove_batch, "n_gpus": G,
             "workers_per_gpu": 4, "verified_by_oracle_verifier": verified, "batch_identical": same,
-            "gate_program": "compiled at circuit load (NVRTC, sm_100a)" if not a.no_compile_gates else "interpreted bytecode",
+            "gate_program": "compiled at circuit load (NVRTC, sm_100a)" if compiled else
+                            "interpreted bytecode" + (f" (compilation failed: {compile_err})" if compile_err else ""),
             "note": "BASELINE configs 2-4 (header_range_256/512, rotate) need the Rust witness generator: not measured here"}
 
 

@@ -1,7 +1,7 @@
 #!/bin/bash
 # usage: tools/scale.sh "8 4 2" [peer|nccl]   -- bench.py at the listed GPU counts, one summary line each
 for N in $1; do
-  timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 5 --exchange ${2:-peer} 2>&1 | tail -1 > gpurun_out/bench_g${N}_${2:-peer}.json
+  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 5 --exchange ${2:-peer} 2>&1 | tail -1 > gpurun_out/bench_g${N}_${2:-peer}.json
   python - <<PY
 import json
 try:

@@ -17,7 +17,7 @@ import time
 import numpy as np
 
 from . import gates as gate_lib
-from ._lib import Context, DeviceArray, check, default_context, load, ptr, vp
+from ._lib import Context, DeviceArray, VxError, check, default_context, load, ptr, vp
 from .challenger import Challenger, hash_no_pad_host, hash_pad_host
 from .plonky2 import PolynomialBatch
 
@@ -97,13 +97,19 @@ class CircuitData:
 
         # circuit-load-time specialisation: the gate program compiled to a straight-line sm_100a kernel (NVRTC, tens of
         # seconds once per circuit); vx_quotient then runs it instead of interpreting the bytecode.  Same results.
-        self.gates_compiled = False
+        self.gates_compiled, self.gates_compile_error = False, None
         if compile_gates:
-            self.compile_gates()
+            self.compile_gates(strict=False)
 
-    def compile_gates(self, tuning: int = 0) -> bool:
-        """tuning: 0 = defaults, else min blocks per SM | (threads per block / 32) << 8 | (operations per fence) << 16"""
-        check(load().vx_quotient_compile(self.ctx.handle, ctypes.byref(self.desc), tuning), "vx_quotient_compile")
+    def compile_gates(self, tuning: int = 0, strict: bool = True) -> bool:
+        """tuning: 0 = defaults, else min blocks per SM | (threads per block / 32) << 8 | (operations per fence) << 16.
+        strict=False: a box without NVRTC (or a failed compilation) leaves the circuit on the bytecode interpreter -- the
+        same GPU path it used before, not a fallback to the CPU -- and the reason in `gates_compile_error`."""
+        rc = load().vx_quotient_compile(self.ctx.handle, ctypes.byref(self.desc), tuning)
+        if rc != 0:
+            self.gates_compile_error = f"code {rc}: " + load().vx_last_error().decode("utf-8", "replace")
+            if strict:
+                raise VxError("vx_quotient_compile failed with " + self.gates_compile_error)
         self.gates_compiled = bool(load().vx_quotient_is_compiled(self.ctx.handle, ctypes.byref(self.desc)))
         return self.gates_compiled
 
