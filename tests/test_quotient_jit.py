@@ -54,6 +54,28 @@ def test_generated_source_mirrors_the_program():
     assert "A0(22)" in src and "A0(21)" not in src
 
 
+def test_every_gate_kind_has_a_translation():
+    """All 19 gate programs (every opcode of the bytecode) go through the generator; the statement counts follow the
+    program.  (Compiling this one takes ~75 s of NVRTC: it runs on the GPU under VX_TEST_JIT_ALL=1.)"""
+    d, prog, _keep, gate_ids = _desc(synth.ALL_KINDS)
+    assert len(gate_ids) == 19
+    src = _source(d)
+    ops = {v: k for k, v in gate_lib.OP.items()}
+    count, pc = {}, 0
+    while pc < len(prog):
+        op = ops[int(prog[pc]) & 0xff]
+        count[op] = count.get(op, 0) + 1
+        pc += 2 if op in ("LOADK", "ADDK", "MULK", "RSUBK", "SUBK", "MADK") else 5 if op in ("MDS12K", "DENSE12", "PARTIAL12") else 1
+    assert src.count("GlAcc2 h0, h1;") == count["BEGINGATE"] == 18              # NoopGate has no constraints
+    assert src.count("= gl_mul_cc(r") + src.count("y = gl_mul_cc(a, gl_sub(a, 3))") * 2 == \
+        count["MUL"] + count.get("MULK", 0) + 2 * count.get("RANGE4", 0)
+    assert src.count("gl_mul_add_cc(") == count["MADK"]
+    assert src.count("= gl_add(r") == count["ADD"] + count.get("ADDK", 0)
+    assert src.count("= gl_sub(") == count["SUB"] + count.get("SUBK", 0) + count.get("RSUBK", 0)
+    assert src.count("p.pi_hash[") == count["LOADPI"] == 4
+    assert src.count("VX_FENCE(") >= sum(count.values()) // 16
+
+
 def test_malformed_programs_are_rejected():
     d, prog, _keep, _ = _desc(("arith",))
     bad = prog.copy()

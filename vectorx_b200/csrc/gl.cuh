@@ -85,9 +85,6 @@ GL_D u64 gl_reduce96(u64 lo, u32 hi) {
 // eps as an opaque run-time constant: with the literal 0xffffffff ptxas splits x*eps + t into IMAD.HI (4 issue cycles on
 // the FMA-heavy pipe) + IMAD.IADD; from a constant-bank operand it stays ONE IMAD.WIDE.U32 with carry-out.
 static __constant__ u32 c_gl_eps = 0xFFFFFFFFu;
-#ifndef GL_CARRY_MERGE
-#define GL_CARRY_MERGE 1
-#endif
 
 // x = x3*2^96 + x2*2^64 + x1*2^32 + x0  ->  some u64 representative of x mod p.
 //   t = x2*eps + (x1:x0)  (carry C),  t -= x3  (borrow B);  x = t + (C - B)*2^64 = t + (C - B)*eps  (mod p)
@@ -102,17 +99,10 @@ GL_D u64 gl_reduce128_cc(u32 x0, u32 x1, u32 x2, u32 x3) {
         ".reg .u32 t0, t1, w2, s;\n\t"
         "mad.lo.cc.u32 t0, %4, %6, %2;\n\t"
         "madc.hi.cc.u32 t1, %4, %6, %3;\n\t"
-#if GL_CARRY_MERGE
         "addc.u32 w2, 0xffffffff, 0;\n\t"        // -1 + C
         "sub.cc.u32 t0, t0, %5;\n\t"
         "subc.cc.u32 t1, t1, 0;\n\t"
         "addc.u32 w2, w2, 0;\n\t"                // + (1 - B): CC.CF after a subtraction is the hardware carry = no borrow
-#else
-        "addc.u32 w2, 0, 0;\n\t"
-        "sub.cc.u32 t0, t0, %5;\n\t"
-        "subc.cc.u32 t1, t1, 0;\n\t"
-        "subc.u32 w2, w2, 0;\n\t"                 // w2 = C - B in {-1, 0, 1}
-#endif
         "shr.s32 s, w2, 31;\n\t"
         "sub.cc.u32 %0, t0, w2;\n\t"              // t += w2*eps = (w2 << 32) - sext(w2)
         "subc.u32 t1, t1, s;\n\t"
@@ -172,17 +162,10 @@ GL_D void gl_mul128_cc(u64 a, u64 b, u32& r0, u32& r1, u32& r2, u32& r3) {
         "mov.b64 {l3, h3}, p3;\n\t"
         "mad.lo.cc.u32 m0, %5, %6, l1;\n\t"       // (m2:m1:m0) = a1*b0 + a0*b1
         "madc.hi.cc.u32 m1, %5, %6, h1;\n\t"
-#if GL_CARRY_MERGE
         "addc.u32 m2, h3, 0;\n\t"               // two addc into one register: ptxas emits ONE IADD3.X with two carry-ins
         "add.cc.u32 %1, h0, m0;\n\t"
         "addc.cc.u32 %2, l3, m1;\n\t"
         "addc.u32 %3, m2, 0;\n\t"
-#else
-        "addc.u32 m2, 0, 0;\n\t"
-        "add.cc.u32 %1, h0, m0;\n\t"
-        "addc.cc.u32 %2, l3, m1;\n\t"
-        "addc.u32 %3, h3, m2;\n\t"
-#endif
         "}"
         : "=r"(r0), "=&r"(r1), "=&r"(r2), "=&r"(r3)
         : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
@@ -206,17 +189,10 @@ GL_D u64 gl_mul_add_cc(u64 a, u64 b, u64 c) {
         ".reg .u32 m0, m1, m2;\n\t"
         "mad.lo.cc.u32 m0, %3, %4, %5;\n\t"
         "madc.hi.cc.u32 m1, %3, %4, %6;\n\t"
-#if GL_CARRY_MERGE
         "addc.u32 m2, %9, 0;\n\t"
         "add.cc.u32 %0, %7, m0;\n\t"
         "addc.cc.u32 %1, %8, m1;\n\t"
         "addc.u32 %2, m2, 0;\n\t"
-#else
-        "addc.u32 m2, 0, 0;\n\t"
-        "add.cc.u32 %0, %7, m0;\n\t"
-        "addc.cc.u32 %1, %8, m1;\n\t"
-        "addc.u32 %2, %9, m2;\n\t"
-#endif
         "}"
         : "=&r"(r1), "=&r"(r2), "=&r"(r3)
         : "r"(a1), "r"(b0), "r"(lo32(p1)), "r"(hi32(p1)), "r"(hi32(p0)), "r"(lo32(p3)), "r"(hi32(p3)));
@@ -239,17 +215,10 @@ GL_D u64 gl_sqr_cc(u64 a) {
         "mov.b64 {l3, h3}, p3;\n\t"
         "mad.lo.cc.u32 m0, %4, %5, l1;\n\t"       // (m2:m1:m0) = 2 * a0*a1
         "madc.hi.cc.u32 m1, %4, %5, h1;\n\t"
-#if GL_CARRY_MERGE
         "addc.u32 m2, h3, 0;\n\t"               // two addc into one register: ptxas emits ONE IADD3.X with two carry-ins
         "add.cc.u32 %1, h0, m0;\n\t"
         "addc.cc.u32 %2, l3, m1;\n\t"
         "addc.u32 %3, m2, 0;\n\t"
-#else
-        "addc.u32 m2, 0, 0;\n\t"
-        "add.cc.u32 %1, h0, m0;\n\t"
-        "addc.cc.u32 %2, l3, m1;\n\t"
-        "addc.u32 %3, h3, m2;\n\t"
-#endif
         "}"
         : "=r"(r0), "=&r"(r1), "=&r"(r2), "=&r"(r3)
         : "r"(a0), "r"(a1));
@@ -369,17 +338,10 @@ GL_D u64 gl_acc_reduce(const GlAcc& t) {
         "addc.u32 w4, w4, 0;\n\t"
         "mad.lo.cc.u32 t0, w2, %11, %2;\n\t"     // t = w2*eps + (w1:w0), carry C
         "madc.hi.cc.u32 t1, w2, %11, w1;\n\t"
-#if GL_CARRY_MERGE
         "addc.u32 c, 0xffffffff, 0;\n\t"       // -1 + C
         "sub.cc.u32 t0, t0, w3;\n\t"            // t -= (w4:w3): hardware carry = 1 - B
         "subc.cc.u32 t1, t1, w4;\n\t"
         "addc.u32 c, c, 0;\n\t"                 // c = C - B, both carries taken by ONE IADD3.X
-#else
-        "addc.u32 c, 0, 0;\n\t"
-        "sub.cc.u32 t0, t0, w3;\n\t"            // t -= (w4:w3), borrow B;  c = C - B
-        "subc.cc.u32 t1, t1, w4;\n\t"
-        "subc.u32 c, c, 0;\n\t"
-#endif
         "shr.s32 m, c, 31;\n\t"
         "sub.cc.u32 %0, t0, c;\n\t"             // t += c*eps
         "subc.u32 t1, t1, m;\n\t"
