@@ -90,7 +90,9 @@ static __constant__ u32 c_gl_eps = 0xFFFFFFFFu;
 //   t = x2*eps + (x1:x0)  (carry C),  t -= x3  (borrow B);  x = t + (C - B)*2^64 = t + (C - B)*eps  (mod p)
 // and t + (C - B)*eps always lands in [0, 2^64): C = 1 needs t <= 2^64 - 2^33 + 1, B = 1 (x3 < 2^32) needs
 // t >= 2^64 - 2^32 + 1, so the single signed fix-up can neither overflow nor underflow.
-// x2*eps + (x1:x0) is ONE accumulating IMAD.WIDE.U32 with carry-out (1 FMA-heavy + 9 ALU instructions).  Measured and
+// x2*eps + (x1:x0) is ONE accumulating IMAD.WIDE.U32 with carry-out (1 FMA-heavy + 7 ALU instructions: C - B comes out of
+// ONE IADD3.X -- `addc w2, -1, 0` after the multiply-add and `addc w2, w2, 0` after the subtraction, whose CC.CF is the hardware
+// carry = 1 - B, are two carries into the same register, which ptxas fuses).  Measured and
 // rejected (profiles/r01*, profiles/r02_poseidon_ab.md): x2*eps = (x2 << 32) - x2 on the ALU pipe (12 ALU instructions, leaf
 // hashing 9.56 vs 8.64 ms), and the two fix-ups as predicated +-eps adds (ptxas materialises the predicates: more code).
 GL_D u64 gl_reduce128_cc(u32 x0, u32 x1, u32 x2, u32 x3) {
