@@ -205,7 +205,11 @@ __global__ void __launch_bounds__(POSEIDON_BLOCK) level_hash_kernel(u64* __restr
 // (< 12) owns state element i, the S-box layer runs in parallel and the MDS layer gathers the 12 elements with warp
 // shuffles (spec round structure: add constants, x^7, MDS; partial rounds apply x^7 on lane 0 only).  ~5x lower latency,
 // ~3x more thread-instructions: used (inside level_hash_fused_kernel) only while a level has at most VX_COOP_MAX_PAIRS pairs.
+// (8192 / 16384 measured: interior levels of 2^19 leaves 0.667 -> 0.691 / 0.751 ms, of a shard's 2^16 leaves 0.390 -> 0.337 /
+// 0.361 ms -- profiles/r02_coop_threshold_ab.log; 4096 kept)
+#ifndef VX_COOP_MAX_PAIRS
 #define VX_COOP_MAX_PAIRS 4096
+#endif
 
 // The cooperative permutation: lane (of a 16-lane group) el < 12 holds state element el; returns the permuted element.
 // `s` enters WITHOUT the first round's constants.
@@ -241,7 +245,7 @@ GL_D u64 poseidon_coop_permute(u64 s, const uint32_t lane, const uint32_t el, co
         ah += bh;
         u64 l = al + ((u64)lo32(ah) << 32);
         u32 c = l < al;
-        s = gl_reduce96(l, hi32(ah) + c);
+        s = gl_reduce96_cc(lo32(l), hi32(l), hi32(ah) + c);
     }
     return s;
 }
